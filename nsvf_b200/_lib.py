@@ -1,0 +1,72 @@
+"""ctypes binding of libnsvf_b200.so (C ABI declared in include/nsvf_b200.h).
+
+There is no CPU fallback anywhere in this package: if the shared library is missing the import of
+any operator fails loudly, and every operator rejects non-CUDA tensors.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libnsvf_b200.so")
+
+c_int, c_ll, c_float, c_size_t, c_void_p = (ctypes.c_int, ctypes.c_longlong, ctypes.c_float,
+                                            ctypes.c_size_t, ctypes.c_void_p)
+
+# name -> (restype, argtypes); must list every symbol of include/nsvf_b200.h (tests check this)
+SIGNATURES = {
+    "nsvf_version": (c_int, []),
+    "nsvf_last_error": (ctypes.c_char_p, []),
+    "nsvf_ref_rcp": (c_int, [c_void_p, c_ll, c_void_p, c_void_p]),
+    "nsvf_aabb_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "nsvf_aabb_intersect": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p,
+                                    c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
+    "nsvf_svo_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "nsvf_svo_intersect": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
+    "nsvf_inverse_cdf_sampling": (c_int, [c_void_p, c_int, c_int, c_ll, c_int, c_int, c_int, c_float,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p]),
+    "nsvf_uniform_ray_sampling": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float] + [c_void_p] * 7),
+    "nsvf_octree_build": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p]),
+    "nsvf_octree_flatten": (c_int, [c_void_p, c_void_p, c_ll]),
+    "nsvf_trilinear_embed_fwd": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_float, c_void_p]),
+    "nsvf_trilinear_embed_bwd": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_float, c_void_p, c_void_p, c_void_p]),
+    "nsvf_composite_fwd": (c_int, [c_void_p, c_ll, c_int] + [c_void_p] * 7),
+    "nsvf_composite_bwd": (c_int, [c_void_p, c_ll, c_int] + [c_void_p] * 9),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once. Raises ImportError (never falls back) when it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "nsvf_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C nsvf_b200/csrc`. There is no CPU / PyTorch fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("nsvf_b200: " + load().nsvf_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """Device (or host) pointer of a tensor, None -> NULL."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream(device):
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream

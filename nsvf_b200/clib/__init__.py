@@ -1,0 +1,184 @@
+"""Level-2 boundary: the callables of the reference's `fairnr/clib/__init__.py` (same names, argument
+order and results), running on the sm_100a kernels.
+
+    aabb_ray_intersect(voxelsize, n_max, points, ray_start, ray_dir)              clib/__init__.py:58-95
+    svo_ray_intersect(voxelsize, n_max, points, children, ray_start, ray_dir)     :98-135
+    uniform_ray_sampling(pts_idx, min_depth, max_depth, step_size, max_ray_length, deterministic)  :178-228
+    inverse_cdf_sampling(pts_idx, min_depth, max_depth, probs, steps, fixed_step_size, deterministic)  :231-300
+
+What is NOT carried over from the reference wrappers (results are unchanged, see tests/test_clib_gpu.py):
+  * the voxel set / octree is never replicated G <= 2048 times (`points.expand(S*G, ...).contiguous()`,
+    up to 8 GB) and rays are not padded and re-tiled: our kernels take [S, N, 3] rays directly;
+  * the inverse-CDF wrapper's padding rows (copies of ray 0), its 800-column chunk loop with six
+    .contiguous() slices per chunk, and the full-tensor `ne(-1).sum(-1).max()` reduction are folded
+    into one kernel launch (`valid_rays`, `ray_chunk`, `max_count` of nsvf_inverse_cdf_sampling);
+    with `deterministic=True` the constant 0.5 noise tensor is not materialised at all.
+  * RNG contract kept: non-deterministic noise is drawn exactly like the reference does
+    (`new_zeros(G, H/G, max_steps).uniform_().clamp(0.001, 0.999)`), so a seeded run reproduces the
+    reference's samples.
+All outputs are marked non-differentiable and backward returns None, as in the reference.
+"""
+import numpy as np
+import torch
+from torch.autograd import Function
+
+from .. import _lib
+from . import _ext
+
+MAX_DEPTH = 10000.0
+_L = _lib.load()
+_p = _lib.ptr
+
+
+class AABBRayIntersect(Function):
+    @staticmethod
+    def forward(ctx, voxelsize, n_max, points, ray_start, ray_dir):
+        inds, min_depth, max_depth = _ext.aabb_intersect(
+            ray_start.float().contiguous(), ray_dir.float().contiguous(), points.float().contiguous(),
+            voxelsize, n_max)
+        min_depth = min_depth.type_as(ray_start)
+        max_depth = max_depth.type_as(ray_start)
+        ctx.mark_non_differentiable(inds)
+        ctx.mark_non_differentiable(min_depth)
+        ctx.mark_non_differentiable(max_depth)
+        return inds, min_depth, max_depth
+
+    @staticmethod
+    def backward(ctx, a, b, c):
+        return None, None, None, None, None
+
+
+aabb_ray_intersect = AABBRayIntersect.apply
+
+
+class SparseVoxelOctreeRayIntersect(Function):
+    @staticmethod
+    def forward(ctx, voxelsize, n_max, points, children, ray_start, ray_dir):
+        inds, min_depth, max_depth = _ext.svo_intersect(
+            ray_start.float().contiguous(), ray_dir.float().contiguous(), points.float().contiguous(),
+            children.int().contiguous(), voxelsize, n_max)
+        min_depth = min_depth.type_as(ray_start)
+        max_depth = max_depth.type_as(ray_start)
+        ctx.mark_non_differentiable(inds)
+        ctx.mark_non_differentiable(min_depth)
+        ctx.mark_non_differentiable(max_depth)
+        return inds, min_depth, max_depth
+
+    @staticmethod
+    def backward(ctx, a, b, c):
+        return None, None, None, None, None, None
+
+
+svo_ray_intersect = SparseVoxelOctreeRayIntersect.apply
+
+
+class UniformRaySampling(Function):
+    @staticmethod
+    def forward(ctx, pts_idx, min_depth, max_depth, step_size, max_ray_length, deterministic=False):
+        # same tiling as the reference (the kernel's umin == 0 quirk reads the previous ray's row)
+        G, N, P = 256, pts_idx.size(0), pts_idx.size(1)
+        H = int(np.ceil(N / G)) * G
+        if H > N:
+            pts_idx = torch.cat([pts_idx, pts_idx[:H - N]], 0)
+            min_depth = torch.cat([min_depth, min_depth[:H - N]], 0)
+            max_depth = torch.cat([max_depth, max_depth[:H - N]], 0)
+        pts_idx = pts_idx.reshape(G, -1, P)
+        min_depth = min_depth.reshape(G, -1, P)
+        max_depth = max_depth.reshape(G, -1, P)
+
+        max_steps = int(max_ray_length / step_size)
+        max_steps = max_steps + min_depth.size(-1) * 2
+        noise = min_depth.new_zeros(*min_depth.size()[:-1], max_steps)
+        if deterministic:
+            noise += 0.5
+        else:
+            noise = noise.uniform_()
+
+        sampled_idx, sampled_depth, sampled_dists = _ext.uniform_ray_sampling(
+            pts_idx.int().contiguous(), min_depth.float().contiguous(), max_depth.float().contiguous(),
+            noise.float(), step_size, max_steps)
+        sampled_depth = sampled_depth.type_as(min_depth)
+        sampled_dists = sampled_dists.type_as(min_depth)
+
+        sampled_idx = sampled_idx.reshape(H, -1)[:N]
+        sampled_depth = sampled_depth.reshape(H, -1)[:N]
+        sampled_dists = sampled_dists.reshape(H, -1)[:N]
+
+        max_len = sampled_idx.ne(-1).sum(-1).max()
+        sampled_idx = sampled_idx[:, :max_len]
+        sampled_depth = sampled_depth[:, :max_len]
+        sampled_dists = sampled_dists[:, :max_len]
+
+        ctx.mark_non_differentiable(sampled_idx)
+        ctx.mark_non_differentiable(sampled_depth)
+        ctx.mark_non_differentiable(sampled_dists)
+        return sampled_idx, sampled_depth, sampled_dists
+
+    @staticmethod
+    def backward(ctx, a, b, c):
+        return None, None, None, None, None, None
+
+
+uniform_ray_sampling = UniformRaySampling.apply
+
+
+class InverseCDFRaySampling(Function):
+    @staticmethod
+    def forward(ctx, pts_idx, min_depth, max_depth, probs, steps, fixed_step_size=-1, deterministic=False):
+        G, N, P = 200, pts_idx.size(0), pts_idx.size(1)
+        R = int(np.ceil(N / G))          # rays per block row of the reference's [G, R, P] tiling
+        dev = pts_idx.device
+        in_dtype = min_depth.dtype
+
+        pts_idx = pts_idx.int().contiguous()
+        min_depth = min_depth.float().contiguous()
+        max_depth = max_depth.float().contiguous()
+        probs = probs.float().contiguous()
+        steps = steps.float().contiguous()
+
+        # reference: max_steps = steps.ceil().long().max() + P over the padded rays (copies of ray 0)
+        max_steps = int(steps.ceil().long().max()) + P
+        if deterministic:
+            noise, noise_ptr = None, None
+        else:
+            # identical draw to the reference: numel G*R*max_steps from the current generator
+            noise = min_depth.new_zeros(G, R, max_steps).uniform_().clamp(min=0.001, max=0.999)
+            noise_ptr = _p(noise)
+
+        sampled_idx = torch.empty((N, max_steps), dtype=torch.int32, device=dev)
+        sampled_depth = torch.empty((N, max_steps), dtype=torch.float32, device=dev)
+        sampled_dists = torch.empty((N, max_steps), dtype=torch.float32, device=dev)
+        max_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        fixed = float(fixed_step_size)
+        with torch.cuda.device(dev):
+            _lib.check(_L.nsvf_inverse_cdf_sampling(
+                _lib.current_stream(dev), G, R, N, 4 * G, P, max_steps, fixed, _p(pts_idx), _p(min_depth),
+                _p(max_depth), noise_ptr, 0.5, _p(probs), _p(steps), _p(sampled_idx), _p(sampled_depth),
+                _p(sampled_dists), _p(max_count)))
+        sampled_depth = sampled_depth.to(in_dtype)
+        sampled_dists = sampled_dists.to(in_dtype)
+
+        max_len = int(max_count.item())
+        sampled_idx = sampled_idx[:, :max_len]
+        sampled_depth = sampled_depth[:, :max_len]
+        sampled_dists = sampled_dists[:, :max_len]
+
+        ctx.mark_non_differentiable(sampled_idx)
+        ctx.mark_non_differentiable(sampled_depth)
+        ctx.mark_non_differentiable(sampled_dists)
+        return sampled_idx, sampled_depth, sampled_dists
+
+    @staticmethod
+    def backward(ctx, a, b, c):
+        return None, None, None, None, None, None, None
+
+
+inverse_cdf_sampling = InverseCDFRaySampling.apply
+
+
+def ball_ray_intersect(*args, **kwargs):
+    return _ext.ball_intersect(*args, **kwargs)
+
+
+def triangle_ray_intersect(*args, **kwargs):
+    return _ext.triangle_intersect(None, None, None, None, None, None)

@@ -1,0 +1,160 @@
+"""Level-1 boundary: the 7 functions of the reference's pybind module `fairnr.clib._ext`
+(fairnr/clib/src/binding.cpp:11-20) with the same names, argument order, dtypes, output shapes and
+fill values, implemented on the sm_100a kernels behind the C ABI (include/nsvf_b200.h).
+
+Checks mirror fairnr/clib/include/utils.h:10-30 (CHECK_CONTIGUOUS / CHECK_IS_FLOAT / CHECK_IS_INT /
+CHECK_CUDA -> RuntimeError with the same message text).  Scalar arguments may be Python numbers or
+0-dim tensors (the reference passes `self.voxel_size`, `self.max_hits` buffers; pybind converts them
+through __float__/__int__, so max_hits = 202.5 arrives as 202).
+"""
+import torch
+
+from .. import _lib
+
+_L = _lib.load()
+_p = _lib.ptr
+
+
+def _chk(cond, msg):
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _check_float_cuda(**tensors):
+    for name, t in tensors.items():
+        _chk(t.is_contiguous(), name + " must be a contiguous tensor")
+        _chk(t.dtype == torch.float32, name + " must be a float tensor")
+        _chk(t.is_cuda, name + " must be a CUDA tensor")
+
+
+def _check_int_cuda(**tensors):
+    for name, t in tensors.items():
+        _chk(t.is_contiguous(), name + " must be a contiguous tensor")
+        _chk(t.dtype == torch.int32, name + " must be an int tensor")
+        _chk(t.is_cuda, name + " must be a CUDA tensor")
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+def _hit_outputs(ray_start, n_max):
+    b, m = ray_start.shape[0], ray_start.shape[1]
+    idx = torch.empty((b, m, n_max), dtype=torch.int32, device=ray_start.device)
+    dmin = torch.empty((b, m, n_max), dtype=torch.float32, device=ray_start.device)
+    dmax = torch.empty((b, m, n_max), dtype=torch.float32, device=ray_start.device)
+    return idx, dmin, dmax
+
+
+def aabb_intersect(ray_start, ray_dir, points, voxelsize, n_max, shared_points=False):
+    """fairnr/clib/src/intersect.cpp:49-75.  ray_start, ray_dir f32 [B,M,3]; points f32 [B,n,3]
+    -> idx i32 [B,M,n_max] (-1 fill), min_depth, max_depth f32 [B,M,n_max] (0 fill).
+
+    `shared_points=True` (extension): points is [1,n,3] or [n,3] and serves every batch row, which is
+    what the Level-2 wrapper uses instead of materialising B copies (fairnr/clib/__init__.py:71).
+    """
+    _check_float_cuda(ray_start=ray_start, ray_dir=ray_dir, points=points)
+    voxelsize, n_max = float(voxelsize), int(n_max)
+    b, m = ray_start.shape[0], ray_start.shape[1]
+    if shared_points:
+        n, stride, trees = points.shape[-2], 0, 1
+    else:
+        _chk(points.dim() == 3 and points.shape[0] == b, "points must be [B, n, 3] with B == ray_start.size(0)")
+        n, stride, trees = points.shape[1], points.shape[1] * 3, b
+    idx, dmin, dmax = _hit_outputs(ray_start, n_max)
+    with torch.cuda.device(ray_start.device):
+        ws_bytes = _L.nsvf_aabb_workspace_bytes(n, trees)
+        ws = _workspace(ws_bytes, ray_start.device)
+        _lib.check(_L.nsvf_aabb_intersect(
+            _lib.current_stream(ray_start.device), b, n, m, voxelsize, n_max, _p(ray_start), _p(ray_dir),
+            _p(points), stride, _p(idx), _p(dmin), _p(dmax), _p(ws), ws.numel()))
+    return idx, dmin, dmax
+
+
+def svo_intersect(ray_start, ray_dir, points, children, voxelsize, n_max, shared_tree=False):
+    """fairnr/clib/src/intersect.cpp:84-112.  points f32 [B,T,3] node centres, children i32 [B,T,9]."""
+    _check_float_cuda(ray_start=ray_start, ray_dir=ray_dir, points=points)
+    _chk(children.is_contiguous(), "children must be a contiguous tensor")
+    _chk(children.is_cuda, "children must be a CUDA tensor")
+    _chk(children.dtype == torch.int32, "children must be an int tensor")  # the reference reinterprets blindly
+    voxelsize, n_max = float(voxelsize), int(n_max)
+    b, m = ray_start.shape[0], ray_start.shape[1]
+    if shared_tree:
+        T, stride, trees = points.shape[-2], 0, 1
+    else:
+        _chk(points.dim() == 3 and points.shape[0] == b, "points must be [B, T, 3] with B == ray_start.size(0)")
+        T, stride, trees = points.shape[1], points.shape[1], b
+    _chk(children.shape[-2] == T and children.shape[-1] == 9, "children must be [.., T, 9]")
+    idx, dmin, dmax = _hit_outputs(ray_start, n_max)
+    with torch.cuda.device(ray_start.device):
+        ws_bytes = _L.nsvf_svo_workspace_bytes(T, trees)
+        ws = _workspace(ws_bytes, ray_start.device)
+        _lib.check(_L.nsvf_svo_intersect(
+            _lib.current_stream(ray_start.device), b, T, m, voxelsize, n_max, _p(ray_start), _p(ray_dir),
+            _p(points), _p(children), stride, _p(idx), _p(dmin), _p(dmax), _p(ws), ws.numel()))
+    return idx, dmin, dmax
+
+
+def ball_intersect(ray_start, ray_dir, points, radius, n_max):
+    """fairnr/clib/src/intersect.cpp:15-44 — no caller anywhere in the reference: out of scope."""
+    raise NotImplementedError("ball_intersect is outside the NSVF hot path (no caller in the reference)")
+
+
+def triangle_intersect(ray_start, ray_dir, face_points, cagesize, blur, n_max):
+    """fairnr/clib/src/intersect.cpp:120-146 — TriangleMeshEncoder only: not built yet."""
+    raise NotImplementedError("triangle_intersect is outside the NSVF hot path (SURVEY.md §8f, rank 4)")
+
+
+def uniform_ray_sampling(pts_idx, min_depth, max_depth, uniform_noise, step_size, max_steps):
+    """fairnr/clib/src/sample.cpp:23-55.  [G,R,P] inputs, noise [G,R,max_steps] -> 3 x [G,R,max_steps]."""
+    _check_float_cuda(min_depth=min_depth, max_depth=max_depth, uniform_noise=uniform_noise)
+    _check_int_cuda(pts_idx=pts_idx)
+    step_size, max_steps = float(step_size), int(max_steps)
+    g, r, p = min_depth.shape
+    dev = pts_idx.device
+    sidx = torch.empty((g, r, max_steps), dtype=torch.int32, device=dev)
+    sdepth = torch.empty((g, r, max_steps), dtype=torch.float32, device=dev)
+    sdists = torch.empty((g, r, max_steps), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_L.nsvf_uniform_ray_sampling(
+            _lib.current_stream(dev), g, r, p, max_steps, step_size, _p(pts_idx), _p(min_depth), _p(max_depth),
+            _p(uniform_noise), _p(sidx), _p(sdepth), _p(sdists)))
+    return sidx, sdepth, sdists
+
+
+def inverse_cdf_sampling(pts_idx, min_depth, max_depth, uniform_noise, probs, steps, fixed_step_size):
+    """fairnr/clib/src/sample.cpp:58-95.  max_steps = uniform_noise.size(-1)."""
+    _check_float_cuda(min_depth=min_depth, max_depth=max_depth, uniform_noise=uniform_noise, probs=probs, steps=steps)
+    _check_int_cuda(pts_idx=pts_idx)
+    fixed_step_size = float(fixed_step_size)
+    g, r, p = min_depth.shape
+    max_steps = uniform_noise.shape[-1]
+    dev = pts_idx.device
+    sidx = torch.empty((g, r, max_steps), dtype=torch.int32, device=dev)
+    sdepth = torch.empty((g, r, max_steps), dtype=torch.float32, device=dev)
+    sdists = torch.empty((g, r, max_steps), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_L.nsvf_inverse_cdf_sampling(
+            _lib.current_stream(dev), g, r, -1, 0, p, max_steps, fixed_step_size, _p(pts_idx), _p(min_depth),
+            _p(max_depth), _p(uniform_noise), 0.5, _p(probs), _p(steps), _p(sidx), _p(sdepth), _p(sdists), None))
+    return sidx, sdepth, sdists
+
+
+def build_octree(center, points, depth):
+    """fairnr/clib/src/octree.cpp:125-135.  center [3] (any real dtype), points i64 [n,3], depth int ->
+    (centers i32 [T,3], children i32 [T,9]) on center's device.  The tree is built on the host from one
+    D2H copy (the reference syncs once per point per level through .item())."""
+    depth = int(depth)
+    dev = center.device
+    c = center.detach().to("cpu", torch.float64).contiguous()
+    p = points.detach().to("cpu", torch.int64).contiguous()
+    _chk(p.dim() == 2 and p.shape[1] == 3, "points must be [n, 3]")
+    import ctypes
+    total, term = ctypes.c_longlong(0), ctypes.c_longlong(0)
+    _lib.check(_L.nsvf_octree_build(c.data_ptr(), p.data_ptr(), p.shape[0], depth,
+                                    ctypes.addressof(total), ctypes.addressof(term)))
+    T = total.value
+    centers = torch.empty((T, 3), dtype=torch.int32)
+    children = torch.empty((T, 9), dtype=torch.int32)
+    _lib.check(_L.nsvf_octree_flatten(centers.data_ptr(), children.data_ptr(), T))
+    return centers.to(dev), children.to(dev)

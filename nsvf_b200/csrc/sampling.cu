@@ -1,0 +1,323 @@
+// Ray sampling for sm_100a: inverse-CDF sampling (the live sampler) and uniform ray sampling.
+//
+// Replaces fairnr/clib/src/sample_gpu.cu:108-202 (inverse_cdf_sampling_kernel) and :15-106
+// (uniform_ray_sampling_kernel) plus the host glue fairnr/clib/src/sample.cpp:23-95.
+//
+// The per-ray state machine is inherently serial and data dependent, so one lane still owns one ray,
+// but (a) the three dense outputs [rays, max_steps] are staged through shared-memory tiles and flushed
+// by the whole warp with coalesced stores (the reference writes them with a stride of 4*max_steps
+// bytes between lanes), and (b) the kernel itself writes the -1 / 0 padding, which replaces the three
+// host-side fill kernels (-ones / zeros) of sample.cpp:40-48, 80-88.
+//
+// Quirks of the reference that are reproduced on purpose:
+//   * `(~done)` is always true, so the trailing loop runs after `done` and emits one more sample whose
+//     voxel id is read at pts_idx[H + curr_bin] (curr_bin may equal max_hits: the next ray's slot 0);
+//     reads past the end of the tensor are defined here as -1.
+//   * the trailing loop's stop test reads pts_idx[curr_bin] of ray 0 of the block row.
+//   * a sample that would land at s >= max_steps is dropped (the reference writes out of the row).
+#include "common.cuh"
+#include "nsvf_b200.h"
+
+namespace nsvf {
+
+constexpr int kSampWarps = 4;
+
+struct CdfState {
+  int curr_bin, s, curr_step, total_steps, phase;  // phase 0: step begin, 1: inside while, 2: trailing, 3: finished
+  float curr_min_depth, curr_max_depth, curr_min_cdf, curr_max_cdf, step_size, z_low, curr_cdf;
+};
+
+// Emits at most one sample; returns true if one was produced.
+__device__ __forceinline__ bool cdf_next(CdfState& st, int max_hits, int max_steps, long long H, int next_idx0,
+                                         const int* __restrict__ pts_idx, const int* __restrict__ row0_idx,
+                                         const float* __restrict__ min_depth, const float* __restrict__ max_depth,
+                                         const float* __restrict__ probs, const float* __restrict__ noise_row,
+                                         float noise_const, int& o_idx, float& o_dist, float& o_depth) {
+  for (;;) {
+    if (st.phase == 0) {
+      if (st.curr_step >= st.total_steps) { st.phase = 2; continue; }
+      const int ns = st.curr_step < max_steps ? st.curr_step : max_steps - 1;  // reference reads OOB here
+      const float nz = noise_row != nullptr ? noise_row[ns] : noise_const;
+      st.curr_cdf = __fmul_rn(__fadd_rn((float)st.curr_step, nz), st.step_size);
+      st.phase = 1;
+    }
+    if (st.phase == 1) {
+      if (st.curr_cdf > st.curr_max_cdf) {
+        o_idx = pts_idx[H + st.curr_bin];
+        o_dist = __fsub_rn(st.curr_max_depth, st.z_low);
+        o_depth = __fmul_rn(__fadd_rn(st.curr_max_depth, st.z_low), 0.5f);
+        st.curr_bin++;
+        if (st.curr_bin >= max_hits || pts_idx[H + st.curr_bin] == -1) {
+          st.phase = 2;  // done = true; break; if (done) break;
+        } else {
+          st.curr_min_depth = min_depth[H + st.curr_bin];
+          st.curr_max_depth = max_depth[H + st.curr_bin];
+          st.curr_min_cdf = st.curr_max_cdf;
+          st.curr_max_cdf = __fadd_rn(st.curr_max_cdf, probs[H + st.curr_bin]);
+          st.z_low = st.curr_min_depth;
+        }
+        return true;
+      }
+      const float u = __fdiv_rn(__fsub_rn(st.curr_cdf, st.curr_min_cdf), __fsub_rn(st.curr_max_cdf, st.curr_min_cdf));
+      const float z = __fmaf_rn(u, __fsub_rn(st.curr_max_depth, st.curr_min_depth), st.curr_min_depth);
+      o_idx = pts_idx[H + st.curr_bin];
+      o_dist = __fsub_rn(z, st.z_low);
+      o_depth = __fmul_rn(__fadd_rn(z, st.z_low), 0.5f);
+      st.z_low = z;
+      st.curr_step++;
+      st.phase = 0;
+      return true;
+    }
+    if (st.phase == 2) {
+      if (!(st.z_low < st.curr_max_depth)) { st.phase = 3; return false; }
+      // reference: pts_idx[H + curr_bin]; curr_bin == max_hits is slot 0 of the next ray in memory
+      o_idx = st.curr_bin < max_hits ? pts_idx[H + st.curr_bin] : next_idx0;
+      o_dist = __fsub_rn(st.curr_max_depth, st.z_low);
+      o_depth = __fmul_rn(__fadd_rn(st.curr_max_depth, st.z_low), 0.5f);
+      st.curr_bin++;
+      if (st.curr_bin >= max_hits || row0_idx[st.curr_bin] == -1) {
+        st.phase = 3;
+      } else {
+        st.curr_min_depth = min_depth[H + st.curr_bin];
+        st.curr_max_depth = max_depth[H + st.curr_bin];
+        st.z_low = st.curr_min_depth;
+      }
+      return true;
+    }
+    return false;  // phase 3
+  }
+}
+
+template <int TS>
+__global__ void __launch_bounds__(kSampWarps * 32)
+inverse_cdf_sampling_kernel(int b, int num_rays, long long valid_rays, int ray_chunk, int max_hits, int max_steps,
+                            float fixed_step_size, const int* __restrict__ pts_idx,
+                            const float* __restrict__ min_depth, const float* __restrict__ max_depth,
+                            const float* __restrict__ noise, float noise_const, const float* __restrict__ probs,
+                            const float* __restrict__ steps, int* __restrict__ sampled_idx,
+                            float* __restrict__ sampled_depth, float* __restrict__ sampled_dists,
+                            int* __restrict__ max_count) {
+  constexpr int LD = TS + 1;
+  __shared__ int t_idx[kSampWarps][32 * LD];
+  __shared__ float t_depth[kSampWarps][32 * LD];
+  __shared__ float t_dist[kSampWarps][32 * LD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long total_rays = valid_rays;  // rays >= valid_rays are padding aliases of ray 0: never computed
+  const long long n_groups = (total_rays + 31) / 32;
+  int my_max = 0;
+
+  for (long long g = (long long)blockIdx.x * kSampWarps + warp; g < n_groups; g += (long long)gridDim.x * kSampWarps) {
+    const long long ray = g * 32 + lane;
+    const bool active = ray < total_rays;
+    const long long H = ray * max_hits;
+    CdfState st;
+    const int* row0_idx = pts_idx;
+    const float* noise_row = noise;
+    st.phase = 3;
+    st.s = 0;
+    int next_idx0 = -1, n_valid = 0;
+    if (active) {
+      const long long batch = ray / num_rays;
+      const int r = (int)(ray - batch * num_rays);
+      const int c0 = (r / ray_chunk) * ray_chunk;
+      // ray 0 of this block row within its column chunk (reference :194 + clib/__init__.py:259-270)
+      const long long row0 = batch * num_rays + c0;
+      row0_idx = pts_idx + (row0 < valid_rays ? row0 : 0) * max_hits;
+      // the ray that follows this one in the reference's contiguous chunk slice
+      long long nxt = -1;
+      if (r + 1 < min(c0 + ray_chunk, num_rays)) nxt = ray + 1;
+      else if (batch + 1 < b) nxt = (batch + 1) * num_rays + c0;
+      if (nxt >= 0) next_idx0 = pts_idx[(nxt < valid_rays ? nxt : 0) * max_hits];
+      noise_row = noise != nullptr ? noise + ray * max_steps : nullptr;
+      st.curr_bin = 0;
+      st.curr_step = 0;
+      st.curr_min_depth = min_depth[H];
+      st.curr_max_depth = max_depth[H];
+      st.curr_min_cdf = 0.0f;
+      st.curr_max_cdf = probs[H];
+      const float sj = steps[ray];
+      st.step_size = __fdiv_rn(1.0f, sj);  // 1.0 / steps[j] in double then rounded: same value
+      st.z_low = st.curr_min_depth;
+      st.total_steps = (int)ceilf(sj);
+      if (fixed_step_size > 0.0f) st.step_size = fixed_step_size;
+      st.curr_cdf = 0.0f;
+      st.phase = 0;
+    }
+    const long long out_base = g * 32 * (long long)max_steps;
+    const int rows = (int)min((long long)32, total_rays - g * 32);
+
+    for (int t0 = 0; t0 < max_steps; t0 += TS) {
+      const int tw = min(TS, max_steps - t0);
+      // fill my row of the tile
+      int c = 0;
+      while (c < tw && st.phase != 3) {
+        int oi; float od, oz;
+        if (cdf_next(st, max_hits, max_steps, H, next_idx0, pts_idx, row0_idx, min_depth, max_depth, probs,
+                     noise_row, noise_const, oi, od, oz)) {
+          n_valid += (oi != -1);
+          t_idx[warp][lane * LD + c] = oi;
+          t_dist[warp][lane * LD + c] = od;
+          t_depth[warp][lane * LD + c] = oz;
+          ++c;
+        }
+      }
+      for (; c < tw; ++c) {
+        t_idx[warp][lane * LD + c] = -1;
+        t_dist[warp][lane * LD + c] = 0.0f;
+        t_depth[warp][lane * LD + c] = 0.0f;
+      }
+      __syncwarp();
+      // coalesced flush: 32/TS rows per instruction
+      constexpr int RPI = 32 / TS;
+      const int cc = lane % TS, rsub = lane / TS;
+      for (int r = 0; r < rows; r += RPI) {
+        const int rr = r + rsub;
+        if (rr < rows && cc < tw) {
+          const long long o = out_base + (long long)rr * max_steps + t0 + cc;
+          sampled_idx[o] = t_idx[warp][rr * LD + cc];
+          sampled_depth[o] = t_depth[warp][rr * LD + cc];
+          sampled_dists[o] = t_dist[warp][rr * LD + cc];
+        }
+      }
+      __syncwarp();
+      // every lane finished: the rest of all rows is padding, written directly
+      if (__all_sync(NSVF_FULL_MASK, st.phase == 3)) {
+        const int tnext = t0 + TS;
+        if (tnext < max_steps) {
+          const int rem = max_steps - tnext;
+          for (int r = 0; r < rows; ++r) {
+            const long long o = out_base + (long long)r * max_steps + tnext;
+            for (int k = lane; k < rem; k += 32) {
+              sampled_idx[o + k] = -1;
+              sampled_depth[o + k] = 0.0f;
+              sampled_dists[o + k] = 0.0f;
+            }
+          }
+        }
+        break;
+      }
+    }
+    my_max = max(my_max, n_valid);
+  }
+  if (max_count != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_max = max(my_max, __shfl_xor_sync(NSVF_FULL_MASK, my_max, o));
+    if (lane == 0 && my_max > 0) atomicMax(max_count, my_max);
+  }
+}
+
+// Faithful restatement of the two-phase uniform sampler (dead code in the live model path: no caller
+// in fairnr/modules/encoder.py). One thread per ray, in-place in global memory like the reference;
+// the kernel pre-fills its own row (idx -1, depth 0, dists 0) instead of relying on host fills.
+__global__ void uniform_ray_sampling_kernel(long long total_rays, int max_hits, int max_steps, float step_size,
+                                            const int* __restrict__ pts_idx, const float* __restrict__ min_depth,
+                                            const float* __restrict__ max_depth, const float* __restrict__ noise,
+                                            int* sampled_idx, float* sampled_depth, float* sampled_dists) {
+  const long long total_hits = total_rays * max_hits;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < total_rays;
+       j += (long long)gridDim.x * blockDim.x) {
+    const long long H = j * max_hits, K = j * max_steps;
+    for (int t = 0; t < max_steps; ++t) {
+      sampled_idx[K + t] = -1;
+      sampled_depth[K + t] = 0.0f;
+      sampled_dists[K + t] = 0.0f;
+    }
+    int s = 0, ucur = 0, umin = 0, umax = 0;
+    float last_min_depth = 0.f, last_max_depth = 0.f, curr_depth = 0.f;
+    // merge voxel entries, voxel exits and march points (reference :47-81)
+    for (;;) {
+      if (umax == max_hits || ucur == max_steps || pts_idx[H + umax] == -1) break;
+      last_min_depth = umin < max_hits ? min_depth[H + umin] : 10000.0f;
+      last_max_depth = umax < max_hits ? max_depth[H + umax] : 10000.0f;
+      if (ucur < max_steps)
+        curr_depth = __fmaf_rn(__fadd_rn((float)ucur, noise[K + ucur]), step_size, min_depth[H]);
+      if (s >= max_steps) break;  // reference would write past the row
+      if (last_max_depth <= curr_depth && last_max_depth <= last_min_depth) {
+        sampled_depth[K + s] = last_max_depth;
+        sampled_idx[K + s] = pts_idx[H + umax];
+        umax++; s++; continue;
+      }
+      if (curr_depth <= last_min_depth && curr_depth <= last_max_depth) {
+        sampled_depth[K + s] = curr_depth;
+        // reference reads pts_idx[H + umin - 1]; with umin == 0 that is the previous ray's last slot
+        const long long f = H + umin - 1;
+        sampled_idx[K + s] = (f >= 0 && f < total_hits) ? pts_idx[f] : -1;
+        ucur++; s++; continue;
+      }
+      if (last_min_depth <= curr_depth && last_min_depth <= last_max_depth) {
+        sampled_depth[K + s] = last_min_depth;
+        sampled_idx[K + s] = umin < max_hits ? pts_idx[H + umin] : -1;
+        umin++; s++; continue;
+      }
+      break;  // NaN inputs: the reference would spin forever
+    }
+    // mid-points, distances, in-voxel filter, compaction (reference :83-100)
+    int step = 0;
+    umin = 0; umax = 0;
+    for (ucur = 0; ucur < max_steps - 1; ucur++) {
+      if (sampled_idx[K + ucur + 1] == -1) break;
+      const float l_depth = sampled_depth[K + ucur];
+      const float r_depth = sampled_depth[K + ucur + 1];
+      sampled_depth[K + ucur] = __fmul_rn(__fadd_rn(l_depth, r_depth), 0.5f);
+      sampled_dists[K + ucur] = __fsub_rn(r_depth, l_depth);
+      if (umin < max_hits && sampled_depth[K + ucur] >= min_depth[H + umin] && pts_idx[H + umin] > -1) umin++;
+      if (umax < max_hits && sampled_depth[K + ucur] >= max_depth[H + umax] && pts_idx[H + umax] > -1) umax++;
+      if (umax == max_hits || pts_idx[H + umax] == -1) break;
+      if (umin - 1 == umax && sampled_dists[K + ucur] > 0) {
+        sampled_depth[K + step] = sampled_depth[K + ucur];
+        sampled_dists[K + step] = sampled_dists[K + ucur];
+        sampled_idx[K + step] = sampled_idx[K + ucur];
+        step++;
+      }
+    }
+    for (int t = step; t < max_steps; t++) sampled_idx[K + t] = -1;
+  }
+}
+
+}  // namespace nsvf
+
+using namespace nsvf;
+
+extern "C" int nsvf_inverse_cdf_sampling(nsvf_stream_t stream_, int b, int num_rays, long long valid_rays,
+                                         int ray_chunk, int max_hits, int max_steps, float fixed_step_size,
+                                         const int* pts_idx, const float* min_depth, const float* max_depth,
+                                         const float* uniform_noise, float noise_const, const float* probs,
+                                         const float* steps, int* sampled_idx, float* sampled_depth,
+                                         float* sampled_dists, int* max_count) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSVF_REQUIRE(b >= 0 && num_rays >= 0 && max_hits >= 0 && max_steps >= 0, "inverse_cdf_sampling: negative size");
+  if (b == 0 || num_rays == 0 || max_steps == 0) return 0;
+  NSVF_REQUIRE(max_hits > 0, "inverse_cdf_sampling: max_hits must be > 0 (the reference reads slot 0 of every ray)");
+  const long long total_rays = (long long)b * num_rays;
+  if (valid_rays < 0 || valid_rays > total_rays) valid_rays = total_rays;
+  if (ray_chunk <= 0 || ray_chunk > num_rays) ray_chunk = num_rays;
+  if (valid_rays == 0) return 0;
+  const long long groups = (valid_rays + 31) / 32;
+  long long want = (groups + kSampWarps - 1) / kSampWarps;
+  long long cap = (long long)num_sms() * 8;
+  int grid = (int)(want < cap ? want : cap);
+  inverse_cdf_sampling_kernel<16><<<grid, kSampWarps * 32, 0, stream>>>(
+      b, num_rays, valid_rays, ray_chunk, max_hits, max_steps, fixed_step_size, pts_idx, min_depth, max_depth,
+      uniform_noise, noise_const, probs, steps, sampled_idx, sampled_depth, sampled_dists, max_count);
+  NSVF_LAUNCH_OK("inverse_cdf_sampling_kernel");
+  return 0;
+}
+
+extern "C" int nsvf_uniform_ray_sampling(nsvf_stream_t stream_, int b, int num_rays, int max_hits, int max_steps,
+                                         float step_size, const int* pts_idx, const float* min_depth,
+                                         const float* max_depth, const float* uniform_noise, int* sampled_idx,
+                                         float* sampled_depth, float* sampled_dists) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSVF_REQUIRE(b >= 0 && num_rays >= 0 && max_hits >= 0 && max_steps >= 0, "uniform_ray_sampling: negative size");
+  if (b == 0 || num_rays == 0 || max_steps == 0) return 0;
+  NSVF_REQUIRE(max_hits > 0, "uniform_ray_sampling: max_hits must be > 0");
+  const long long total_rays = (long long)b * num_rays;
+  long long want = (total_rays + 127) / 128;
+  long long cap = (long long)num_sms() * 16;
+  int grid = (int)(want < cap ? want : cap);
+  uniform_ray_sampling_kernel<<<grid, 128, 0, stream>>>(total_rays, max_hits, max_steps, step_size, pts_idx,
+                                                        min_depth, max_depth, uniform_noise, sampled_idx,
+                                                        sampled_depth, sampled_dists);
+  NSVF_LAUNCH_OK("uniform_ray_sampling_kernel");
+  return 0;
+}

@@ -1,0 +1,182 @@
+// Ray / sparse-voxel-octree intersection for sm_100a.
+//
+// Replaces fairnr/clib/src/intersect_gpu.cu:170-237 (svo_intersect_point_kernel) and its host glue
+// fairnr/clib/src/intersect.cpp:84-112.  The reference emits leaves in its DFS order (children pushed
+// 0..7, popped LIFO, root = node T-1) and truncates at n_max, so the traversal ORDER is part of the
+// integer contract; we keep exactly that order and the bit-identical slab test (common.cuh) and change
+// everything around it:
+//   * a prep kernel packs each node into one 64-byte record {c-hv, c+hv, leaf flag, 8 children}
+//     (reference: 3 + 9 scattered 4-byte loads per visit, hv recomputed per visit);
+//   * 1/dir is computed once per ray (reference: 3 MUFU per node visit);
+//   * the DFS stack is an uninitialised per-thread array (reference zero-fills 1 KiB per ray);
+//   * output rows are pre-filled (-1 / 0) with coalesced stores by the whole CTA, then hits are
+//     written in place (reference: 3 cudaMemsets + an uncoalesced per-thread -1 loop).
+#include "common.cuh"
+#include "nsvf_b200.h"
+
+namespace nsvf {
+
+constexpr int kSvoStack = 256;   // reference bound (intersect_gpu.cu:205,209)
+constexpr int kSvoThreads = 128;
+
+struct __align__(16) SvoNode {
+  float lo[3];
+  float hi[3];
+  int leaf;   // children[k][8] == 1
+  int pad;
+  int child[8];
+};
+static_assert(sizeof(SvoNode) == 64, "SvoNode must be one 64-byte record");
+
+__global__ void svo_pack_kernel(const float* __restrict__ points, const int* __restrict__ children,
+                                long long tree_stride_nodes, int T, float half_voxel,
+                                SvoNode* __restrict__ nodes) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= T) return;
+  const float* p = points + ((long long)blockIdx.y * tree_stride_nodes + k) * 3;
+  const int* ch = children + ((long long)blockIdx.y * tree_stride_nodes + k) * 9;
+  SvoNode nd;
+  int size = ch[8];
+  // reference: half_voxel * float(children[k * 9 + 8])  (intersect_gpu.cu:217)
+  float hv = __fmul_rn(half_voxel, (float)size);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float c = p[a];
+    nd.lo[a] = __fsub_rn(c, hv);
+    nd.hi[a] = __fadd_rn(c, hv);
+  }
+  nd.leaf = (size == 1);
+  nd.pad = 0;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) nd.child[u] = ch[u];
+  int4* dst = reinterpret_cast<int4*>(nodes + (long long)blockIdx.y * T + k);
+  const int4* src = reinterpret_cast<const int4*>(&nd);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dst[q] = src[q];
+}
+
+__global__ void __launch_bounds__(kSvoThreads)
+svo_intersect_kernel(const SvoNode* __restrict__ nodes_all, int T, long long rays_per_tree, int n_max,
+                     const float* __restrict__ ray_start, const float* __restrict__ ray_dir,
+                     int* __restrict__ out_idx, float* __restrict__ out_min, float* __restrict__ out_max,
+                     int* __restrict__ overflow_flag) {
+  const SvoNode* nodes = nodes_all + (long long)blockIdx.y * T;
+  const long long ray_base = (long long)blockIdx.y * rays_per_tree;
+
+  for (long long tile = (long long)blockIdx.x * kSvoThreads; tile < rays_per_tree;
+       tile += (long long)gridDim.x * kSvoThreads) {
+    const long long tile_rays = min((long long)kSvoThreads, rays_per_tree - tile);
+    // 1) coalesced pre-fill of this tile's rows
+    {
+      const long long base = (ray_base + tile) * n_max;
+      const long long cells = tile_rays * n_max;
+      for (long long c = threadIdx.x; c < cells; c += kSvoThreads) {
+        out_idx[base + c] = -1;
+        out_min[base + c] = 0.0f;
+        out_max[base + c] = 0.0f;
+      }
+    }
+    __syncthreads();
+    // 2) one thread per ray: the reference DFS
+    if (threadIdx.x < tile_rays) {
+      const long long ray = ray_base + tile + threadIdx.x;
+      const float ox = ray_start[ray * 3 + 0], oy = ray_start[ray * 3 + 1], oz = ray_start[ray * 3 + 2];
+      const float ix = ref_rcp(ray_dir[ray * 3 + 0]), iy = ref_rcp(ray_dir[ray * 3 + 1]),
+                  iz = ref_rcp(ray_dir[ray * 3 + 2]);
+      const bool regular = regular_component(ox, ix) && regular_component(oy, iy) && regular_component(oz, iz);
+      const long long row = ray * n_max;
+      int stack[kSvoStack];
+      int ptr = 0, cnt = 0;
+      stack[0] = T - 1;  // ROOT node is always the last
+      while (ptr > -1 && cnt < n_max) {
+        const int k = stack[ptr--];
+        const int4* rec = reinterpret_cast<const int4*>(nodes + k);
+        const int4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
+        const float lx = __int_as_float(q0.x), ly = __int_as_float(q0.y), lz = __int_as_float(q0.z);
+        const float hx = __int_as_float(q0.w), hy = __int_as_float(q1.x), hz = __int_as_float(q1.y);
+        float tn, tf;
+        bool hit;
+        if (regular) {
+          // fmin/fmax ordering == the reference's swap when no NaN can occur
+          float a0 = __fmul_rn(__fsub_rn(lx, ox), ix), b0 = __fmul_rn(__fsub_rn(hx, ox), ix);
+          float a1 = __fmul_rn(__fsub_rn(ly, oy), iy), b1 = __fmul_rn(__fsub_rn(hy, oy), iy);
+          float a2 = __fmul_rn(__fsub_rn(lz, oz), iz), b2 = __fmul_rn(__fsub_rn(hz, oz), iz);
+          tn = fmaxf(fmaxf(fmaxf(0.0f, fminf(a0, b0)), fminf(a1, b1)), fminf(a2, b2));
+          tf = fminf(fminf(fminf(100000.0f, fmaxf(a0, b0)), fmaxf(a1, b1)), fmaxf(a2, b2));
+          hit = tn <= tf;
+        } else {
+          hit = slab_exact(ox, oy, oz, ix, iy, iz, lx, ly, lz, hx, hy, hz, tn, tf);
+        }
+        if (!hit) continue;
+        if (q1.z) {  // terminal node
+          out_idx[row + cnt] = k;
+          out_min[row + cnt] = tn;
+          out_max[row + cnt] = tf;
+          ++cnt;
+          continue;
+        }
+        const int4 c0 = __ldg(rec + 2), c1 = __ldg(rec + 3);
+        if (ptr + 8 >= kSvoStack) {  // reference: device assert((ptr < 256)); we flag and stop this ray
+          atomicExch(overflow_flag, 1);
+          break;
+        }
+        if (c0.x > -1) stack[++ptr] = c0.x;
+        if (c0.y > -1) stack[++ptr] = c0.y;
+        if (c0.z > -1) stack[++ptr] = c0.z;
+        if (c0.w > -1) stack[++ptr] = c0.w;
+        if (c1.x > -1) stack[++ptr] = c1.x;
+        if (c1.y > -1) stack[++ptr] = c1.y;
+        if (c1.z > -1) stack[++ptr] = c1.z;
+        if (c1.w > -1) stack[++ptr] = c1.w;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace nsvf
+
+using namespace nsvf;
+
+extern "C" size_t nsvf_svo_workspace_bytes(int T, int n_trees) {
+  if (T <= 0 || n_trees <= 0) return 0;
+  return (size_t)T * n_trees * sizeof(SvoNode) + 128;  // + overflow flag
+}
+
+extern "C" int nsvf_svo_intersect(nsvf_stream_t stream_, int b, int T, int m, float voxelsize, int n_max,
+                                  const float* ray_start, const float* ray_dir, const float* points,
+                                  const int* children, long long tree_batch_stride_nodes, int* idx,
+                                  float* min_depth, float* max_depth, void* workspace, size_t workspace_bytes) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSVF_REQUIRE(b >= 0 && T >= 0 && m >= 0 && n_max >= 0, "svo_intersect: negative size");
+  if (b == 0 || m == 0 || n_max == 0) return 0;
+  const long long rays = (long long)b * m;
+  NSVF_REQUIRE(T > 0, "svo_intersect: empty octree (the reference reads node T-1 as the root)");
+  NSVF_REQUIRE(tree_batch_stride_nodes == 0 || tree_batch_stride_nodes >= T,
+               "svo_intersect: tree_batch_stride_nodes must be 0 (shared octree) or >= T");
+  const int n_trees = tree_batch_stride_nodes == 0 ? 1 : b;
+  const size_t need = nsvf_svo_workspace_bytes(T, n_trees);
+  NSVF_REQUIRE(workspace != nullptr && workspace_bytes >= need, "svo_intersect: workspace too small (%zu < %zu bytes)",
+               workspace_bytes, need);
+  NSVF_REQUIRE(((uintptr_t)workspace & 127) == 0, "svo_intersect: workspace must be 128-byte aligned");
+  int* flag = (int*)workspace;
+  SvoNode* nodes = (SvoNode*)((char*)workspace + 128);
+  NSVF_CUDA_OK(cudaMemsetAsync(flag, 0, 128, stream));
+  const float half_voxel = voxelsize * 0.5f;
+  {
+    dim3 grid((T + 255) / 256, n_trees);
+    svo_pack_kernel<<<grid, 256, 0, stream>>>(points, children, tree_batch_stride_nodes, T, half_voxel, nodes);
+    NSVF_LAUNCH_OK("svo_pack_kernel");
+  }
+  const long long rays_per_tree = n_trees == 1 ? rays : m;
+  long long want = (rays_per_tree + kSvoThreads - 1) / kSvoThreads;
+  long long cap = (long long)num_sms() * 8;
+  if (n_trees > 1) cap = (cap + n_trees - 1) / n_trees;
+  int gx = (int)(want < cap ? want : cap);
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, n_trees);
+  svo_intersect_kernel<<<grid, kSvoThreads, 0, stream>>>(nodes, T, rays_per_tree, n_max, ray_start, ray_dir, idx,
+                                                         min_depth, max_depth, flag);
+  NSVF_LAUNCH_OK("svo_intersect_kernel");
+  return 0;
+}

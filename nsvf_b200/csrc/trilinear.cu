@@ -1,0 +1,261 @@
+// Fused trilinear voxel-corner embedding interpolation (gather) and its scatter-add backward, sm_100a.
+//
+// Replaces the torch-level sequence of SparseVoxelEncoder.forward, fairnr/modules/encoder.py:582-590
+// (F.embedding x3 -> [M,8,D] materialisation -> offset_points -> trilinear_interp,
+// fairnr/data/geometry.py:195-200) with ONE gather kernel that never materialises the [M,8,D] rows,
+// and autograd's embedding backward with one red.global.add.v4.f32 scatter kernel that first merges
+// runs of consecutive samples lying in the same voxel (ray-marched samples arrive in ray order).
+//
+// Math (identical op order to the reference where it is defined):
+//   p_a   = (xyz_a - centre[idx]_a) / voxel_size + 0.5                      (IEEE division)
+//   w_j   = (q_jx ? p_x : 1 - p_x) * (q_jy ? p_y : 1 - p_y) * (q_jz ? p_z : 1 - p_z),  j = 4*qx + 2*qy + qz
+//           (p*q + (1-p)*(1-q) with q in {0,1} reduces to exactly these values)
+//   emb   = sum_j w_j * values[feats[idx][j]]
+#include "common.cuh"
+#include "nsvf_b200.h"
+
+namespace nsvf {
+
+__device__ __forceinline__ void corner_weights(float px, float py, float pz, float w[8]) {
+  const float ax[2] = {__fsub_rn(1.0f, px), px};
+  const float ay[2] = {__fsub_rn(1.0f, py), py};
+  const float az[2] = {__fsub_rn(1.0f, pz), pz};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) w[j] = __fmul_rn(__fmul_rn(ax[(j >> 2) & 1], ay[(j >> 1) & 1]), az[j & 1]);
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// D == 32: 8 lanes per sample, one float4 (4 dims) per lane; a warp handles 4 samples per step.
+__global__ void __launch_bounds__(256)
+trilinear_fwd_d32_kernel(long long M, const int* __restrict__ sampled_idx, const float* __restrict__ xyz,
+                         const int* __restrict__ feats, const float* __restrict__ centres,
+                         const float* __restrict__ values, float voxel_size, float* __restrict__ out) {
+  const int sub = threadIdx.x & 7;
+  for (long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3; s < M;
+       s += ((long long)gridDim.x * blockDim.x) >> 3) {
+    const int v = sampled_idx[s];
+    const float px = __fadd_rn(__fdiv_rn(__fsub_rn(xyz[s * 3 + 0], __ldg(centres + (long long)v * 3 + 0)), voxel_size), 0.5f);
+    const float py = __fadd_rn(__fdiv_rn(__fsub_rn(xyz[s * 3 + 1], __ldg(centres + (long long)v * 3 + 1)), voxel_size), 0.5f);
+    const float pz = __fadd_rn(__fdiv_rn(__fsub_rn(xyz[s * 3 + 2], __ldg(centres + (long long)v * 3 + 2)), voxel_size), 0.5f);
+    float w[8];
+    corner_weights(px, py, pz, w);
+    const int4 k0 = __ldg(reinterpret_cast<const int4*>(feats + (long long)v * 8));
+    const int4 k1 = __ldg(reinterpret_cast<const int4*>(feats + (long long)v * 8) + 1);
+    const int key[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+    float4 e[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) e[j] = __ldg(reinterpret_cast<const float4*>(values + (long long)key[j] * 32) + sub);
+    float4 acc = make_float4(w[0] * e[0].x, w[0] * e[0].y, w[0] * e[0].z, w[0] * e[0].w);
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+      acc.x = fmaf(w[j], e[j].x, acc.x);
+      acc.y = fmaf(w[j], e[j].y, acc.y);
+      acc.z = fmaf(w[j], e[j].z, acc.z);
+      acc.w = fmaf(w[j], e[j].w, acc.w);
+    }
+    reinterpret_cast<float4*>(out + s * 32)[sub] = acc;
+  }
+}
+
+// generic D: one warp per sample, lane strides over the D dims.
+__global__ void __launch_bounds__(256)
+trilinear_fwd_generic_kernel(long long M, int D, const int* __restrict__ sampled_idx, const float* __restrict__ xyz,
+                             const int* __restrict__ feats, const float* __restrict__ centres,
+                             const float* __restrict__ values, float voxel_size, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  for (long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < M;
+       s += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int v = sampled_idx[s];
+    const float px = __fadd_rn(__fdiv_rn(__fsub_rn(xyz[s * 3 + 0], centres[(long long)v * 3 + 0]), voxel_size), 0.5f);
+    const float py = __fadd_rn(__fdiv_rn(__fsub_rn(xyz[s * 3 + 1], centres[(long long)v * 3 + 1]), voxel_size), 0.5f);
+    const float pz = __fadd_rn(__fdiv_rn(__fsub_rn(xyz[s * 3 + 2], centres[(long long)v * 3 + 2]), voxel_size), 0.5f);
+    float w[8];
+    corner_weights(px, py, pz, w);
+    int key[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) key[j] = feats[(long long)v * 8 + j];
+    for (int d = lane; d < D; d += 32) {
+      float acc = w[0] * values[(long long)key[0] * D + d];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) acc = fmaf(w[j], values[(long long)key[j] * D + d], acc);
+      out[s * D + d] = acc;
+    }
+  }
+}
+
+// Backward, D == 32. Each 8-lane group walks a run of `RUN` consecutive samples and keeps the 8 corner
+// gradients (8 x float4 per lane) in registers while the voxel id does not change; one vectorised
+// reduction per corner per run segment. grad_xyz (optional) needs the corner rows again:
+//   d emb_d / d xyz_a = (1 / voxel_size) * sum_j (d w_j / d p_a) * E_j[d]
+constexpr int kTriRun = 8;
+
+__global__ void __launch_bounds__(256)
+trilinear_bwd_d32_kernel(long long M, const int* __restrict__ sampled_idx, const float* __restrict__ xyz,
+                         const int* __restrict__ feats, const float* __restrict__ centres,
+                         const float* __restrict__ values, float voxel_size, const float* __restrict__ grad_out,
+                         float* __restrict__ grad_values, float* __restrict__ grad_xyz) {
+  const int sub = threadIdx.x & 7;
+  const unsigned gmask = 0xffu << (threadIdx.x & 24);
+  const long long n_runs = (M + kTriRun - 1) / kTriRun;
+  for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < n_runs;
+       r += ((long long)gridDim.x * blockDim.x) >> 3) {
+    const long long s0 = r * kTriRun;
+    const long long s1 = min(M, s0 + kTriRun);
+    int cur = -1;
+    int key[8];
+    float4 acc[8];
+    for (long long s = s0; s < s1; ++s) {
+      const int v = sampled_idx[s];
+      if (v != cur) {
+        if (cur >= 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) red_add_v4(grad_values + (long long)key[j] * 32 + sub * 4, acc[j]);
+        }
+        cur = v;
+        const int4 k0 = __ldg(reinterpret_cast<const int4*>(feats + (long long)v * 8));
+        const int4 k1 = __ldg(reinterpret_cast<const int4*>(feats + (long long)v * 8) + 1);
+        key[0] = k0.x; key[1] = k0.y; key[2] = k0.z; key[3] = k0.w;
+        key[4] = k1.x; key[5] = k1.y; key[6] = k1.z; key[7] = k1.w;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const float px = __fadd_rn(__fdiv_rn(__fsub_rn(xyz[s * 3 + 0], __ldg(centres + (long long)v * 3 + 0)), voxel_size), 0.5f);
+      const float py = __fadd_rn(__fdiv_rn(__fsub_rn(xyz[s * 3 + 1], __ldg(centres + (long long)v * 3 + 1)), voxel_size), 0.5f);
+      const float pz = __fadd_rn(__fdiv_rn(__fsub_rn(xyz[s * 3 + 2], __ldg(centres + (long long)v * 3 + 2)), voxel_size), 0.5f);
+      float w[8];
+      corner_weights(px, py, pz, w);
+      const float4 g = __ldg(reinterpret_cast<const float4*>(grad_out + s * 32) + sub);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j].x = fmaf(w[j], g.x, acc[j].x);
+        acc[j].y = fmaf(w[j], g.y, acc[j].y);
+        acc[j].z = fmaf(w[j], g.z, acc[j].z);
+        acc[j].w = fmaf(w[j], g.w, acc[j].w);
+      }
+      if (grad_xyz != nullptr) {
+        const float ax[2] = {1.0f - px, px}, ay[2] = {1.0f - py, py}, az[2] = {1.0f - pz, pz};
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 e = __ldg(reinterpret_cast<const float4*>(values + (long long)key[j] * 32) + sub);
+          const float dot = g.x * e.x + g.y * e.y + g.z * e.z + g.w * e.w;
+          const float sx = ((j >> 2) & 1) ? 1.f : -1.f, sy = ((j >> 1) & 1) ? 1.f : -1.f, sz = (j & 1) ? 1.f : -1.f;
+          gx = fmaf(sx * ay[(j >> 1) & 1] * az[j & 1], dot, gx);
+          gy = fmaf(sy * ax[(j >> 2) & 1] * az[j & 1], dot, gy);
+          gz = fmaf(sz * ax[(j >> 2) & 1] * ay[(j >> 1) & 1], dot, gz);
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {  // reduce over the 8 lanes of this sample only
+          gx += __shfl_xor_sync(gmask, gx, o);
+          gy += __shfl_xor_sync(gmask, gy, o);
+          gz += __shfl_xor_sync(gmask, gz, o);
+        }
+        if (sub < 3) grad_xyz[s * 3 + sub] = (sub == 0 ? gx : (sub == 1 ? gy : gz)) / voxel_size;
+      }
+    }
+    if (cur >= 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red_add_v4(grad_values + (long long)key[j] * 32 + sub * 4, acc[j]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+trilinear_bwd_generic_kernel(long long M, int D, const int* __restrict__ sampled_idx, const float* __restrict__ xyz,
+                             const int* __restrict__ feats, const float* __restrict__ centres,
+                             const float* __restrict__ values, float voxel_size, const float* __restrict__ grad_out,
+                             float* __restrict__ grad_values, float* __restrict__ grad_xyz) {
+  const int lane = threadIdx.x & 31;
+  for (long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < M;
+       s += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int v = sampled_idx[s];
+    const float px = __fadd_rn(__fdiv_rn(__fsub_rn(xyz[s * 3 + 0], centres[(long long)v * 3 + 0]), voxel_size), 0.5f);
+    const float py = __fadd_rn(__fdiv_rn(__fsub_rn(xyz[s * 3 + 1], centres[(long long)v * 3 + 1]), voxel_size), 0.5f);
+    const float pz = __fadd_rn(__fdiv_rn(__fsub_rn(xyz[s * 3 + 2], centres[(long long)v * 3 + 2]), voxel_size), 0.5f);
+    float w[8];
+    corner_weights(px, py, pz, w);
+    const float ax[2] = {1.0f - px, px}, ay[2] = {1.0f - py, py}, az[2] = {1.0f - pz, pz};
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float g = grad_out[s * D + d];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const long long row = (long long)feats[(long long)v * 8 + j] * D + d;
+        atomicAdd(grad_values + row, w[j] * g);
+        if (grad_xyz != nullptr) {
+          const float dot = g * values[row];
+          const float sx = ((j >> 2) & 1) ? 1.f : -1.f, sy = ((j >> 1) & 1) ? 1.f : -1.f, sz = (j & 1) ? 1.f : -1.f;
+          gx = fmaf(sx * ay[(j >> 1) & 1] * az[j & 1], dot, gx);
+          gy = fmaf(sy * ax[(j >> 2) & 1] * az[j & 1], dot, gy);
+          gz = fmaf(sz * ax[(j >> 2) & 1] * ay[(j >> 1) & 1], dot, gz);
+        }
+      }
+    }
+    if (grad_xyz != nullptr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        gx += __shfl_xor_sync(NSVF_FULL_MASK, gx, o);
+        gy += __shfl_xor_sync(NSVF_FULL_MASK, gy, o);
+        gz += __shfl_xor_sync(NSVF_FULL_MASK, gz, o);
+      }
+      if (lane < 3) grad_xyz[s * 3 + lane] = (lane == 0 ? gx : (lane == 1 ? gy : gz)) / voxel_size;
+    }
+  }
+}
+
+static int grid_for(long long work_items, int items_per_block, int max_blocks_per_sm) {
+  long long want = (work_items + items_per_block - 1) / items_per_block;
+  long long cap = (long long)num_sms() * max_blocks_per_sm;
+  long long g = want < cap ? want : cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+}  // namespace nsvf
+
+using namespace nsvf;
+
+extern "C" int nsvf_trilinear_embed_fwd(nsvf_stream_t stream_, long long M, int D, const int* sampled_idx,
+                                        const float* sampled_xyz, const int* feats, const float* centres,
+                                        const float* values, float voxel_size, float* out) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSVF_REQUIRE(M >= 0 && D > 0, "trilinear_embed_fwd: bad sizes");
+  if (M == 0) return 0;
+  if (D == 32) {
+    NSVF_REQUIRE((((uintptr_t)values | (uintptr_t)out | (uintptr_t)feats) & 15) == 0,
+                 "trilinear_embed_fwd: values/out/feats must be 16-byte aligned");
+    trilinear_fwd_d32_kernel<<<grid_for(M, 32, 16), 256, 0, stream>>>(M, sampled_idx, sampled_xyz, feats, centres,
+                                                                      values, voxel_size, out);
+  } else {
+    trilinear_fwd_generic_kernel<<<grid_for(M, 8, 16), 256, 0, stream>>>(M, D, sampled_idx, sampled_xyz, feats,
+                                                                         centres, values, voxel_size, out);
+  }
+  NSVF_LAUNCH_OK("trilinear_fwd_kernel");
+  return 0;
+}
+
+extern "C" int nsvf_trilinear_embed_bwd(nsvf_stream_t stream_, long long M, int D, const int* sampled_idx,
+                                        const float* sampled_xyz, const int* feats, const float* centres,
+                                        const float* values, float voxel_size, const float* grad_out,
+                                        float* grad_values, float* grad_xyz) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSVF_REQUIRE(M >= 0 && D > 0, "trilinear_embed_bwd: bad sizes");
+  if (M == 0) return 0;
+  if (D == 32) {
+    NSVF_REQUIRE((((uintptr_t)values | (uintptr_t)grad_out | (uintptr_t)grad_values | (uintptr_t)feats) & 15) == 0,
+                 "trilinear_embed_bwd: values/grad_out/grad_values/feats must be 16-byte aligned");
+    const long long runs = (M + kTriRun - 1) / kTriRun;
+    trilinear_bwd_d32_kernel<<<grid_for(runs, 32, 16), 256, 0, stream>>>(M, sampled_idx, sampled_xyz, feats, centres,
+                                                                         values, voxel_size, grad_out, grad_values,
+                                                                         grad_xyz);
+  } else {
+    trilinear_bwd_generic_kernel<<<grid_for(M, 8, 16), 256, 0, stream>>>(M, D, sampled_idx, sampled_xyz, feats,
+                                                                         centres, values, voxel_size, grad_out,
+                                                                         grad_values, grad_xyz);
+  }
+  NSVF_LAUNCH_OK("trilinear_bwd_kernel");
+  return 0;
+}

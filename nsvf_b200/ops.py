@@ -1,0 +1,119 @@
+"""Differentiable fused operators that replace inline torch code of the reference's modules.
+
+  trilinear_embed(sampled_idx, sampled_xyz, feats, centres, values, voxel_size)
+        = SparseVoxelEncoder.forward's interpolation, fairnr/modules/encoder.py:582-590
+          (trilinear_interp / offset_points, fairnr/data/geometry.py:195-200, 229-238)
+  composite(free_energy, texture, sampled_depth)
+        = the compositing block of VolumeRenderer.forward_chunk, fairnr/modules/renderer.py:193-218
+
+Both run on the C ABI (include/nsvf_b200.h); CUDA float32 tensors only, no fallback.
+"""
+import torch
+from torch.autograd import Function
+
+from . import _lib
+
+_L = _lib.load()
+_p = _lib.ptr
+
+
+def _need_cuda(**tensors):
+    for name, t in tensors.items():
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("nsvf_b200: %s must be a CUDA tensor (there is no CPU path)" % name)
+
+
+def as_int32_feats(feats):
+    """feats is an int64 buffer in the reference (encoder.py:287); the kernels read int32 keys."""
+    return feats if feats.dtype == torch.int32 else feats.to(torch.int32)
+
+
+class TrilinearEmbed(Function):
+    @staticmethod
+    def forward(ctx, sampled_idx, sampled_xyz, feats, centres, values, voxel_size):
+        _need_cuda(sampled_idx=sampled_idx, sampled_xyz=sampled_xyz, feats=feats, centres=centres, values=values)
+        voxel_size = float(voxel_size)
+        idx = sampled_idx.to(torch.int32).contiguous()
+        xyz = sampled_xyz.detach().float().contiguous()
+        feats32 = as_int32_feats(feats).contiguous()
+        centres = centres.detach().float().contiguous()
+        vals = values.detach().float().contiguous()
+        M, D = idx.numel(), vals.shape[-1]
+        out = torch.empty((M, D), dtype=torch.float32, device=vals.device)
+        with torch.cuda.device(vals.device):
+            _lib.check(_L.nsvf_trilinear_embed_fwd(_lib.current_stream(vals.device), M, D, _p(idx), _p(xyz),
+                                                   _p(feats32), _p(centres), _p(vals), voxel_size, _p(out)))
+        ctx.save_for_backward(idx, xyz, feats32, centres, vals)
+        ctx.voxel_size = voxel_size
+        ctx.values_shape = values.shape
+        ctx.mark_non_differentiable()
+        return out.to(values.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, xyz, feats32, centres, vals = ctx.saved_tensors
+        need_values, need_xyz = ctx.needs_input_grad[4], ctx.needs_input_grad[1]
+        if not (need_values or need_xyz):
+            return None, None, None, None, None, None
+        M, D = idx.numel(), vals.shape[-1]
+        g = grad_out.float().contiguous()
+        grad_values = torch.zeros(ctx.values_shape, dtype=torch.float32, device=vals.device)
+        grad_xyz = torch.empty((M, 3), dtype=torch.float32, device=vals.device) if need_xyz else None
+        with torch.cuda.device(vals.device):
+            _lib.check(_L.nsvf_trilinear_embed_bwd(_lib.current_stream(vals.device), M, D, _p(idx), _p(xyz),
+                                                   _p(feats32), _p(centres), _p(vals), ctx.voxel_size, _p(g),
+                                                   _p(grad_values), _p(grad_xyz)))
+        return None, grad_xyz, None, None, (grad_values if need_values else None), None
+
+
+def trilinear_embed(sampled_idx, sampled_xyz, feats, centres, values, voxel_size):
+    """emb[M, D] = sum_j w_j(xyz) * values[feats[idx][j]]  (see include/nsvf_b200.h)."""
+    return TrilinearEmbed.apply(sampled_idx, sampled_xyz, feats, centres, values, voxel_size)
+
+
+class Composite(Function):
+    @staticmethod
+    def forward(ctx, free_energy, texture, sampled_depth):
+        _need_cuda(free_energy=free_energy, texture=texture, sampled_depth=sampled_depth)
+        fe = free_energy.detach().float().contiguous()
+        tex = texture.detach().float().contiguous() if texture is not None else None
+        dep = sampled_depth.detach().float().contiguous()
+        B, K = fe.shape
+        dev = fe.device
+        probs = torch.empty((B, K), dtype=torch.float32, device=dev)
+        depth = torch.empty((B,), dtype=torch.float32, device=dev)
+        missed = torch.empty((B,), dtype=torch.float32, device=dev)
+        colors = torch.empty((B, 3), dtype=torch.float32, device=dev) if tex is not None else None
+        with torch.cuda.device(dev):
+            _lib.check(_L.nsvf_composite_fwd(_lib.current_stream(dev), B, K, _p(fe), _p(tex), _p(dep), _p(probs),
+                                             _p(depth), _p(missed), _p(colors)))
+        ctx.save_for_backward(fe, tex, dep)
+        ctx.has_tex = tex is not None
+        if colors is None:
+            colors = torch.zeros((B, 3), dtype=torch.float32, device=dev)
+        return probs, depth, missed, colors
+
+    @staticmethod
+    def backward(ctx, g_probs, g_depth, g_missed, g_colors):
+        fe, tex, dep = ctx.saved_tensors
+        B, K = fe.shape
+        dev = fe.device
+        need_fe, need_tex = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and ctx.has_tex
+        if not (need_fe or need_tex):
+            return None, None, None
+
+        def c(t):
+            return None if t is None else t.float().contiguous()
+        g_probs, g_depth, g_missed, g_colors = c(g_probs), c(g_depth), c(g_missed), c(g_colors)
+        g_fe = torch.empty((B, K), dtype=torch.float32, device=dev)
+        g_tex = torch.empty((B, K, 3), dtype=torch.float32, device=dev) if need_tex else None
+        with torch.cuda.device(dev):
+            _lib.check(_L.nsvf_composite_bwd(_lib.current_stream(dev), B, K, _p(fe), _p(tex), _p(dep), _p(g_probs),
+                                             _p(g_depth), _p(g_missed), _p(g_colors if ctx.has_tex else None),
+                                             _p(g_fe), _p(g_tex)))
+        return (g_fe if need_fe else None), g_tex, None
+
+
+def composite(free_energy, texture, sampled_depth):
+    """(probs[B,K], depth[B], missed[B], colors[B,3]) from free energy, rgb and sample depths."""
+    return Composite.apply(free_energy, texture, sampled_depth)
