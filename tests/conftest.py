@@ -1,0 +1,30 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `pytest -m gpu`)")
+
+
+@pytest.fixture(scope="session")
+def ref_ext():
+    """The UNMODIFIED reference extension compiled for sm_100a (oracle/_ref/ref_ext.so), or skip."""
+    from oracle import build_ref
+    mod = build_ref.load()
+    if mod is None:
+        pytest.skip("oracle/_ref/ref_ext.so not built (run `python oracle/build_ref.py` where /root/reference exists)")
+    return mod
+
+
+@pytest.fixture(scope="session")
+def cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")

@@ -1,0 +1,185 @@
+"""GPU parity of ray/voxel intersection: ours (C ABI) vs the reference CUDA kernels (oracle/_ref) vs the
+CPU oracle.  Integer outputs bit-exact; depths are produced by the identical fp32 op sequence, so they
+are compared for equality too (torch.equal treats -0.0 == +0.0)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import wrappers
+from nsvf_b200 import synthetic
+from nsvf_b200 import clib
+from nsvf_b200.clib import _ext as ours
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp3(a, b, what):
+    for x, y, nm in zip(a, b, ("idx", "min_depth", "max_depth")):
+        x, y = torch.as_tensor(x).cpu(), torch.as_tensor(y).cpu()
+        assert x.shape == y.shape, (what, nm, x.shape, y.shape)
+        assert torch.equal(x, y), "%s: %s differs in %d of %d entries" % (what, nm, int((x != y).sum()), x.numel())
+
+
+def _oracle_aabb(rs, rd, pts, vs, n_max):
+    inv = helpers.ref_rcp(rd)
+    return oracle.aabb_intersect(rs.cpu().numpy(), rd.cpu().numpy(), pts.cpu().numpy(), vs, n_max, inv.cpu().numpy())
+
+
+@pytest.mark.parametrize("name,n_rays,n_max", [("C1", 8192, 60), ("C1", 4096, 5), ("C2", 8192, 60)])
+def test_aabb_level1_vs_reference_and_oracle(cuda, ref_ext, name, n_rays, n_max):
+    scene = synthetic.make_scene(name)
+    pts, _, _ = helpers.scene_tensors(scene, cuda)
+    o, d = helpers.rays_for(name, n_rays, 1, cuda)
+    B = 4
+    rs, rd = o.view(B, -1, 3).contiguous(), d.view(B, -1, 3).contiguous()
+    ptsB = pts.unsqueeze(0).expand(B, -1, -1).contiguous()
+    mine = ours.aabb_intersect(rs, rd, ptsB, scene.voxel_size, n_max)
+    ref = ref_ext.aabb_intersect(rs, rd, ptsB, scene.voxel_size, n_max)
+    _cmp3(mine, ref, "ours vs reference CUDA")
+    _cmp3(mine, _oracle_aabb(rs, rd, ptsB, scene.voxel_size, n_max), "ours vs CPU oracle")
+    assert int((mine[0] >= 0).sum()) > n_rays  # the case is not vacuous
+    # shared voxel set (no replication) gives the same answer
+    _cmp3(ours.aabb_intersect(rs, rd, pts, scene.voxel_size, n_max, shared_points=True), mine, "shared vs replicated")
+
+
+def test_aabb_multilevel_hierarchy_vs_reference(cuda, ref_ext):
+    """~14k and ~112k voxels: 3- and 4-level hierarchies, upper levels staged by TMA, level 0/1 from global."""
+    for times, n_max, n_rays in ((1, 90, 4096), (2, 135, 2048)):
+        pts0 = synthetic.carve_shell(synthetic.bbox_voxels([-2.4] * 3, [2.4] * 3, 0.4))
+        p, vs = synthetic.split_points(pts0, 0.4, times)
+        p[:, 0] += np.float32(vs / 10)  # the encoder's precompute shift (encoder.py:383)
+        pts = torch.from_numpy(p).to(cuda)
+        rs, rd = synthetic.camera_rays(64, 64, 1, device=cuda)
+        rs = rs.expand_as(rd)[:, :n_rays].contiguous()
+        rd = rd[:, :n_rays].contiguous()
+        mine = ours.aabb_intersect(rs, rd, pts.unsqueeze(0), vs, n_max)
+        ref = ref_ext.aabb_intersect(rs, rd, pts.unsqueeze(0).contiguous(), vs, n_max)
+        _cmp3(mine, ref, "ours vs reference CUDA, n=%d" % len(p))
+        assert int((mine[0] >= 0).sum(-1).max()) > 20
+
+
+def test_aabb_truncation_keeps_lowest_indices(cuda, ref_ext):
+    scene = synthetic.make_scene("C1")
+    pts, _, _ = helpers.scene_tensors(scene, cuda)
+    o, d = helpers.rays_for("C1", 2048, 3, cuda)
+    full = ours.aabb_intersect(o[None], d[None], pts[None], scene.voxel_size, 60)[0][0]
+    for n_max in (1, 2, 7, 33):
+        cut = ours.aabb_intersect(o[None], d[None], pts[None], scene.voxel_size, n_max)[0][0]
+        assert torch.equal(cut, full[:, :n_max])
+        _cmp3(ours.aabb_intersect(o[None], d[None], pts[None], scene.voxel_size, n_max),
+              ref_ext.aabb_intersect(o[None].contiguous(), d[None].contiguous(), pts[None].contiguous(),
+                                     scene.voxel_size, n_max), "n_max=%d" % n_max)
+
+
+def test_aabb_axis_aligned_and_degenerate_rays(cuda, ref_ext):
+    """KAT-3 plus the NaN paths of the slab test: zero / negative-zero direction components, origins
+    exactly on voxel face planes, origins inside voxels."""
+    scene = synthetic.make_scene("C1")
+    pts, _, _ = helpers.scene_tensors(scene, cuda)
+    y0, z0 = -0.875 + 0.25 * 2, -0.875 + 0.25 * 5
+    rays = [
+        ((-3.0, y0, z0), (1.0, 0.0, 0.0)),
+        ((-3.0, y0, z0), (1.0, -0.0, 0.0)),
+        ((-3.0, y0 + 0.125, z0), (1.0, 0.0, 0.0)),        # on a face plane, +0 direction
+        ((-3.0, y0 + 0.125, z0), (1.0, -0.0, -0.0)),      # on a face plane, -0 direction
+        ((-3.0, y0 - 0.125, z0 + 0.125), (1.0, 0.0, -0.0)),
+        ((3.0, y0, z0), (-1.0, 0.0, 0.0)),
+        ((y0, 3.0, z0), (0.0, -1.0, 0.0)),
+        ((y0, z0, -3.0), (-0.0, 0.0, 1.0)),
+        ((0.0, 0.0, 0.0), (0.0, 0.0, 1.0)),               # starts inside, on lattice planes
+        ((0.125, 0.125, 0.125), (1.0, 1.0, 1.0)),
+        ((-3.0, -3.0, -3.0), (1.0, 1.0, 1.0)),            # exactly through corners
+        ((-3.0, y0, z0), (1.0, 1e-30, -1e-30)),
+        ((-3.0, y0, z0), (-1.0, 0.0, 0.0)),               # pointing away
+        ((-3.0, y0, z0), (float("nan"), 0.0, 0.0)),
+    ]
+    rs = torch.tensor([r[0] for r in rays], dtype=torch.float32, device=cuda)[None].contiguous()
+    rd = torch.tensor([r[1] for r in rays], dtype=torch.float32, device=cuda)[None].contiguous()
+    mine = ours.aabb_intersect(rs, rd, pts[None].contiguous(), scene.voxel_size, 60)
+    ref = ref_ext.aabb_intersect(rs, rd, pts[None].contiguous(), scene.voxel_size, 60)
+    _cmp3(mine, ref, "degenerate rays vs reference CUDA")
+    _cmp3(mine, _oracle_aabb(rs, rd, pts[None], scene.voxel_size, 60), "degenerate rays vs oracle")
+    # KAT-3: the first ray crosses the 8 voxels of one x-row, entry/exit = (c_x -+ 0.125) + 3
+    idx = mine[0][0, 0]
+    hit = idx[idx >= 0]
+    assert hit.numel() == 8
+    cx = pts[hit.long(), 0]
+    assert torch.equal(mine[1][0, 0, :8], (cx - 0.125) + 3.0)
+    assert torch.equal(mine[2][0, 0, :8], (cx + 0.125) + 3.0)
+
+
+def test_aabb_edge_shapes(cuda):
+    scene = synthetic.make_scene("C2")
+    pts, _, _ = helpers.scene_tensors(scene, cuda)
+    e = torch.empty((1, 0, 3), device=cuda)
+    out = ours.aabb_intersect(e, e, pts[None].contiguous(), 0.4, 60)
+    assert out[0].shape == (1, 0, 60)
+    o, d = helpers.rays_for("C2", 33, 5, cuda)   # ragged: not a multiple of anything
+    far = pts + 100.0
+    idx, dmin, dmax = ours.aabb_intersect(o[None].contiguous(), d[None].contiguous(), far[None].contiguous(), 0.4, 7)
+    assert int((idx != -1).sum()) == 0 and float(dmin.abs().sum() + dmax.abs().sum()) == 0.0
+    one = ours.aabb_intersect(o[None].contiguous(), d[None].contiguous(), pts[None, :1].contiguous(), 0.4, 3)
+    assert one[0].shape == (1, 33, 3)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        ours.aabb_intersect(o[None].cpu(), d[None].cpu(), pts[None].cpu(), 0.4, 3)
+    with pytest.raises(RuntimeError, match="must be a float tensor"):
+        ours.aabb_intersect(o[None].double(), d[None].double(), pts[None].double(), 0.4, 3)
+    with pytest.raises(RuntimeError, match="must be a contiguous tensor"):
+        ours.aabb_intersect(o[None].expand(2, -1, -1), d[None].expand(2, -1, -1), pts[None].expand(2, -1, -1), 0.4, 3)
+
+
+def test_aabb_level2_wrapper_matches_reference_wrapper(cuda, ref_ext):
+    """fairnr.clib.aabb_ray_intersect semantics (ray tiling / padding / voxel replication) end to end."""
+    scene = synthetic.make_scene("C1")
+    pts, _, _ = helpers.scene_tensors(scene, cuda)
+    o, d = helpers.rays_for("C1", 5000, 7, cuda)     # 5000 is not a multiple of G=2048: wrap padding
+    S = 1   # the reference wrapper's points.expand(S*G, ...) only works for a single shape
+    rs, rd, P = o[None].contiguous(), d[None].contiguous(), pts[None].contiguous()
+    vs, mh = torch.tensor(scene.voxel_size, device=cuda), torch.tensor(60.0, device=cuda)   # 0-dim tensor scalars
+    mine = clib.aabb_ray_intersect(vs, mh, P, rs, rd)
+    ref = wrappers.aabb_ray_intersect(ref_ext, float(vs), int(mh), P, rs, rd)
+    _cmp3(mine, ref, "Level-2 aabb_ray_intersect")
+    assert mine[0].shape == (S, 5000, 60) and not mine[0].requires_grad
+
+
+def _svo_inputs(name_or_pts, vs, cuda):
+    pts = torch.from_numpy(name_or_pts).to(cuda)
+    centers, children = helpers.easy_octree(pts, vs, ours.build_octree)
+    return pts, centers.contiguous(), children.contiguous()
+
+
+@pytest.mark.parametrize("times,n_max,n_rays", [(0, 60, 4096), (1, 90, 4096), (2, 135, 2048), (1, 4, 2048)])
+def test_svo_level1_vs_reference_and_oracle(cuda, ref_ext, times, n_max, n_rays):
+    pts0 = synthetic.carve_shell(synthetic.bbox_voxels([-2.4] * 3, [2.4] * 3, 0.4))
+    p, vs = synthetic.split_points(pts0, 0.4, times)
+    pts, centers, children = _svo_inputs(p, vs, cuda)
+    rs, rd = synthetic.camera_rays(64, 64, 2, device=cuda)
+    rs = rs.expand_as(rd)[:, :n_rays].contiguous()
+    rd = rd[:, :n_rays].contiguous()
+    cB = centers[None].expand(2, -1, -1).contiguous()
+    chB = children[None].expand(2, -1, -1).contiguous()
+    mine = ours.svo_intersect(rs, rd, cB, chB, vs, n_max)
+    ref = ref_ext.svo_intersect(rs, rd, cB, chB, vs, n_max)
+    _cmp3(mine, ref, "svo ours vs reference CUDA (T=%d)" % centers.shape[0])
+    inv = helpers.ref_rcp(rd)
+    orc = oracle.svo_intersect(rs.cpu().numpy(), rd.cpu().numpy(), cB.cpu().numpy(), chB.cpu().numpy(), vs, n_max,
+                               inv.cpu().numpy())
+    _cmp3(mine, orc, "svo ours vs CPU oracle")
+    _cmp3(ours.svo_intersect(rs, rd, centers, children, vs, n_max, shared_tree=True), mine, "shared vs replicated")
+    assert int((mine[0] >= 0).sum()) > n_rays
+    if n_max >= 60:
+        # property: leaf k == voxel k, and (untruncated) the svo hit SET equals aabb's on the same centres
+        a = ours.aabb_intersect(rs, rd, pts, vs, n_max, shared_points=True)[0]
+        assert torch.equal(a.sort(-1)[0], mine[0].sort(-1)[0])
+
+
+def test_svo_level2_wrapper_matches_reference_wrapper(cuda, ref_ext):
+    pts0 = synthetic.carve_shell(synthetic.bbox_voxels([-2.4] * 3, [2.4] * 3, 0.4))
+    pts, centers, children = _svo_inputs(pts0, 0.4, cuda)
+    rs, rd = synthetic.camera_rays(50, 50, 1, device=cuda)
+    rs = rs.expand_as(rd).contiguous()
+    mine = clib.svo_ray_intersect(0.4, 60, centers[None], children[None], rs, rd)
+    ref = wrappers.svo_ray_intersect(ref_ext, 0.4, 60, centers[None], children[None], rs, rd)
+    _cmp3(mine, ref, "Level-2 svo_ray_intersect")

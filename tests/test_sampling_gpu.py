@@ -1,0 +1,125 @@
+"""GPU parity of ray sampling: ours vs the reference CUDA kernels vs the CPU oracle, on inputs produced by
+the real pipeline (intersect -> sort -> probs/steps), with the noise supplied as an identical tensor."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import wrappers
+from nsvf_b200 import synthetic, clib
+from nsvf_b200.clib import _ext as ours
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _pipeline(cuda, name, n_rays, seed, n_max=None, keep_misses=False):
+    scene = synthetic.make_scene(name)
+    pts, _, _ = helpers.scene_tensors(scene, cuda)
+    o, d = helpers.rays_for(name, n_rays, seed, cuda)
+    n_max = n_max or scene.max_hits
+    idx, dmin, dmax = ours.aabb_intersect(o[None].contiguous(), d[None].contiguous(), pts, scene.voxel_size, n_max,
+                                          shared_points=True)
+    idx, dmin, dmax, hits = wrappers.sort_hits(idx[0], dmin[0], dmax[0])
+    if not keep_misses:
+        idx, dmin, dmax = idx[hits], dmin[hits], dmax[hits]
+    probs, steps = wrappers.probs_and_steps(idx, dmin, dmax, scene.step_size)
+    return scene, idx.contiguous(), dmin.contiguous(), dmax.contiguous(), probs.contiguous(), steps.contiguous()
+
+
+def _eq3(a, b, what):
+    for x, y, nm in zip(a, b, ("sampled_idx", "sampled_depth", "sampled_dists")):
+        x, y = torch.as_tensor(x).cpu(), torch.as_tensor(y).cpu()
+        assert x.shape == y.shape, (what, nm, x.shape, y.shape)
+        assert torch.equal(x, y), "%s: %s differs in %d of %d entries" % (what, nm, int((x != y).sum()), x.numel())
+
+
+@pytest.mark.parametrize("name,n_rays,n_max,fixed", [("C1", 8000, 60, -1.0), ("C2", 6000, 60, -1.0),
+                                                     ("C1", 3000, 4, -1.0), ("C1", 3000, 60, 0.02)])
+def test_inverse_cdf_level1_vs_reference_and_oracle(cuda, ref_ext, name, n_rays, n_max, fixed):
+    scene, idx, dmin, dmax, probs, steps = _pipeline(cuda, name, n_rays, 11, n_max)
+    N, P = idx.shape
+    G = 8
+    R = N // G
+    cut = lambda t: t[:G * R].reshape(G, R, *t.shape[1:]).contiguous()
+    idx, dmin, dmax, probs, steps = map(cut, (idx, dmin, dmax, probs, steps))
+    max_steps = int(steps.ceil().max()) + P
+    torch.manual_seed(3)
+    noise = torch.zeros(G, R, max_steps, device=cuda).uniform_().clamp(min=0.001, max=0.999)
+    mine = ours.inverse_cdf_sampling(idx, dmin, dmax, noise, probs, steps, fixed)
+    ref = ref_ext.inverse_cdf_sampling(idx, dmin, dmax, noise, probs, steps, fixed)
+    if n_max == 4:
+        # saturated rays (all max_hits bins valid): the reference's extra sample reads the NEXT ray's slot 0
+        # and, for the very last ray, memory past the tensor (UB). Compare all rows but the last.
+        mine = [t.reshape(G * R, -1)[:-1] for t in mine]
+        ref = [t.reshape(G * R, -1)[:-1] for t in ref]
+        _eq3(mine, ref, "inverse_cdf ours vs reference CUDA (saturated)")
+        return
+    _eq3(mine, ref, "inverse_cdf ours vs reference CUDA")
+    orc = oracle.inverse_cdf_sampling(*[t.cpu().numpy() for t in (idx, dmin, dmax, noise, probs, steps)], fixed)
+    _eq3(mine, orc, "inverse_cdf ours vs CPU oracle")
+    n = (mine[0] != -1).sum(-1)
+    assert int(n.max()) > 20 and int(n.min()) >= 1
+    # property: every sample lies inside the [min,max] span of its ray and inside its own voxel's bin
+    sidx, sdepth, sdist = mine
+    valid = sidx != -1
+    lo = dmin[..., :1].expand_as(sdepth)
+    hi = dmax.masked_fill(idx.eq(-1), 0).max(-1, keepdim=True)[0].expand_as(sdepth)
+    assert bool(((sdepth >= lo - 1e-4) & (sdepth <= hi + 1e-4))[valid].all())
+
+
+def test_inverse_cdf_level2_wrapper_matches_reference_wrapper(cuda, ref_ext):
+    """fairnr.clib.inverse_cdf_sampling end to end: padding to a multiple of 200 with copies of ray 0, [200,R,P]
+    tiling, 800-column chunks, identical noise draw under the same seed, trimming to max_len."""
+    for n_rays, det in ((8192, False), (8192, True), (1234, False)):
+        scene, idx, dmin, dmax, probs, steps = _pipeline(cuda, "C1", n_rays, 5)
+        torch.manual_seed(17)
+        mine = clib.inverse_cdf_sampling(idx, dmin, dmax, probs, steps, -1, det)
+        torch.manual_seed(17)
+        ref = wrappers.inverse_cdf_sampling(ref_ext, idx, dmin, dmax, probs, steps, -1, det)
+        _eq3(mine, ref, "Level-2 inverse_cdf_sampling det=%s N=%d" % (det, idx.shape[0]))
+
+
+def test_inverse_cdf_level2_many_chunks(cuda, ref_ext):
+    """> 160 000 rays -> R > 800: exercises the reference wrapper's column chunk loop (ray_chunk quirks)."""
+    scene = synthetic.make_scene("C2")
+    pts, _, _ = helpers.scene_tensors(scene, cuda)
+    rs, rd = synthetic.camera_rays(450, 450, 1, radius=3.0, device=cuda)
+    rs = rs.expand_as(rd).contiguous()
+    idx, dmin, dmax = ours.aabb_intersect(rs, rd, pts, scene.voxel_size, 20, shared_points=True)
+    idx, dmin, dmax, hits = wrappers.sort_hits(idx[0], dmin[0], dmax[0])
+    idx, dmin, dmax = idx[hits].contiguous(), dmin[hits].contiguous(), dmax[hits].contiguous()
+    assert idx.shape[0] > 160000
+    probs, steps = wrappers.probs_and_steps(idx, dmin, dmax, scene.step_size)
+    mine = clib.inverse_cdf_sampling(idx, dmin, dmax, probs, steps, -1, True)
+    ref = wrappers.inverse_cdf_sampling(ref_ext, idx, dmin, dmax, probs, steps, -1, True)
+    _eq3(mine, ref, "Level-2 inverse_cdf_sampling, chunked")
+
+
+@pytest.mark.parametrize("name,n_rays", [("C1", 4096), ("C2", 4096)])
+def test_uniform_level1_vs_reference_and_oracle(cuda, ref_ext, name, n_rays):
+    scene, idx, dmin, dmax, _, _ = _pipeline(cuda, name, n_rays, 23)
+    N, P = idx.shape
+    G = 16
+    R = N // G
+    cut = lambda t: t[:G * R].reshape(G, R, *t.shape[1:]).contiguous()
+    idx, dmin, dmax = map(cut, (idx, dmin, dmax))
+    span = float((dmax.masked_fill(idx.eq(-1), 0).max(-1)[0] - dmin[..., 0]).max())
+    max_steps = int(span / scene.step_size) + 2 * P
+    torch.manual_seed(4)
+    noise = torch.zeros(G, R, max_steps, device=cuda).uniform_().clamp(min=0.001, max=0.999)
+    mine = ours.uniform_ray_sampling(idx, dmin, dmax, noise, scene.step_size, max_steps)
+    ref = ref_ext.uniform_ray_sampling(idx, dmin, dmax, noise, scene.step_size, max_steps)
+    assert torch.equal(mine[0], ref[0]), "uniform sampled_idx differs from the reference CUDA kernel"
+    valid = mine[0] != -1      # beyond the compacted prefix the reference leaves stale merge values
+    assert torch.equal(mine[1][valid], ref[1][valid]) and torch.equal(mine[2][valid], ref[2][valid])
+    orc = oracle.uniform_ray_sampling(*[t.cpu().numpy() for t in (idx, dmin, dmax, noise)], scene.step_size, max_steps)
+    _eq3(mine, orc, "uniform ours vs CPU oracle")
+    assert int(valid.sum(-1).max()) > 20
+
+
+def test_uniform_level2_wrapper_runs(cuda):
+    scene, idx, dmin, dmax, _, _ = _pipeline(cuda, "C1", 1000, 2)
+    sidx, sdepth, sdist = clib.uniform_ray_sampling(idx, dmin, dmax, scene.step_size, 3.0, True)
+    assert sidx.shape[0] == idx.shape[0] and sidx.shape == sdepth.shape == sdist.shape
+    assert int((sidx != -1).sum(-1).max()) == sidx.shape[1]
