@@ -1,0 +1,463 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config, one JSON line on stdout (rank 0).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a kernels)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port, host cores)
+
+Workload (config.workload = "C2"): the `nsvf_base` training step of BASELINE.json configs[1] —
+Synthetic-NeRF-shaped scene (bbox centres +-1.2, voxel 0.4 -> 343 voxels, step = voxel/8, max_hits 60),
+4 views x 800x800 rays per GPU intersected (`--no-sampling-at-reader`), 4 x 2048 rays sampled from the hit mask
+and marched (inverse-CDF sampling -> trilinear interpolation -> field MLP -> compositing), loss, backward, Adam.
+Random-init weights, synthetic cameras / targets (no datasets offline).  The field MLP (545 297 parameters,
+fp32) runs on torch/cuBLAS as BASELINE.json prescribes; everything else is the hand-written path.
+
+  value  = marched rays per second, whole job (all ranks), inputs resident in HBM
+  e2e    = same, through the public pipeline call with HOST (pinned) rays + targets copied in every step and the
+           loss read back
+  roofline = the dominant hand-written kernel (aabb_intersect_kernel), timed live with CUDA events recorded
+           around the launch inside the timed steps (nsvf_profile_kernel hook)
+  cpu_baseline = the oracle port (oracle/, C + OpenMP + torch-CPU MLP) on a bounded sample of the same step
+  frame  = ms per 800x800 frame on the C3 scene (~112k voxels, eval, early termination 0.01), extra key
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+VIEWS, RES, PIX_PER_VIEW = 4, 800, 2048
+METRIC = "rays/s (intersect+sample+composite), nsvf_base training step"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-frame", action="store_true", help="skip the C3 full-frame extra")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-fraction", type=int, default=16, help="CPU arms run 1/FRACTION of the rays per step")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks: sampled DURING the timed region through NVML (same counters nvidia-smi prints)
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+        while not self._halt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# synthetic inputs
+# ------------------------------------------------------------------------------------------------------
+def make_batches(n_batches, rank, pinned):
+    from nsvf_b200 import synthetic
+    out = []
+    for b in range(n_batches):
+        rs, rd = synthetic.camera_rays(RES, RES, VIEWS, radius=3.2, seed=137 * b + rank)   # unique_seed = step*137+rank
+        g = torch.Generator().manual_seed(1000 + 137 * b + rank)
+        target = torch.rand(VIEWS * RES * RES, 3, generator=g) * 2 - 1                    # min_color = -1 range
+        rs, rd = rs[None, :, None, 0, :].contiguous(), rd[None].contiguous()               # [1,V,1,3], [1,V,P,3]
+        if pinned:
+            rs, rd, target = rs.pin_memory(), rd.pin_memory(), target.pin_memory()
+        out.append((rs, rd, target))
+    return out
+
+
+def build_model(device, scene_name="C2", train=True, field="mlp", tolerance=0.0, chunk=64, sigma_bias=0.0, seed=0):
+    from nsvf_b200 import synthetic
+    from nsvf_b200.encoder import SparseVoxelEncoder
+    from nsvf_b200.field import RadianceField, TrivialField
+    from nsvf_b200.renderer import VolumeRenderer
+    from nsvf_b200.pipeline import NSVFPipeline
+    torch.manual_seed(seed)
+    scene = synthetic.make_scene(scene_name)
+    enc = SparseVoxelEncoder(scene.points, scene.voxel_size, max_hits=scene.max_hits)
+    fld = RadianceField(sigma_bias=sigma_bias) if field == "mlp" else TrivialField()
+    ren = VolumeRenderer(chunk_size=chunk, discrete_regularization=train, raymarching_tolerance=tolerance)
+    pipe = NSVFPipeline(enc, fld, ren, pixel_per_view=PIX_PER_VIEW if train else 0).to(device)
+    return pipe.train(train), scene
+
+
+def loss_fn(out, target):
+    sel = target if out["sampled"] is None else target[out["sampled"].reshape(-1)]
+    rgb = ((out["colors"] - sel) ** 2).mean() * 128.0          # --color-weight 128
+    alpha = (out["missed"] ** 2).mean()                        # --alpha-weight 1 (all sampled rays hit the object mask)
+    return rgb + alpha
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from nsvf_b200 import _lib
+    L = _lib.load()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    pipe, scene = build_model(dev)
+    model = pipe
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        model = DDP(pipe, device_ids=[local])   # NCCL all-reduce of values.weight.grad + MLP grads
+    opt = torch.optim.Adam([p for p in pipe.parameters() if p.requires_grad], lr=1e-3, betas=(0.9, 0.999))
+    host = make_batches(2, rank, pinned=True)
+    resident = [tuple(t.to(dev) for t in b) for b in host]
+    staging = tuple(torch.empty_like(t, device=dev) for t in host[0])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def step(rs, rd, target):
+        flush.zero_()
+        out = model(rs, rd)
+        loss = loss_fn(out, target)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss, out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, from_host):
+        """n steps; returns (ms total via CUDA events on the launching stream, list of dominant-kernel ms)."""
+        k_evs = []
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); b.record()                                    # materialise the cudaEvent_t handles
+            _lib.check(L.nsvf_profile_kernel(b"aabb_intersect_kernel", a.cuda_event, b.cuda_event))
+            if from_host:
+                hb = host[i % len(host)]
+                for d, s in zip(staging, hb):
+                    d.copy_(s, non_blocking=True)                     # H2D from pinned memory, inside the timed region
+                loss, out = step(*staging)
+                loss.item()                                           # D2H read of the step's result
+            else:
+                loss, out = step(*resident[i % len(resident)])
+            k_evs.append((a, b))
+        e1.record()
+        barrier()
+        L.nsvf_profile_kernel(None, None, None)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, [a.elapsed_time(b) for a, b in k_evs], float(loss.item()), out
+
+    timed(max(args.warmup, 3), False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = L.nsvf_kernel_launches()
+    ms, kms, loss_val, out = timed(args.steps, False)
+    launches = L.nsvf_kernel_launches() - launches0
+    clocks = sampler.stop()
+    timed(1, True)
+    ms_e2e, _, _, _ = timed(args.steps, True)
+
+    rays_marched = VIEWS * PIX_PER_VIEW
+    rays_intersected = VIEWS * RES * RES
+    value = world * rays_marched * args.steps / (ms / 1e3)
+    e2e_value = world * rays_marched * args.steps / (ms_e2e / 1e3)
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+
+    # roofline of the dominant hand-written kernel: algorithmic bytes = 24 B/ray in + 12*P B/ray out (+ scene once)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+    P = scene.max_hits
+    alg_bytes = rays_intersected * (24 + 12 * P) + 12 * scene.n
+    k_ms = float(np.mean(kms))
+    achieved = alg_bytes / (k_ms / 1e3) / 1e9
+    roofline = {"kernel": "aabb_intersect_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_launch": alg_bytes,
+                "share_of_step": round(k_ms / (ms / args.steps), 4)}
+
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: nsvf_base training step, 343 voxels (voxel 0.4, step 1/8, max_hits 60), "
+                               "4 views x 800x800 rays intersected + 4 x 2048 rays marched per GPU, fwd+bwd+Adam, "
+                               "field MLP fp32 on cuBLAS", "rays_intersected_per_step_per_gpu": rays_intersected,
+                   "rays_marched_per_step_per_gpu": rays_marched, "samples_evaluated_per_step": int(out["ae"]),
+                   "l2": "256 MiB memset at the start of every step (inside the timed region)",
+                   "parallelism": "dp%d (rays sharded by view, voxel set replicated, NCCL grad all-reduce)" % world},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": round(e2e_value, 1), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": round(ms_e2e / args.steps, 4)},
+        "roofline": roofline, "loss": round(loss_val, 5),
+    }
+
+    if rank == 0:
+        try:
+            line["stages_ms"] = stage_times(dev, pipe, resident[0])
+        except Exception as e:   # informational only
+            line["stages_ms"] = {"error": repr(e)[:200]}
+    if world > 1:
+        dist.barrier()
+    if rank == 0 and not args.no_frame:
+        try:
+            line["frame"] = frame_bench(dev)
+        except Exception as e:
+            line["frame"] = {"error": repr(e)[:200]}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_arm(steps=2, warmup=1, fraction=args.cpu_fraction)["cpu_baseline"]
+        except Exception as e:
+            line["cpu_baseline"] = {"error": repr(e)[:200]}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def _time(fn, n=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return round(e0.elapsed_time(e1) / n, 4)
+
+
+def stage_times(dev, pipe, batch):
+    """Informational per-stage device times of one C2 step (separate, untimed pass)."""
+    from nsvf_b200 import clib, ops
+    enc = pipe.encoder
+    rs, rd, _ = batch
+    st = enc.precompute(id=torch.zeros(1, dtype=torch.long, device=dev))
+    pts = st["voxel_center_xyz"]
+    S, V, P, _ = rd.shape
+    rs_f = rs.expand_as(rd).contiguous().view(S, V * P, 3)
+    rd_f = rd.reshape(S, V * P, 3)
+    res = {}
+    res["intersect_kernel_call"] = _time(lambda: clib.aabb_ray_intersect(enc.voxel_size, enc.max_hits, pts, rs_f, rd_f))
+    res["ray_intersect_total(sort+mask glue)"] = _time(lambda: enc.ray_intersect(rs, rd, st))
+    pipe.train()
+    with torch.no_grad():
+        _, rdd, inter, hits, _ = pipe.intersecting(rs, rd, st)
+    inter = {k: v.reshape(-1, *v.shape[2:])[hits.reshape(-1)] for k, v in inter.items()}
+    res["inverse_cdf_sampling"] = _time(lambda: enc.ray_sample(inter))
+    samples = enc.ray_sample(inter)
+    sidx = samples["sampled_point_voxel_idx"]
+    mask = sidx.ne(-1)
+    M = int(mask.sum())
+    vox = sidx[mask]
+    xyz = torch.randn(M, 3, device=dev) * 0.1 + pts.reshape(-1, 3)[vox.long()]
+    feats, values = st["voxel_vertex_idx"].reshape(-1, 8).int(), st["voxel_vertex_emb"].reshape(-1, 32).detach()
+    res["trilinear_fwd"] = _time(lambda: ops.trilinear_embed(vox, xyz, feats, pts.reshape(-1, 3), values, enc.voxel_size))
+    v2 = values.clone().requires_grad_(True)
+    emb = ops.trilinear_embed(vox, xyz, feats, pts.reshape(-1, 3), v2, enc.voxel_size)
+    g = torch.randn_like(emb)
+    res["trilinear_bwd"] = _time(lambda: torch.autograd.grad(emb, v2, g, retain_graph=True))
+    fld = pipe.field
+    dirs = torch.nn.functional.normalize(torch.randn(M, 3, device=dev), dim=-1)
+
+    def mlp():
+        o = fld({"emb": emb.detach().requires_grad_(True), "ray": dirs})
+        (o["sigma"].sum() + o["texture"].sum()).backward()
+    res["field_mlp_fwd_bwd(cuBLAS)"] = _time(mlp, n=3, warm=1)
+    B, K = sidx.shape
+    fe = torch.rand(B, K, device=dev).requires_grad_(True)
+    tex = torch.rand(B, K, 3, device=dev).requires_grad_(True)
+    dep = samples["sampled_point_depth"]
+    res["composite_fwd"] = _time(lambda: ops.composite(fe, tex, dep))
+    o = ops.composite(fe, tex, dep)
+    res["composite_bwd"] = _time(lambda: torch.autograd.grad([o[1].sum() + o[2].sum() + o[3].sum()], [fe, tex],
+                                                             retain_graph=True))
+    res["samples"] = M
+    res["K"] = K
+    return res
+
+
+def frame_bench(dev):
+    """ms per 800x800 frame on the C3 scene (BASELINE.json configs[2]): eval, early termination 0.01, chunk 512."""
+    from nsvf_b200 import synthetic
+    res = {}
+    rs, rd = synthetic.camera_rays(RES, RES, 1, radius=4.5, seed=7, device=dev)
+    rs, rd = rs[None, :, None, 0, :].contiguous(), rd[None].contiguous()
+    for name, field in (("with_field_mlp", "mlp"), ("hot_path_only(trivial field)", "trivial")):
+        pipe, scene = build_model(dev, "C3", train=False, field=field, tolerance=0.01, chunk=512, sigma_bias=2.0)
+        with torch.no_grad():
+            pipe(rs, rd)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            n = 2
+            for _ in range(n):
+                out = pipe(rs, rd)
+            e1.record()
+            torch.cuda.synchronize()
+        res[name] = {"ms_per_800x800_frame": round(e0.elapsed_time(e1) / n, 3), "field_evaluations": int(out["ae"]),
+                     "rays_hit": int(out["hits"].sum())}
+        res["voxels"] = scene.n
+        del pipe
+    return res
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the box's host cores (cpu_baseline and --impl reference)
+# ------------------------------------------------------------------------------------------------------
+def cpu_arm(steps, warmup, fraction):
+    import oracle
+    from oracle import wrappers
+    from nsvf_b200 import synthetic
+    from nsvf_b200.field import RadianceField
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    oracle.build()
+    scene = synthetic.make_scene("C2")
+    pts = scene.points.copy()
+    pts[:, 0] += np.float32(scene.voxel_size / 10)
+    torch.manual_seed(0)
+    field = RadianceField()
+    values = torch.from_numpy(scene.values.copy()).requires_grad_(True)
+    opt = torch.optim.Adam(list(p for p in field.parameters() if p.requires_grad) + [values], lr=1e-3)
+    pix = RES * RES // fraction
+    k = PIX_PER_VIEW // fraction
+    rs_all, rd_all = synthetic.camera_rays(RES, RES, VIEWS, radius=3.2, seed=0)
+    rng = np.random.RandomState(0)
+
+    def one_step():
+        sel = rng.choice(RES * RES, pix, replace=False)
+        rd = rd_all[:, sel].numpy()
+        rs = np.broadcast_to(rs_all.numpy(), (VIEWS, RES * RES, 3))[:, sel]
+        idx, dmin, dmax = oracle.aabb_intersect(rs.reshape(1, -1, 3), rd.reshape(1, -1, 3), pts, scene.voxel_size, scene.max_hits)
+        idx_t, dmin_t, dmax_t, hits = wrappers.sort_hits(*[torch.from_numpy(a[0]) for a in (idx, dmin, dmax)])
+        hit_ids = hits.nonzero()[:, 0].numpy()
+        take = np.sort(rng.choice(hit_ids, min(VIEWS * k, len(hit_ids)), replace=False))
+        idx_t, dmin_t, dmax_t = idx_t[take], dmin_t[take], dmax_t[take]
+        probs, stp = wrappers.probs_and_steps(idx_t, dmin_t, dmax_t, scene.step_size)
+        sidx, sdep, sdist = wrappers.inverse_cdf_sampling(wrappers.NumpyExt(), idx_t, dmin_t, dmax_t, probs, stp, -1, False)
+        sidx, sdep, sdist = wrappers.mask_samples(sidx, sdep, sdist)
+        mask = sidx.ne(-1)
+        o = torch.from_numpy(rs.reshape(-1, 3)[take].copy())
+        d = torch.from_numpy(rd.reshape(-1, 3)[take].copy())
+        xyz = (o[:, None] + d[:, None] * sdep[..., None])[mask]
+        vox = sidx[mask].numpy()
+        emb = torch.from_numpy(oracle.trilinear_fwd(vox, xyz.numpy(), scene.feats, pts, values.detach().numpy(),
+                                                    scene.voxel_size)).requires_grad_(True)
+        out = field({"emb": emb, "ray": d[:, None].expand(*sdep.shape, 3)[mask]})
+        fe_c = torch.relu(out["sigma"] + torch.randn_like(out["sigma"])) * sdist[mask] * 7.0
+        fe = torch.zeros_like(sdep).masked_scatter(mask, fe_c)
+        tex = torch.zeros(*sdep.shape, 3).masked_scatter(mask[..., None].expand(-1, -1, 3), out["texture"])
+        p_, dep_, mis_, col_ = [torch.from_numpy(a) for a in oracle.composite_fwd(fe.detach().numpy(), tex.detach().numpy(), sdep.numpy())]
+        target = torch.rand(col_.shape) * 2 - 1
+        col_.requires_grad_(True); mis_.requires_grad_(True)
+        loss = ((col_ + mis_[:, None] - target) ** 2).mean() * 128 + (mis_ ** 2).mean()
+        loss.backward()
+        g_fe, g_tex = oracle.composite_bwd(fe.detach().numpy(), tex.detach().numpy(), sdep.numpy(), None, None,
+                                           mis_.grad.numpy(), col_.grad.numpy())
+        opt.zero_grad(set_to_none=True)
+        torch.autograd.backward([fe, tex], [torch.from_numpy(g_fe), torch.from_numpy(g_tex)])
+        gv, _ = oracle.trilinear_bwd(vox, xyz.numpy(), scene.feats, pts, values.detach().numpy(), scene.voxel_size,
+                                     emb.grad.numpy())
+        values.grad = torch.from_numpy(gv)
+        opt.step()
+        return len(take), int(mask.sum())
+
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    rays = 0
+    for _ in range(steps):
+        r, m = one_step()
+        rays += r
+    dt = time.perf_counter() - t0
+    value = rays / dt
+    sample = ("1/%d of the C2 step per CPU step: %d rays intersected, %d rays marched (%d samples), fwd+bwd+Adam; "
+              "C oracle with OpenMP for intersect/sample/interp/composite, torch-CPU fp32 MLP" %
+              (fraction, VIEWS * pix, r, m))
+    return {"value": value, "ms_per_step": dt / steps * 1e3, "steps": steps,
+            "cpu_baseline": {"value": round(value, 2), "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_arm(max(args.steps, 1), max(args.warmup, 1), args.cpu_fraction)
+    line = {"impl": "reference", "metric": METRIC, "value": round(r["value"], 2), "unit": "rays/s", "n_gpus": args.gpus,
+            "steps": max(args.steps, 1), "warmup": max(args.warmup, 1), "ms_per_step": round(r["ms_per_step"], 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2: nsvf_base training step (bounded CPU sample, see cpu_baseline.sample)"},
+            "cpu_baseline": r["cpu_baseline"],
+            "e2e": {"value": round(r["value"], 2), "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

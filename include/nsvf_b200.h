@@ -35,6 +35,14 @@ typedef void* nsvf_stream_t;
 NSVF_API int nsvf_version(void);
 NSVF_API const char* nsvf_last_error(void);
 
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
+NSVF_API unsigned long long nsvf_kernel_launches(void);
+
+/* Measurement hook: cudaEvent_t `ev_start` / `ev_stop` are recorded on the launching stream immediately
+ * before / after every launch of the kernel called `name` (e.g. "aabb_intersect_kernel"), so a caller can
+ * time one kernel inside a longer step without a profiler.  name = NULL or "" clears the hook. */
+NSVF_API int nsvf_profile_kernel(const char* name, void* ev_start, void* ev_stop);
+
 /* y[i] = __fdividef(1.0f, x[i]) — the reciprocal the reference slab test uses
  * (fairnr/clib/src/intersect_gpu.cu:86-90). Test helper: lets a CPU oracle consume the exact values. */
 NSVF_API int nsvf_ref_rcp(nsvf_stream_t stream, long long n, const float* x, float* y);
@@ -53,6 +61,23 @@ NSVF_API int nsvf_aabb_intersect(nsvf_stream_t stream, int b, int n, int m, floa
                         const float* ray_start, const float* ray_dir, const float* points,
                         long long points_batch_stride, int* idx, float* min_depth, float* max_depth,
                         void* workspace, size_t workspace_bytes);
+
+/* Same intersection with the post-processing of SparseVoxelEncoder.ray_intersect fused in
+ * (fairnr/modules/encoder.py:519-524: masked_fill(idx == -1, MAX_DEPTH), sort by min_depth, gather, any):
+ * each ray's hits are sorted by entry depth (ties: ascending voxel index), unused slots hold idx -1 and
+ * `empty_depth` (the encoder uses 10000.0), and hits u8 [b, m] (optional) = "the ray hit something". */
+NSVF_API int nsvf_aabb_intersect_sorted(nsvf_stream_t stream, int b, int n, int m, float voxelsize, int n_max,
+                                        float empty_depth, const float* ray_start, const float* ray_dir,
+                                        const float* points, long long points_batch_stride, int* idx,
+                                        float* min_depth, float* max_depth, unsigned char* hits, void* workspace,
+                                        size_t workspace_bytes);
+
+/* Any-hit query: hits u8 [b, m] = 1 iff nsvf_aabb_intersect would report at least one hit for the ray.  Lets
+ * the training path (`--no-sampling-at-reader`, fairnr/models/nsvf.py:48-60) draw pixels from the hit mask of
+ * all V x H x W rays without materialising [rays, n_max] x 3 outputs for rays it will not march. */
+NSVF_API int nsvf_aabb_hit_mask(nsvf_stream_t stream, int b, int n, int m, float voxelsize, const float* ray_start,
+                                const float* ray_dir, const float* points, long long points_batch_stride,
+                                unsigned char* hits, void* workspace, size_t workspace_bytes);
 
 /* Replaces svo_intersect, fairnr/clib/src/intersect.cpp:84-112 + intersect_gpu.cu:170-237.
  *   points   : f32 [T, 3] node centres, children : i32 [T, 9] (slot 8 = node size in voxels, 1 = leaf),
@@ -132,6 +157,56 @@ NSVF_API int nsvf_composite_bwd(nsvf_stream_t stream, long long B, int K, const 
                        const float* sampled_depth, const float* grad_probs, const float* grad_depth,
                        const float* grad_missed, const float* grad_colors, float* grad_free_energy,
                        float* grad_texture);
+
+/* ---- sample compaction ---------------------------------------------------------------------------------
+ * Replaces the boolean-mask compaction of VolumeRenderer.forward_once, fairnr/modules/renderer.py:88-100
+ * (sample_mask = idx != -1 & ~early_stop; xyz = ray_start + ray_dir * depth; s[sample_mask] for every tensor).
+ *   sampled_idx i32 / sampled_depth, sampled_dists f32 : [B,K]; only columns [col0, col1) are considered
+ *   early_stop u8 [B] or NULL (rays with a non-zero flag contribute no samples)
+ *   nsvf_compact_count : counts i64 [B] = valid samples per ray
+ *   nsvf_compact_fill  : offsets_incl i64 [B] = inclusive prefix sum of counts (any device scan);
+ *                        writes, in row-major order of the valid samples, out_vox i32 [M], out_xyz f32 [M,3],
+ *                        out_dir f32 [M,3] (or NULL), out_dists f32 [M] (or NULL), out_flat i64 [M] = ray*K + k */
+NSVF_API int nsvf_compact_count(nsvf_stream_t stream, long long B, int K, int col0, int col1, const int* sampled_idx,
+                                const unsigned char* early_stop, long long* counts);
+NSVF_API int nsvf_compact_fill(nsvf_stream_t stream, long long B, int K, int col0, int col1, const int* sampled_idx,
+                               const float* sampled_depth, const float* sampled_dists,
+                               const unsigned char* early_stop, const float* ray_start, const float* ray_dir,
+                               const long long* offsets_incl, int* out_vox, float* out_xyz, float* out_dir,
+                               float* out_dists, long long* out_flat);
+
+/* ---- half-voxel splitting --------------------------------------------------------------------------------
+ * Replaces splitting_points, fairnr/data/geometry.py:250-274 (+ discretize_points :241-247, offset_points
+ * :229-238), called by SparseVoxelEncoder.splitting, fairnr/modules/encoder.py:656-676.
+ * Two phases because the number of unique new corner keys Kc' sizes the outputs:
+ *   pmin f32[3], max_coord i32[3] : HOST values — per-axis min of `points`, and per-axis max of
+ *                                   round((points - pmin) / quarter_voxel), quarter_voxel = half_voxel / 2
+ *   nsvf_split_mark : new_points f32 [8n,3] (children centres, child order x slowest - z fastest) and
+ *                     *n_keys (device i32) = Kc'
+ *   nsvf_split_emit : new_feats i32 [8n,8] = lexicographic rank of each child's corner keys (== torch.unique's
+ *                     inverse), new_keys i32 [Kc',3] (optional), new_values f32 [Kc',D] (optional) = the parent's
+ *                     trilinear interpolant at the key, parent = the smallest voxel index touching the key;
+ *                     parent i32 [Kc'] is scratch.  `workspace` must be the one phase 1 filled. */
+NSVF_API size_t nsvf_split_workspace_bytes(const int* max_coord);
+NSVF_API int nsvf_split_mark(nsvf_stream_t stream, int n, const float* points, float half_voxel, const float* pmin,
+                             const int* max_coord, float* new_points, int* n_keys, void* workspace,
+                             size_t workspace_bytes);
+NSVF_API int nsvf_split_emit(nsvf_stream_t stream, int n, int D, const float* points, const int* feats,
+                             const float* values, float half_voxel, const float* pmin, const int* max_coord,
+                             int n_keys, int* new_feats, int* parent, int* new_keys, float* new_values,
+                             void* workspace, size_t workspace_bytes);
+
+/* ---- pruning --------------------------------------------------------------------------------------------
+ * Replaces SparseVoxelEncoder.get_scores / pruning, fairnr/modules/encoder.py:605-654.
+ *   nsvf_prune_lattice_embed : out f32 [nv, bits^3, D] = interpolated embeddings at the bits^3 lattice points
+ *                              (offset_points(points, voxel_size/2, bits), closed voxel) of voxels [v0, v0+nv);
+ *                              feats i32 [n,8], centres f32 [n,3], values f32 [Kc,D]
+ *   nsvf_prune_keep          : sigma f32 [nv, L] (the field's density at those points) ->
+ *                              keep u8 [nv] = (1 - min_l exp(-relu(sigma))) > th; min_score f32 [nv] optional */
+NSVF_API int nsvf_prune_lattice_embed(nsvf_stream_t stream, int nv, int v0, int bits, int D, const int* feats,
+                                      const float* centres, const float* values, float voxel_size, float* out);
+NSVF_API int nsvf_prune_keep(nsvf_stream_t stream, int nv, int L, const float* sigma, float th, unsigned char* keep,
+                             float* min_score);
 
 #ifdef __cplusplus
 }

@@ -16,10 +16,16 @@ c_int, c_ll, c_float, c_size_t, c_void_p = (ctypes.c_int, ctypes.c_longlong, cty
 SIGNATURES = {
     "nsvf_version": (c_int, []),
     "nsvf_last_error": (ctypes.c_char_p, []),
+    "nsvf_kernel_launches": (ctypes.c_ulonglong, []),
+    "nsvf_profile_kernel": (c_int, [ctypes.c_char_p, c_void_p, c_void_p]),
     "nsvf_ref_rcp": (c_int, [c_void_p, c_ll, c_void_p, c_void_p]),
     "nsvf_aabb_workspace_bytes": (c_size_t, [c_int, c_int]),
     "nsvf_aabb_intersect": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p,
                                     c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
+    "nsvf_aabb_intersect_sorted": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_int, c_float, c_void_p, c_void_p,
+                                           c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
+    "nsvf_aabb_hit_mask": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_ll,
+                                   c_void_p, c_void_p, c_size_t]),
     "nsvf_svo_workspace_bytes": (c_size_t, [c_int, c_int]),
     "nsvf_svo_intersect": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
@@ -35,6 +41,16 @@ SIGNATURES = {
                                          c_float, c_void_p, c_void_p, c_void_p]),
     "nsvf_composite_fwd": (c_int, [c_void_p, c_ll, c_int] + [c_void_p] * 7),
     "nsvf_composite_bwd": (c_int, [c_void_p, c_ll, c_int] + [c_void_p] * 9),
+    "nsvf_split_workspace_bytes": (c_size_t, [c_void_p]),
+    "nsvf_split_mark": (c_int, [c_void_p, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_size_t]),
+    "nsvf_split_emit": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
+    "nsvf_prune_lattice_embed": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float,
+                                         c_void_p]),
+    "nsvf_prune_keep": (c_int, [c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p]),
+    "nsvf_compact_count": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "nsvf_compact_fill": (c_int, [c_void_p, c_ll, c_int, c_int, c_int] + [c_void_p] * 12),
 }
 
 _lib = None

@@ -20,18 +20,21 @@ def _chk(cond, msg):
         raise RuntimeError(msg)
 
 
-def _check_float_cuda(**tensors):
-    for name, t in tensors.items():
+def _check(floats, ints=None):
+    """Same order as the reference: CHECK_CONTIGUOUS on everything, then dtypes, then CHECK_CUDA."""
+    ints = ints or {}
+    for name, t in list(ints.items()) + list(floats.items()):
         _chk(t.is_contiguous(), name + " must be a contiguous tensor")
+    for name, t in floats.items():
         _chk(t.dtype == torch.float32, name + " must be a float tensor")
-        _chk(t.is_cuda, name + " must be a CUDA tensor")
-
-
-def _check_int_cuda(**tensors):
-    for name, t in tensors.items():
-        _chk(t.is_contiguous(), name + " must be a contiguous tensor")
+    for name, t in ints.items():
         _chk(t.dtype == torch.int32, name + " must be an int tensor")
+    for name, t in list(ints.items()) + list(floats.items()):
         _chk(t.is_cuda, name + " must be a CUDA tensor")
+
+
+def _check_float_cuda(**tensors):
+    _check(tensors)
 
 
 def _workspace(nbytes, device):
@@ -71,6 +74,43 @@ def aabb_intersect(ray_start, ray_dir, points, voxelsize, n_max, shared_points=F
     return idx, dmin, dmax
 
 
+def _aabb_args(ray_start, ray_dir, points, shared_points):
+    _check_float_cuda(ray_start=ray_start, ray_dir=ray_dir, points=points)
+    b, m = ray_start.shape[0], ray_start.shape[1]
+    if shared_points:
+        return b, m, points.shape[-2], 0, 1
+    _chk(points.dim() == 3 and points.shape[0] == b, "points must be [B, n, 3] with B == ray_start.size(0)")
+    return b, m, points.shape[1], points.shape[1] * 3, b
+
+
+def aabb_intersect_sorted(ray_start, ray_dir, points, voxelsize, n_max, empty_depth=10000.0, shared_points=False):
+    """Extension (not in the reference _ext): aabb_intersect + the sort / fill / any() of
+    SparseVoxelEncoder.ray_intersect (encoder.py:519-524) in one kernel.
+    -> idx i32, min_depth f32, max_depth f32 [B,M,n_max] sorted by entry depth, hits bool [B,M]."""
+    b, m, n, stride, trees = _aabb_args(ray_start, ray_dir, points, shared_points)
+    voxelsize, n_max = float(voxelsize), int(n_max)
+    idx, dmin, dmax = _hit_outputs(ray_start, n_max)
+    hits = torch.empty((b, m), dtype=torch.uint8, device=ray_start.device)
+    with torch.cuda.device(ray_start.device):
+        ws = _workspace(_L.nsvf_aabb_workspace_bytes(n, trees), ray_start.device)
+        _lib.check(_L.nsvf_aabb_intersect_sorted(
+            _lib.current_stream(ray_start.device), b, n, m, voxelsize, n_max, float(empty_depth), _p(ray_start),
+            _p(ray_dir), _p(points), stride, _p(idx), _p(dmin), _p(dmax), _p(hits), _p(ws), ws.numel()))
+    return idx, dmin, dmax, hits.bool()
+
+
+def aabb_hit_mask(ray_start, ray_dir, points, voxelsize, shared_points=False):
+    """Extension: hits bool [B,M] = any(aabb_intersect(...).idx != -1) without producing the hit lists."""
+    b, m, n, stride, trees = _aabb_args(ray_start, ray_dir, points, shared_points)
+    hits = torch.empty((b, m), dtype=torch.uint8, device=ray_start.device)
+    with torch.cuda.device(ray_start.device):
+        ws = _workspace(_L.nsvf_aabb_workspace_bytes(n, trees), ray_start.device)
+        _lib.check(_L.nsvf_aabb_hit_mask(
+            _lib.current_stream(ray_start.device), b, n, m, float(voxelsize), _p(ray_start), _p(ray_dir), _p(points),
+            stride, _p(hits), _p(ws), ws.numel()))
+    return hits.bool()
+
+
 def svo_intersect(ray_start, ray_dir, points, children, voxelsize, n_max, shared_tree=False):
     """fairnr/clib/src/intersect.cpp:84-112.  points f32 [B,T,3] node centres, children i32 [B,T,9]."""
     _check_float_cuda(ray_start=ray_start, ray_dir=ray_dir, points=points)
@@ -107,8 +147,7 @@ def triangle_intersect(ray_start, ray_dir, face_points, cagesize, blur, n_max):
 
 def uniform_ray_sampling(pts_idx, min_depth, max_depth, uniform_noise, step_size, max_steps):
     """fairnr/clib/src/sample.cpp:23-55.  [G,R,P] inputs, noise [G,R,max_steps] -> 3 x [G,R,max_steps]."""
-    _check_float_cuda(min_depth=min_depth, max_depth=max_depth, uniform_noise=uniform_noise)
-    _check_int_cuda(pts_idx=pts_idx)
+    _check(dict(min_depth=min_depth, max_depth=max_depth, uniform_noise=uniform_noise), dict(pts_idx=pts_idx))
     step_size, max_steps = float(step_size), int(max_steps)
     g, r, p = min_depth.shape
     dev = pts_idx.device
@@ -124,8 +163,8 @@ def uniform_ray_sampling(pts_idx, min_depth, max_depth, uniform_noise, step_size
 
 def inverse_cdf_sampling(pts_idx, min_depth, max_depth, uniform_noise, probs, steps, fixed_step_size):
     """fairnr/clib/src/sample.cpp:58-95.  max_steps = uniform_noise.size(-1)."""
-    _check_float_cuda(min_depth=min_depth, max_depth=max_depth, uniform_noise=uniform_noise, probs=probs, steps=steps)
-    _check_int_cuda(pts_idx=pts_idx)
+    _check(dict(min_depth=min_depth, max_depth=max_depth, uniform_noise=uniform_noise, probs=probs, steps=steps),
+           dict(pts_idx=pts_idx))
     fixed_step_size = float(fixed_step_size)
     g, r, p = min_depth.shape
     max_steps = uniform_noise.shape[-1]

@@ -21,7 +21,7 @@
 
 namespace nsvf {
 
-constexpr int kAabbMaxLevels = 7;          // 32^7 > 2^31 voxels
+constexpr int kAabbMaxLevels = 5;          // up to 32^5 = 33.5 M voxels
 constexpr int kAabbSmemNodes = 4096;       // nodes staged per CTA: 6 * 4096 * 4 B = 96 KiB
 constexpr int kAabbWarps = 8;
 
@@ -138,56 +138,66 @@ __global__ void aabb_build_up_kernel(float* __restrict__ box_all, long long tree
 }
 
 // ---- traversal ------------------------------------------------------------------------------------
+extern __shared__ __align__(128) float aabb_smem[];   // [6][sm_nodes] staged boxes, then per-warp hit buffers
+
+enum AabbMode { kModeIndexOrder = 0, kModeDepthSorted = 1, kModeAnyHit = 2 };
+
 struct AabbRay {
   float ox, oy, oz, ix, iy, iz;
-  bool regular;
-  int nx, ny, nz;  // near-array selectors for the sorted test: 0 -> lo is near, 3 -> hi is near
 };
 
 struct AabbWarp {
   const float* gbox;   // global SoA of this tree
-  const float* sbox;   // shared SoA (array stride = sm_nodes)
   int sm_nodes;
-  int* h_idx;          // per-warp hit buffers in shared memory
-  float* h_min;
-  float* h_max;
+  int hbuf;            // float offset of this warp's hit buffers inside aabb_smem
   int n_max;
 };
 
-// `tree` is the __grid_constant__ kernel parameter: cnt[L] / off[L] with a compile-time L are direct
-// constant-bank operands, no registers.
+// One step of the fast path (regular rays: no NaN can occur, fmin/fmax ordering == the reference's swap):
+// the 32 lanes test nodes base..base+31 of level L.  `tree` is the __grid_constant__ kernel parameter, so
+// cnt[L] / off[L] with a compile-time L are constant-bank operands.
 template <int L>
-__device__ __forceinline__ void aabb_descend(const AabbTree& tree, const AabbWarp& c, const AabbRay& r, int base,
-                                             int& cnt) {
+__device__ __forceinline__ unsigned aabb_test32(const AabbTree& tree, const AabbWarp& c, const AabbRay& r, int base,
+                                                float& tn, float& tf) {
   const int lane = threadIdx.x & 31;
   const int i = base + lane;
-  bool hit = false;
-  float tn = 0.f, tf = 0.f;
-  if (i < tree.cnt[L]) {
-    const int pos = tree.off[L] + i;
-    const bool staged = tree.off[L] >= tree.stage_from;  // uniform per level
-    const float* bp = staged ? c.sbox + (pos - tree.stage_from) : c.gbox + pos;
-    const int stride = staged ? c.sm_nodes : tree.total;
-    if (r.regular) {
-      const float nx = bp[(long long)r.nx * stride], fx = bp[(long long)(3 - r.nx) * stride];
-      const float ny = bp[(long long)(1 + r.ny) * stride], fy = bp[(long long)(4 - r.ny) * stride];
-      const float nz = bp[(long long)(2 + r.nz) * stride], fz = bp[(long long)(5 - r.nz) * stride];
-      hit = slab_sorted(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, nx, ny, nz, fx, fy, fz, tn, tf);
-    } else {
-      const float lx = bp[0], ly = bp[(long long)stride], lz = bp[(long long)2 * stride];
-      const float hx = bp[(long long)3 * stride], hy = bp[(long long)4 * stride], hz = bp[(long long)5 * stride];
-      if (L == 0) hit = slab_exact(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, lx, ly, lz, hx, hy, hz, tn, tf);
-      else hit = slab_enclosing(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, lx, ly, lz, hx, hy, hz);
-    }
+  const bool valid = i < tree.cnt[L];
+  const int pos = tree.off[L] + (valid ? i : tree.cnt[L] - 1);
+  float lx, ly, lz, hx, hy, hz;
+  if (tree.off[L] >= tree.stage_from) {   // level staged in shared memory (uniform)
+    const float* s = aabb_smem + (pos - tree.stage_from);
+    const int st = c.sm_nodes;
+    lx = s[0]; ly = s[st]; lz = s[2 * st]; hx = s[3 * st]; hy = s[4 * st]; hz = s[5 * st];
+  } else {
+    const float* g = c.gbox + pos;
+    const int st = tree.total;
+    lx = __ldg(g); ly = __ldg(g + st); lz = __ldg(g + 2 * st);
+    hx = __ldg(g + 3 * (long long)st); hy = __ldg(g + 4 * (long long)st); hz = __ldg(g + 5 * (long long)st);
   }
-  unsigned m = __ballot_sync(NSVF_FULL_MASK, hit);
+  const float a0 = __fmul_rn(__fsub_rn(lx, r.ox), r.ix), b0 = __fmul_rn(__fsub_rn(hx, r.ox), r.ix);
+  const float a1 = __fmul_rn(__fsub_rn(ly, r.oy), r.iy), b1 = __fmul_rn(__fsub_rn(hy, r.oy), r.iy);
+  const float a2 = __fmul_rn(__fsub_rn(lz, r.oz), r.iz), b2 = __fmul_rn(__fsub_rn(hz, r.oz), r.iz);
+  tn = fmaxf(fmaxf(0.0f, fminf(a0, b0)), fmaxf(fminf(a1, b1), fminf(a2, b2)));
+  tf = fminf(fminf(100000.0f, fmaxf(a0, b0)), fminf(fmaxf(a1, b1), fmaxf(a2, b2)));
+  return __ballot_sync(NSVF_FULL_MASK, valid && (tn <= tf));
+}
+
+template <int L, int MODE>
+__device__ __forceinline__ void aabb_descend(const AabbTree& tree, const AabbWarp& c, const AabbRay& r, int base,
+                                             int& cnt) {
+  float tn, tf;
+  unsigned m = aabb_test32<L>(tree, c, r, base, tn, tf);
   if constexpr (L == 0) {
-    if (hit) {
-      const int rank = cnt + __popc(m & ((1u << lane) - 1u));
-      if (rank < c.n_max) {
-        c.h_idx[rank] = i;
-        c.h_min[rank] = tn;
-        c.h_max[rank] = tf;
+    if constexpr (MODE != kModeAnyHit) {
+      const int lane = threadIdx.x & 31;
+      if ((m >> lane) & 1u) {
+        const int rank = cnt + __popc(m & ((1u << lane) - 1u));
+        if (rank < c.n_max) {
+          float* h = aabb_smem + c.hbuf;
+          reinterpret_cast<int*>(h)[rank] = base + lane;
+          h[c.n_max + rank] = tn;
+          h[2 * c.n_max + rank] = tf;
+        }
       }
     }
     cnt += __popc(m);
@@ -195,20 +205,112 @@ __device__ __forceinline__ void aabb_descend(const AabbTree& tree, const AabbWar
     while (m != 0u && cnt < c.n_max) {
       const int b = __ffs(m) - 1;
       m &= m - 1u;
-      aabb_descend<L - 1>(tree, c, r, (base + b) * 32, cnt);
+      aabb_descend<L - 1, MODE>(tree, c, r, (base + b) * 32, cnt);
     }
   }
 }
 
+// Slow path for rays whose slab test can produce NaN (a zero / non-finite direction component, a non-finite
+// origin): exact select-based test at the leaves, conservative fmin/fmax test on the enclosing nodes.
+// Runtime level loop; never on the hot path.
+__device__ __noinline__ void aabb_traverse_irregular(const AabbTree& tree, const AabbWarp& c, const AabbRay& r,
+                                                     int mode, int& cnt) {
+  const int lane = threadIdx.x & 31;
+  unsigned mask[kAabbMaxLevels];
+  int node[kAabbMaxLevels];
+  int L = tree.nlevels - 1;
+  node[L] = 0;
+  bool fresh = true;   // node[L] group not tested yet
+  for (;;) {
+    if (fresh) {
+      const int i = node[L] + lane;
+      bool hit = false;
+      float tn = 0.f, tf = 0.f;
+      if (i < tree.cnt[L]) {
+        const float* g = c.gbox + tree.off[L] + i;
+        const long long st = tree.total;
+        const float lx = g[0], ly = g[st], lz = g[2 * st], hx = g[3 * st], hy = g[4 * st], hz = g[5 * st];
+        if (L == 0) hit = slab_exact(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, lx, ly, lz, hx, hy, hz, tn, tf);
+        else hit = slab_enclosing(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, lx, ly, lz, hx, hy, hz);
+      }
+      const unsigned m = __ballot_sync(NSVF_FULL_MASK, hit);
+      if (L == 0) {
+        if (mode != kModeAnyHit && hit) {
+          const int rank = cnt + __popc(m & ((1u << lane) - 1u));
+          if (rank < c.n_max) {
+            float* h = aabb_smem + c.hbuf;
+            reinterpret_cast<int*>(h)[rank] = i;
+            h[c.n_max + rank] = tn;
+            h[2 * c.n_max + rank] = tf;
+          }
+        }
+        cnt += __popc(m);
+        mask[0] = 0u;
+      } else {
+        mask[L] = m;
+      }
+      fresh = false;
+    }
+    if (cnt >= c.n_max) return;
+    if (L == 0 || mask[L] == 0u) {       // this group is exhausted: go up
+      if (L == tree.nlevels - 1) return;
+      ++L;
+      continue;
+    }
+    const int b = __ffs(mask[L]) - 1;
+    mask[L] &= mask[L] - 1u;
+    node[L - 1] = (node[L] + b) * 32;
+    --L;
+    fresh = true;
+  }
+}
+
+// Warp-level stable sort of the first `cnt` hits by entry depth (ties keep ascending voxel index).
+// perm[] (ints, in shared memory, >= pow2(cnt) entries) receives the source slot of every sorted position.
+__device__ __forceinline__ void aabb_sort_by_depth(const float* h_min, int cnt, int* perm) {
+  const int lane = threadIdx.x & 31;
+  if (cnt <= 32) {   // rank sort: one element per lane, keys broadcast from shared memory
+    if (lane < cnt) {
+      const float d = h_min[lane];
+      int rank = 0;
+      for (int j = 0; j < cnt; ++j) {
+        const float e = h_min[j];
+        rank += (e < d) || (e == d && j < lane);
+      }
+      perm[rank] = lane;
+    }
+  } else {           // bitonic network over (depth, slot) keys, padded to a power of two with +inf
+    int n2 = 64;
+    while (n2 < cnt) n2 <<= 1;
+    for (int t = lane; t < n2; t += 32) perm[t] = t;
+    __syncwarp();
+    for (int k = 2; k <= n2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = lane; t < n2; t += 32) {
+          const int u = t ^ j;
+          if (u > t) {
+            const int pa = perm[t], pb = perm[u];
+            const float da = pa < cnt ? h_min[pa] : INFINITY, db = pb < cnt ? h_min[pb] : INFINITY;
+            const bool a_gt_b = (da > db) || (da == db && pa > pb);
+            const bool up = (t & k) == 0;
+            if (a_gt_b == up) { perm[t] = pb; perm[u] = pa; }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <int NL, int MODE>
 __global__ void __launch_bounds__(kAabbWarps * 32)
 aabb_intersect_kernel(const __grid_constant__ AabbTree tree, long long tree_stride_box, long long rays_per_tree,
-                      int n_max, const float* __restrict__ ray_start, const float* __restrict__ ray_dir,
-                      int* __restrict__ out_idx, float* __restrict__ out_min, float* __restrict__ out_max) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+                      int n_max, int sort_slots, float empty_depth, const float* __restrict__ ray_start,
+                      const float* __restrict__ ray_dir, int* __restrict__ out_idx, float* __restrict__ out_min,
+                      float* __restrict__ out_max, unsigned char* __restrict__ out_hit) {
   __shared__ __align__(8) uint64_t bar;
   const int sm_nodes = tree.total - tree.stage_from;   // multiple of 32
-  float* sbox = reinterpret_cast<float*>(smem_raw);
-  int* hbuf = reinterpret_cast<int*>(smem_raw + (size_t)6 * sm_nodes * sizeof(float));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* gbox = tree.box + (long long)blockIdx.y * tree_stride_box;
 
@@ -224,26 +326,28 @@ aabb_intersect_kernel(const __grid_constant__ AabbTree tree, long long tree_stri
       mbar_expect_tx(&bar, bytes * 6u);
 #pragma unroll
       for (int a = 0; a < 6; ++a)
-        tma_bulk_g2s(sbox + (size_t)a * sm_nodes, gbox + (long long)a * tree.total + tree.stage_from, bytes, &bar);
+        tma_bulk_g2s(aabb_smem + (size_t)a * sm_nodes, gbox + (long long)a * tree.total + tree.stage_from, bytes, &bar);
     }
     mbar_wait(&bar, 0);
   }
 
   AabbWarp c;
   c.gbox = gbox;
-  c.sbox = sbox;
   c.sm_nodes = sm_nodes;
-  c.n_max = n_max;
-  c.h_idx = hbuf + warp * 3 * n_max;
-  c.h_min = reinterpret_cast<float*>(c.h_idx + n_max);
-  c.h_max = c.h_min + n_max;
+  c.n_max = MODE == kModeAnyHit ? 1 : n_max;
+  const int per_warp = 3 * n_max + sort_slots;
+  c.hbuf = 6 * sm_nodes + warp * per_warp;
+  float* h = aabb_smem + c.hbuf;
+  int* h_idx = reinterpret_cast<int*>(h);
+  float* h_min = h + n_max;
+  float* h_max = h + 2 * n_max;
+  int* perm = reinterpret_cast<int*>(h + 3 * n_max);
 
   const long long ray_base = (long long)blockIdx.y * rays_per_tree;
   for (long long rr = (long long)blockIdx.x * kAabbWarps + warp; rr < rays_per_tree;
        rr += (long long)gridDim.x * kAabbWarps) {
     const long long ray = ray_base + rr;
-    // lanes 0..2 load the origin, 3..5 the direction; broadcast
-    float v = 0.f;
+    float v = 0.f;   // lanes 0..2 load the origin, 3..5 the direction; broadcast
     if (lane < 3) v = ray_start[ray * 3 + lane];
     else if (lane < 6) v = ray_dir[ray * 3 + (lane - 3)];
     AabbRay r;
@@ -253,35 +357,78 @@ aabb_intersect_kernel(const __grid_constant__ AabbTree tree, long long tree_stri
     r.ix = ref_rcp(__shfl_sync(NSVF_FULL_MASK, v, 3));
     r.iy = ref_rcp(__shfl_sync(NSVF_FULL_MASK, v, 4));
     r.iz = ref_rcp(__shfl_sync(NSVF_FULL_MASK, v, 5));
-    r.regular = regular_component(r.ox, r.ix) && regular_component(r.oy, r.iy) && regular_component(r.oz, r.iz);
-    r.nx = r.ix < 0.f ? 3 : 0;
-    r.ny = r.iy < 0.f ? 3 : 0;
-    r.nz = r.iz < 0.f ? 3 : 0;
+    const bool regular =
+        regular_component(r.ox, r.ix) && regular_component(r.oy, r.iy) && regular_component(r.oz, r.iz);
 
     int cnt = 0;
-    switch (tree.nlevels) {
-      case 1: aabb_descend<0>(tree, c, r, 0, cnt); break;
-      case 2: aabb_descend<1>(tree, c, r, 0, cnt); break;
-      case 3: aabb_descend<2>(tree, c, r, 0, cnt); break;
-      case 4: aabb_descend<3>(tree, c, r, 0, cnt); break;
-      case 5: aabb_descend<4>(tree, c, r, 0, cnt); break;
-      case 6: aabb_descend<5>(tree, c, r, 0, cnt); break;
-      default: aabb_descend<6>(tree, c, r, 0, cnt); break;
+    if (regular) aabb_descend<NL - 1, MODE>(tree, c, r, 0, cnt);
+    else aabb_traverse_irregular(tree, c, r, MODE, cnt);
+
+    if constexpr (MODE == kModeAnyHit) {
+      if (lane == 0) out_hit[ray] = cnt > 0;
+    } else {
+      cnt = min(cnt, n_max);
+      __syncwarp();
+      const long long row = ray * n_max;
+      if constexpr (MODE == kModeDepthSorted) {
+        aabb_sort_by_depth(h_min, cnt, perm);
+        for (int l = lane; l < n_max; l += 32) {
+          const bool ok = l < cnt;
+          const int src = ok ? perm[l] : 0;
+          out_idx[row + l] = ok ? h_idx[src] : -1;
+          out_min[row + l] = ok ? h_min[src] : empty_depth;
+          out_max[row + l] = ok ? h_max[src] : empty_depth;
+        }
+        if (out_hit != nullptr && lane == 0) out_hit[ray] = cnt > 0;
+      } else {
+        for (int l = lane; l < n_max; l += 32) {
+          const bool ok = l < cnt;
+          out_idx[row + l] = ok ? h_idx[l] : -1;
+          out_min[row + l] = ok ? h_min[l] : empty_depth;
+          out_max[row + l] = ok ? h_max[l] : empty_depth;
+        }
+      }
+      __syncwarp();
     }
-    cnt = min(cnt, n_max);
-    __syncwarp();
-    const long long row = ray * n_max;
-    for (int l = lane; l < n_max; l += 32) {
-      const bool ok = l < cnt;
-      out_idx[row + l] = ok ? c.h_idx[l] : -1;
-      out_min[row + l] = ok ? c.h_min[l] : 0.0f;
-      out_max[row + l] = ok ? c.h_max[l] : 0.0f;
-    }
-    __syncwarp();
   }
 }
 
 static size_t aabb_tree_floats(int n) { return (size_t)6 * aabb_layout(n).total; }
+
+template <int NL, int MODE>
+static int aabb_launch(cudaStream_t stream, dim3 grid, size_t smem, const AabbTree& tree, long long tree_stride_box,
+                       long long rays_per_tree, int n_max, int sort_slots, float empty_depth, const float* ray_start,
+                       const float* ray_dir, int* idx, float* dmin, float* dmax, unsigned char* hit) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    NSVF_CUDA_OK(cudaFuncSetAttribute(aabb_intersect_kernel<NL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      200 * 1024));
+    attr_set = true;
+  }
+  NSVF_TIMED_LAUNCH("aabb_intersect_kernel", stream,
+                    (aabb_intersect_kernel<NL, MODE><<<grid, kAabbWarps * 32, smem, stream>>>(
+                        tree, tree_stride_box, rays_per_tree, n_max, sort_slots, empty_depth, ray_start, ray_dir, idx,
+                        dmin, dmax, hit)));
+  return 0;
+}
+
+template <int MODE>
+static int aabb_dispatch(int nlevels, cudaStream_t stream, dim3 grid, size_t smem, const AabbTree& tree,
+                         long long tree_stride_box, long long rays_per_tree, int n_max, int sort_slots,
+                         float empty_depth, const float* ray_start, const float* ray_dir, int* idx, float* dmin,
+                         float* dmax, unsigned char* hit) {
+#define NSVF_CASE(N)                                                                                              \
+  case N:                                                                                                         \
+    return aabb_launch<N, MODE>(stream, grid, smem, tree, tree_stride_box, rays_per_tree, n_max, sort_slots,       \
+                                empty_depth, ray_start, ray_dir, idx, dmin, dmax, hit);
+  switch (nlevels) {
+    NSVF_CASE(1) NSVF_CASE(2) NSVF_CASE(3) NSVF_CASE(4) NSVF_CASE(5)
+    default:
+      set_error("aabb_intersect: %d hierarchy levels (more than 32^5 voxels) are not supported", nlevels);
+      return 1;
+  }
+#undef NSVF_CASE
+}
 
 }  // namespace nsvf
 
@@ -292,18 +439,26 @@ extern "C" size_t nsvf_aabb_workspace_bytes(int n, int n_trees) {
   return aabb_tree_floats(n) * sizeof(float) * (size_t)n_trees;
 }
 
-extern "C" int nsvf_aabb_intersect(nsvf_stream_t stream_, int b, int n, int m, float voxelsize, int n_max,
-                                   const float* ray_start, const float* ray_dir, const float* points,
-                                   long long points_batch_stride, int* idx, float* min_depth, float* max_depth,
-                                   void* workspace, size_t workspace_bytes) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+// mode: 0 = reference order (ascending voxel index), 1 = sorted by entry depth, 2 = any-hit mask only
+static int aabb_run(cudaStream_t stream, int mode, int b, int n, int m, float voxelsize, int n_max, float empty_depth,
+                    const float* ray_start, const float* ray_dir, const float* points,
+                    long long points_batch_stride, int* idx, float* min_depth, float* max_depth,
+                    unsigned char* hit, void* workspace, size_t workspace_bytes) {
   NSVF_REQUIRE(b >= 0 && n >= 0 && m >= 0 && n_max >= 0, "aabb_intersect: negative size");
-  if (b == 0 || m == 0 || n_max == 0) return 0;
+  if (b == 0 || m == 0) return 0;
+  if (mode != kModeAnyHit && n_max == 0) return 0;
   const long long rays = (long long)b * m;
-  if (n == 0) {  // nothing to hit: rows are all -1 / 0
-    NSVF_CUDA_OK(cudaMemsetAsync(idx, 0xff, sizeof(int) * rays * n_max, stream));
-    NSVF_CUDA_OK(cudaMemsetAsync(min_depth, 0, sizeof(float) * rays * n_max, stream));
-    NSVF_CUDA_OK(cudaMemsetAsync(max_depth, 0, sizeof(float) * rays * n_max, stream));
+  if (n == 0) {  // nothing to hit
+    if (mode != kModeAnyHit) {
+      NSVF_CUDA_OK(cudaMemsetAsync(idx, 0xff, sizeof(int) * rays * n_max, stream));
+      if (empty_depth == 0.0f) {
+        NSVF_CUDA_OK(cudaMemsetAsync(min_depth, 0, sizeof(float) * rays * n_max, stream));
+        NSVF_CUDA_OK(cudaMemsetAsync(max_depth, 0, sizeof(float) * rays * n_max, stream));
+      } else {
+        NSVF_REQUIRE(false, "aabb_intersect: empty voxel set with a non-zero fill depth is not supported");
+      }
+    }
+    if (hit != nullptr) NSVF_CUDA_OK(cudaMemsetAsync(hit, 0, rays, stream));
     return 0;
   }
   NSVF_REQUIRE(points_batch_stride == 0 || points_batch_stride >= (long long)n * 3,
@@ -319,7 +474,7 @@ extern "C" int nsvf_aabb_intersect(nsvf_stream_t stream_, int b, int n, int m, f
   const long long tree_stride_box = (long long)6 * L.total;
   const float half_voxel = voxelsize * 0.5f;  // reference: float half_voxel = voxelsize * 0.5 (exact)
 
-  {  // build
+  {  // build the hierarchy (O(n), a few small launches)
     int n1 = (n + 31) / 32;
     dim3 grid((n1 + 7) / 8, n_trees);
     aabb_build_l01_kernel<<<grid, 256, 0, stream>>>(points, points_batch_stride, n, half_voxel, box,
@@ -343,24 +498,56 @@ extern "C" int nsvf_aabb_intersect(nsvf_stream_t stream_, int b, int n, int m, f
 
   const long long rays_per_tree = n_trees == 1 ? rays : m;
   const int sm_nodes = L.total - L.stage_from;
-  size_t smem = (size_t)6 * sm_nodes * sizeof(float) + (size_t)kAabbWarps * 3 * n_max * sizeof(int);
-  NSVF_REQUIRE(smem <= 200 * 1024, "aabb_intersect: n_max=%d needs %zu B of shared memory", n_max, smem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NSVF_CUDA_OK(cudaFuncSetAttribute(aabb_intersect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      200 * 1024));
-    attr_set = true;
+  int sort_slots = 0;
+  if (mode == kModeDepthSorted) {
+    sort_slots = 64;
+    while (sort_slots < n_max) sort_slots <<= 1;
   }
+  const int per_warp = mode == kModeAnyHit ? 0 : 3 * n_max + sort_slots;
+  size_t smem = ((size_t)6 * sm_nodes + (size_t)kAabbWarps * per_warp) * sizeof(float);
+  NSVF_REQUIRE(smem <= 200 * 1024, "aabb_intersect: n_max=%d needs %zu B of shared memory", n_max, smem);
   int blocks_per_sm = (int)((220 * 1024) / (smem + 1024));
-  blocks_per_sm = blocks_per_sm < 1 ? 1 : (blocks_per_sm > 8 ? 8 : blocks_per_sm);
+  blocks_per_sm = blocks_per_sm < 1 ? 1 : (blocks_per_sm > 6 ? 6 : blocks_per_sm);
   long long want = (rays_per_tree + kAabbWarps - 1) / kAabbWarps;
   long long cap = (long long)num_sms() * blocks_per_sm;
   if (n_trees > 1) cap = (cap + n_trees - 1) / n_trees;
   int gx = (int)(want < cap ? want : cap);
   if (gx < 1) gx = 1;
   dim3 grid(gx, n_trees);
-  aabb_intersect_kernel<<<grid, kAabbWarps * 32, smem, stream>>>(tree, tree_stride_box, rays_per_tree, n_max,
-                                                                 ray_start, ray_dir, idx, min_depth, max_depth);
-  NSVF_LAUNCH_OK("aabb_intersect_kernel");
-  return 0;
+  const int nm = mode == kModeAnyHit ? 0 : n_max;
+  switch (mode) {
+    case kModeIndexOrder:
+      return aabb_dispatch<kModeIndexOrder>(L.nlevels, stream, grid, smem, tree, tree_stride_box, rays_per_tree, nm,
+                                            sort_slots, empty_depth, ray_start, ray_dir, idx, min_depth, max_depth, hit);
+    case kModeDepthSorted:
+      return aabb_dispatch<kModeDepthSorted>(L.nlevels, stream, grid, smem, tree, tree_stride_box, rays_per_tree, nm,
+                                             sort_slots, empty_depth, ray_start, ray_dir, idx, min_depth, max_depth, hit);
+    default:
+      return aabb_dispatch<kModeAnyHit>(L.nlevels, stream, grid, smem, tree, tree_stride_box, rays_per_tree, nm,
+                                        sort_slots, empty_depth, ray_start, ray_dir, idx, min_depth, max_depth, hit);
+  }
+}
+
+extern "C" int nsvf_aabb_intersect(nsvf_stream_t stream, int b, int n, int m, float voxelsize, int n_max,
+                                   const float* ray_start, const float* ray_dir, const float* points,
+                                   long long points_batch_stride, int* idx, float* min_depth, float* max_depth,
+                                   void* workspace, size_t workspace_bytes) {
+  return aabb_run((cudaStream_t)stream, kModeIndexOrder, b, n, m, voxelsize, n_max, 0.0f, ray_start, ray_dir, points,
+                  points_batch_stride, idx, min_depth, max_depth, nullptr, workspace, workspace_bytes);
+}
+
+extern "C" int nsvf_aabb_intersect_sorted(nsvf_stream_t stream, int b, int n, int m, float voxelsize, int n_max,
+                                          float empty_depth, const float* ray_start, const float* ray_dir,
+                                          const float* points, long long points_batch_stride, int* idx,
+                                          float* min_depth, float* max_depth, unsigned char* hits, void* workspace,
+                                          size_t workspace_bytes) {
+  return aabb_run((cudaStream_t)stream, kModeDepthSorted, b, n, m, voxelsize, n_max, empty_depth, ray_start, ray_dir,
+                  points, points_batch_stride, idx, min_depth, max_depth, hits, workspace, workspace_bytes);
+}
+
+extern "C" int nsvf_aabb_hit_mask(nsvf_stream_t stream, int b, int n, int m, float voxelsize, const float* ray_start,
+                                  const float* ray_dir, const float* points, long long points_batch_stride,
+                                  unsigned char* hits, void* workspace, size_t workspace_bytes) {
+  return aabb_run((cudaStream_t)stream, kModeAnyHit, b, n, m, voxelsize, 0, 0.0f, ray_start, ray_dir, points,
+                  points_batch_stride, nullptr, nullptr, nullptr, hits, workspace, workspace_bytes);
 }

@@ -26,6 +26,16 @@ int cuda_fail(cudaError_t e, const char* what);
   do {                                                             \
     cudaError_t _e = cudaGetLastError();                           \
     if (_e != cudaSuccess) return nsvf::cuda_fail(_e, name);        \
+    nsvf::count_launch();                                          \
+  } while (0)
+// Launch `stmt` (a <<<>>> expression on `stream`), bracketed by the profiling events registered for `name`
+// through nsvf_profile_kernel (no-op when none are registered).
+#define NSVF_TIMED_LAUNCH(name, stream, stmt)                       \
+  do {                                                             \
+    nsvf::profile_mark(name, 0, stream);                           \
+    stmt;                                                          \
+    nsvf::profile_mark(name, 1, stream);                           \
+    NSVF_LAUNCH_OK(name);                                          \
   } while (0)
 #define NSVF_REQUIRE(cond, ...)          \
   do {                                   \
@@ -36,6 +46,8 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 int num_sms();  // SM count of the current device (148 on B200), cached
+void count_launch();
+void profile_mark(const char* name, int which, cudaStream_t stream);
 
 // ---- device helpers ---------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -151,9 +151,8 @@ extern "C" int nsvf_composite_fwd(nsvf_stream_t stream_, long long B, int K, con
   long long want = (B + kCompWarps - 1) / kCompWarps;
   long long cap = (long long)num_sms() * 8;
   int grid = (int)(want < cap ? want : cap);
-  composite_fwd_kernel<<<grid, kCompWarps * 32, 0, stream>>>(B, K, free_energy, texture, sampled_depth, probs, depth,
-                                                            missed, colors);
-  NSVF_LAUNCH_OK("composite_fwd_kernel");
+  NSVF_TIMED_LAUNCH("composite_fwd_kernel", stream, (composite_fwd_kernel<<<grid, kCompWarps * 32, 0, stream>>>(B, K, free_energy, texture, sampled_depth, probs, depth,
+                                                            missed, colors)));
   return 0;
 }
 
@@ -176,9 +175,8 @@ extern "C" int nsvf_composite_bwd(nsvf_stream_t stream_, long long B, int K, con
   per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
   long long cap = (long long)num_sms() * per_sm;
   int grid = (int)(want < cap ? want : cap);
-  composite_bwd_kernel<<<grid, kCompWarps * 32, smem, stream>>>(B, K, free_energy, texture, sampled_depth, grad_probs,
+  NSVF_TIMED_LAUNCH("composite_bwd_kernel", stream, (composite_bwd_kernel<<<grid, kCompWarps * 32, smem, stream>>>(B, K, free_energy, texture, sampled_depth, grad_probs,
                                                                grad_depth, grad_missed, grad_colors,
-                                                               grad_free_energy, grad_texture);
-  NSVF_LAUNCH_OK("composite_bwd_kernel");
+                                                               grad_free_energy, grad_texture)));
   return 0;
 }

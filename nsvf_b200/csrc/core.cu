@@ -1,6 +1,7 @@
 // Library plumbing: error string, version, device properties.
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 
 #include "common.cuh"
 #include "nsvf_b200.h"
@@ -33,6 +34,16 @@ int num_sms() {
   return cached[dev];
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
+static char g_prof_name[64] = "";
+static cudaEvent_t g_prof_ev[2] = {nullptr, nullptr};
+void profile_mark(const char* name, int which, cudaStream_t stream) {
+  if (g_prof_name[0] == 0 || strcmp(name, g_prof_name) != 0 || g_prof_ev[which] == nullptr) return;
+  cudaEventRecord(g_prof_ev[which], stream);
+}
+
 // reference reciprocal, exported so the CPU oracle can be fed the exact MUFU-based 1/d values
 __global__ void ref_rcp_kernel(long long n, const float* __restrict__ x, float* __restrict__ y) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -43,6 +54,20 @@ __global__ void ref_rcp_kernel(long long n, const float* __restrict__ x, float* 
 
 extern "C" int nsvf_version(void) { return NSVF_B200_VERSION; }
 extern "C" const char* nsvf_last_error(void) { return nsvf::g_err; }
+
+extern "C" unsigned long long nsvf_kernel_launches(void) { return nsvf::g_launches; }
+
+extern "C" int nsvf_profile_kernel(const char* name, void* ev_start, void* ev_stop) {
+  if (name == nullptr || name[0] == 0) {
+    nsvf::g_prof_name[0] = 0;
+    nsvf::g_prof_ev[0] = nsvf::g_prof_ev[1] = nullptr;
+    return 0;
+  }
+  strncpy(nsvf::g_prof_name, name, sizeof(nsvf::g_prof_name) - 1);
+  nsvf::g_prof_ev[0] = (cudaEvent_t)ev_start;
+  nsvf::g_prof_ev[1] = (cudaEvent_t)ev_stop;
+  return 0;
+}
 
 extern "C" int nsvf_ref_rcp(nsvf_stream_t stream, long long n, const float* x, float* y) {
   if (n <= 0) return 0;

@@ -296,10 +296,9 @@ extern "C" int nsvf_inverse_cdf_sampling(nsvf_stream_t stream_, int b, int num_r
   long long want = (groups + kSampWarps - 1) / kSampWarps;
   long long cap = (long long)num_sms() * 8;
   int grid = (int)(want < cap ? want : cap);
-  inverse_cdf_sampling_kernel<16><<<grid, kSampWarps * 32, 0, stream>>>(
+  NSVF_TIMED_LAUNCH("inverse_cdf_sampling_kernel", stream, (inverse_cdf_sampling_kernel<16><<<grid, kSampWarps * 32, 0, stream>>>(
       b, num_rays, valid_rays, ray_chunk, max_hits, max_steps, fixed_step_size, pts_idx, min_depth, max_depth,
-      uniform_noise, noise_const, probs, steps, sampled_idx, sampled_depth, sampled_dists, max_count);
-  NSVF_LAUNCH_OK("inverse_cdf_sampling_kernel");
+      uniform_noise, noise_const, probs, steps, sampled_idx, sampled_depth, sampled_dists, max_count)));
   return 0;
 }
 

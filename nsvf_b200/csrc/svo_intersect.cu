@@ -175,8 +175,7 @@ extern "C" int nsvf_svo_intersect(nsvf_stream_t stream_, int b, int T, int m, fl
   int gx = (int)(want < cap ? want : cap);
   if (gx < 1) gx = 1;
   dim3 grid(gx, n_trees);
-  svo_intersect_kernel<<<grid, kSvoThreads, 0, stream>>>(nodes, T, rays_per_tree, n_max, ray_start, ray_dir, idx,
-                                                         min_depth, max_depth, flag);
-  NSVF_LAUNCH_OK("svo_intersect_kernel");
+  NSVF_TIMED_LAUNCH("svo_intersect_kernel", stream, (svo_intersect_kernel<<<grid, kSvoThreads, 0, stream>>>(nodes, T, rays_per_tree, n_max, ray_start, ray_dir, idx,
+                                                         min_depth, max_depth, flag)));
   return 0;
 }

@@ -1,0 +1,277 @@
+"""Host-side mirror of the reference's SparseVoxelEncoder hot-path interface, on the sm_100a kernels.
+
+Same method names, argument meaning and results as fairnr/modules/encoder.py:202-712 for the methods on the
+hot path — precompute (:380-410), ray_intersect (:498-536), ray_sample (:538-556), forward (:558-592),
+pruning / get_scores (:605-654), splitting (:656-676), octree cache (:365-371, 678-688) — so the parity
+tests read like tests of the reference class.  Everything else of the reference class (ply / checkpoint IO,
+export, the other encoder classes) is out of scope.
+
+Differences that do not change results:
+  * corner keys (`feats`) are cached as int32 for the gather kernels (the buffer stays int64);
+  * `forward` is one fused gather kernel (ops.trilinear_embed) instead of 3 F.embedding + ~10 elementwise ops;
+  * the octree is built by nsvf_octree_build (one D2H copy, no per-point device syncs).
+"""
+import logging
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import clib, geometry, ops
+
+logger = logging.getLogger(__name__)
+MAX_DEPTH = 10000.0
+
+
+class SparseVoxelEncoder(nn.Module):
+    def __init__(self, points, voxel_size, max_hits=60, raymarching_stepsize_ratio=0.125, raymarching_stepsize=0.01,
+                 voxel_embed_dim=32, deterministic_step=False, use_octree=False, track_max_probs=False):
+        super().__init__()
+        fine_points = torch.as_tensor(points, dtype=torch.float32)
+        half_voxel = voxel_size * .5
+        fine_feats, fine_keys = geometry.corner_keys(fine_points, half_voxel)   # encoder.py:270-275
+        step_size = raymarching_stepsize_ratio * voxel_size if raymarching_stepsize_ratio > 0 else raymarching_stepsize
+        self.register_buffer("points", fine_points)
+        self.register_buffer("keys", fine_keys.long())
+        self.register_buffer("feats", fine_feats.long())
+        self.register_buffer("num_keys", torch.scalar_tensor(fine_keys.size(0)).long())
+        self.register_buffer("keep", fine_feats.new_ones(fine_feats.size(0)).long())
+        self.register_buffer("voxel_size", torch.scalar_tensor(voxel_size))
+        self.register_buffer("step_size", torch.scalar_tensor(step_size))
+        self.register_buffer("max_hits", torch.scalar_tensor(max_hits))
+        self.embed_dim = voxel_embed_dim
+        self.deterministic_step = deterministic_step
+        self.use_octree = use_octree
+        self.track_max_probs = track_max_probs
+        self._runtime_caches = {"flatten_centers": None, "flatten_children": None, "max_voxel_probs": None}
+        self.values = nn.Embedding(int(self.num_keys), voxel_embed_dim)
+        nn.init.normal_(self.values.weight, mean=0, std=voxel_embed_dim ** -0.5)   # module_utils.py:23-26
+
+    @classmethod
+    def from_bbox(cls, bbox, voxel_size=None, **kw):
+        """bbox = (xmin, ymin, zmin, xmax, ymax, zmax, voxel_size): the reference's bbox.txt line (encoder.py:264-267)."""
+        from . import synthetic
+        bbox = np.asarray(bbox, dtype=np.float64)
+        voxel_size = float(bbox[-1]) if voxel_size is None else voxel_size
+        return cls(synthetic.bbox_voxels(bbox[:3], bbox[3:6], voxel_size), voxel_size, **kw)
+
+    # ---- caches ---------------------------------------------------------------------------------------
+    def reset_runtime_caches(self):
+        if self.use_octree:
+            points = self.points[self.keep.bool()]
+            centers, children = geometry.build_easy_octree(points, self.voxel_size / 2.0)
+            self._runtime_caches["flatten_centers"] = centers
+            self._runtime_caches["flatten_children"] = children
+        if self.track_max_probs:
+            self._runtime_caches["max_voxel_probs"] = self.points.new_zeros(self.points.size(0))
+
+    def clean_runtime_caches(self):
+        for name in self._runtime_caches:
+            self._runtime_caches[name] = None
+
+    @property
+    def flatten_centers(self):
+        if self._runtime_caches["flatten_centers"] is None:
+            self.reset_runtime_caches()
+        return self._runtime_caches["flatten_centers"]
+
+    @property
+    def flatten_children(self):
+        if self._runtime_caches["flatten_children"] is None:
+            self.reset_runtime_caches()
+        return self._runtime_caches["flatten_children"]
+
+    @property
+    def max_voxel_probs(self):
+        if self._runtime_caches["max_voxel_probs"] is None:
+            self.reset_runtime_caches()
+        return self._runtime_caches["max_voxel_probs"]
+
+    @max_voxel_probs.setter
+    def max_voxel_probs(self, x):
+        self._runtime_caches["max_voxel_probs"] = x
+
+    @property
+    def num_voxels(self):
+        return self.keep.long().sum()
+
+    # ---- hot path -------------------------------------------------------------------------------------
+    def precompute(self, id=None, *args, **kwargs):
+        keep = self.keep.bool()
+        feats = self.feats[keep]
+        points = self.points[keep]
+        points[:, 0] += (self.voxel_size / 10)      # the reference's HACK (encoder.py:383), kept for parity
+        values = self.values.weight[: self.num_keys]
+        encoder_states = {"voxel_vertex_idx": feats, "voxel_center_xyz": points, "voxel_vertex_emb": values}
+        if self.use_octree:
+            encoder_states["voxel_octree_center_xyz"] = self.flatten_centers.clone()
+            encoder_states["voxel_octree_children_idx"] = self.flatten_children.clone()
+        if id is not None:   # [1, ...] leading shape dimension, as the reference adds for id
+            encoder_states = {k: v.unsqueeze(0) for k, v in encoder_states.items()}
+        return encoder_states
+
+    def ray_intersect(self, ray_start, ray_dir, encoder_states):
+        point_feats = encoder_states["voxel_vertex_idx"]
+        point_xyz = encoder_states["voxel_center_xyz"]
+        if point_xyz.dim() == 2:
+            point_feats, point_xyz = point_feats.unsqueeze(0), point_xyz.unsqueeze(0)
+        S, V, P, _ = ray_dir.size()
+        H = point_feats.size(1)
+        ray_start = ray_start.expand_as(ray_dir).contiguous().view(S, V * P, 3).contiguous()
+        ray_dir = ray_dir.reshape(S, V * P, 3).contiguous()
+        if self.use_octree:
+            centers = encoder_states["voxel_octree_center_xyz"]
+            children = encoder_states["voxel_octree_children_idx"]
+            if centers.dim() == 2:
+                centers, children = centers.unsqueeze(0), children.unsqueeze(0)
+            pts_idx, min_depth, max_depth = clib.svo_ray_intersect(
+                self.voxel_size, self.max_hits, centers, children, ray_start, ray_dir)
+            # sort by entry depth (encoder.py:519-524)
+            min_depth.masked_fill_(pts_idx.eq(-1), MAX_DEPTH)
+            max_depth.masked_fill_(pts_idx.eq(-1), MAX_DEPTH)
+            min_depth, sorted_idx = min_depth.sort(dim=-1)
+            max_depth = max_depth.gather(-1, sorted_idx)
+            pts_idx = pts_idx.gather(-1, sorted_idx)
+            hits = pts_idx.ne(-1).any(-1)
+        else:
+            # intersection + masked_fill + sort + gather + any() of encoder.py:511-524 in ONE kernel
+            pts_idx, min_depth, max_depth, hits = clib._ext.aabb_intersect_sorted(
+                ray_start.float(), ray_dir.float(), point_xyz.float().contiguous(), self.voxel_size, self.max_hits,
+                MAX_DEPTH)
+            min_depth, max_depth = min_depth.type_as(ray_start), max_depth.type_as(ray_start)
+        if S > 1:
+            pts_idx = (pts_idx + H * torch.arange(S, device=pts_idx.device, dtype=pts_idx.dtype)[:, None, None]
+                       ).masked_fill_(pts_idx.eq(-1), -1)
+        intersection_outputs = {"min_depth": min_depth, "max_depth": max_depth, "intersected_voxel_idx": pts_idx}
+        return ray_start, ray_dir, intersection_outputs, hits
+
+    def ray_hit_mask(self, ray_start, ray_dir, encoder_states):
+        """hits [S, V*P] of ray_intersect without the hit lists (any-hit kernel); aabb path only."""
+        point_xyz = encoder_states["voxel_center_xyz"]
+        if point_xyz.dim() == 2:
+            point_xyz = point_xyz.unsqueeze(0)
+        S, V, P, _ = ray_dir.size()
+        ray_start = ray_start.expand_as(ray_dir).contiguous().view(S, V * P, 3).contiguous()
+        ray_dir = ray_dir.reshape(S, V * P, 3).contiguous()
+        hits = clib._ext.aabb_hit_mask(ray_start.float(), ray_dir.float(), point_xyz.float().contiguous(),
+                                       self.voxel_size)
+        return ray_start, ray_dir, hits
+
+    def ray_sample(self, intersection_outputs):
+        sampled_idx, sampled_depth, sampled_dists = clib.inverse_cdf_sampling(
+            intersection_outputs["intersected_voxel_idx"], intersection_outputs["min_depth"],
+            intersection_outputs["max_depth"], intersection_outputs["probs"], intersection_outputs["steps"],
+            -1, self.deterministic_step or (not self.training))
+        sampled_dists = sampled_dists.clamp(min=0.0)
+        sampled_depth.masked_fill_(sampled_idx.eq(-1), MAX_DEPTH)
+        sampled_dists.masked_fill_(sampled_idx.eq(-1), 0.0)
+        return {"sampled_point_depth": sampled_depth, "sampled_point_distance": sampled_dists,
+                "sampled_point_voxel_idx": sampled_idx}
+
+    @torch.enable_grad()
+    def forward(self, samples, encoder_states):
+        point_feats = encoder_states["voxel_vertex_idx"]
+        point_xyz = encoder_states["voxel_center_xyz"]
+        values = encoder_states["voxel_vertex_emb"]
+        sampled_idx = samples["sampled_point_voxel_idx"]
+        sampled_xyz = samples["sampled_point_xyz"].requires_grad_(True)
+        inputs = {"pos": sampled_xyz, "ray": samples["sampled_point_ray_direction"],
+                  "dists": samples["sampled_point_distance"]}
+        if values is not None:
+            inputs["emb"] = ops.trilinear_embed(sampled_idx, sampled_xyz, point_feats.reshape(-1, 8),
+                                                point_xyz.reshape(-1, 3), values.reshape(-1, values.size(-1)),
+                                                self.voxel_size)
+        return inputs
+
+    @torch.no_grad()
+    def track_voxel_probs(self, voxel_idxs, voxel_probs):
+        """Per-voxel running max of sample probabilities (encoder.py:594-603) without the [4096, n+1] scatter."""
+        n = self.max_voxel_probs.size(0)
+        valid = voxel_idxs.ne(-1)
+        # the reference sums the probabilities a ray deposits in the same voxel before taking the max
+        B, K = voxel_idxs.shape
+        ray = torch.arange(B, device=voxel_idxs.device)[:, None].expand(B, K)[valid]
+        key = ray * n + voxel_idxs[valid].long()
+        uniq, inv = torch.unique(key, return_inverse=True)
+        summed = torch.zeros(uniq.numel(), device=voxel_probs.device, dtype=voxel_probs.dtype).scatter_add_(
+            0, inv, voxel_probs[valid])
+        cur = torch.zeros_like(self.max_voxel_probs).scatter_reduce_(0, uniq % n, summed, reduce="amax")
+        self.max_voxel_probs = torch.max(self.max_voxel_probs, cur)
+
+    @torch.no_grad()
+    def pruning(self, field_fn, th=0.5, encoder_states=None, train_stats=False, voxel_shard=None):
+        """keep-mask update (encoder.py:605-618).  `voxel_shard=(rank, world)` scores only this rank's contiguous
+        slice of the voxels and all-gathers the uint8 keep mask (nsvf_b200.dist.allgather_keep_mask): the
+        multi-GPU pruning of BASELINE.json; the reference recomputes the full mask on every rank."""
+        if not train_stats:
+            if voxel_shard is None:
+                keep, _ = self._prune_scores(field_fn, th, bits=16, encoder_states=encoder_states)
+            else:
+                from . import dist as nsvf_dist
+                rank, world = voxel_shard
+                n = int(self.keep.bool().sum())
+                lo, hi = nsvf_dist.shard_range(n, rank, world)
+                part, _ = self._prune_scores(field_fn, th, bits=16, encoder_states=encoder_states, lo=lo, hi=hi)
+                keep = nsvf_dist.allgather_keep_mask(part, n, rank, world)
+        else:
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_world_size() > 1:
+                dist.all_reduce(self.max_voxel_probs, op=dist.ReduceOp.MAX)
+            keep = self.max_voxel_probs > th
+        self.keep.masked_scatter_(self.keep.bool(), keep.long())
+        logger.info("pruning done. # of voxels before: %d, after: %d", keep.size(0), int(keep.sum()))
+
+    def _prune_scores(self, field_fn, th, bits=16, encoder_states=None, lo=0, hi=None, chunk_size=64):
+        """(keep bool, min_score f32) for voxels [lo, hi): fused lattice interpolation -> field -> keep kernel."""
+        from . import split
+        if encoder_states is None:
+            encoder_states = self.precompute(id=None)
+        feats = ops.as_int32_feats(encoder_states["voxel_vertex_idx"].reshape(-1, 8)).contiguous()
+        points = encoder_states["voxel_center_xyz"].reshape(-1, 3).float().contiguous()
+        values = encoder_states["voxel_vertex_emb"]
+        values = values.reshape(-1, values.size(-1)).detach().float().contiguous()
+        hi = points.size(0) if hi is None else hi
+        keeps, scores = [], []
+        for i in range(lo, hi, chunk_size):          # same 64-voxel granularity per field call as the reference
+            nv = min(chunk_size, hi - i)
+            emb = split.lattice_embed(feats, points, values, self.voxel_size, i, nv, bits)
+            sigma = field_fn({"emb": emb}, outputs=["sigma"])["sigma"]
+            k, s = split.prune_keep(sigma, bits ** 3, th)
+            keeps.append(k)
+            scores.append(s)
+        if not keeps:
+            return points.new_zeros(0, dtype=torch.bool), points.new_zeros(0)
+        return torch.cat(keeps), torch.cat(scores)
+
+    def get_scores(self, field_fn, th=0.5, bits=16, encoder_states=None):
+        """exp(-relu(sigma)) at the bits^3 lattice points of every voxel, [n, bits^3] (encoder.py:620-654)."""
+        from . import split
+        if encoder_states is None:
+            encoder_states = self.precompute(id=None)
+        feats = ops.as_int32_feats(encoder_states["voxel_vertex_idx"].reshape(-1, 8)).contiguous()
+        points = encoder_states["voxel_center_xyz"].reshape(-1, 3).float().contiguous()
+        values = encoder_states["voxel_vertex_emb"]
+        values = values.reshape(-1, values.size(-1)).detach().float().contiguous()
+        out = []
+        for i in range(0, points.size(0), 64):
+            nv = min(64, points.size(0) - i)
+            emb = split.lattice_embed(feats, points, values, self.voxel_size, i, nv, bits)
+            sigma = field_fn({"emb": emb}, outputs=["sigma"])["sigma"]
+            out.append(torch.exp(-torch.relu(sigma).reshape(-1, bits ** 3)))
+        return torch.cat(out, 0)
+
+    @torch.no_grad()
+    def splitting(self):
+        encoder_states = self.precompute(id=None)
+        feats, points, values = (encoder_states["voxel_vertex_idx"], encoder_states["voxel_center_xyz"],
+                                 encoder_states["voxel_vertex_emb"])
+        new_points, new_feats, new_values, new_keys = geometry.splitting_points(
+            points, feats, values, self.voxel_size / 2.0)
+        if new_values is not None:
+            self.values.weight = nn.Parameter(new_values)
+            self.values.num_embeddings = self.values.weight.size(0)
+        self.total_size = new_keys.size(0)
+        self.num_keys = self.num_keys * 0 + self.total_size
+        self.points = new_points
+        self.feats = new_feats
+        self.keep = self.keep.new_ones(new_points.size(0))

@@ -1,0 +1,97 @@
+"""The ray-marching pipeline around the hot path: what BaseModel._forward (fairnr/models/fairnr_model.py:142-186)
+with NSVFModel.intersecting / raymarching / postprocessing (fairnr/models/nsvf.py:43-110, nerf.py:49-62) does,
+restated compactly on top of the encoder / renderer mirrors.  This is the public call bench.py times:
+
+    pipe = NSVFPipeline(encoder, field, renderer, pixel_per_view=2048)
+    out  = pipe(ray_start [S,V,1,3], ray_dir [S,V,P,3])      # S must be 1, like the reference asserts
+
+Training mode with `pixel_per_view > 0` reproduces `--no-sampling-at-reader`: all V*P rays are intersected,
+then `pixel_per_view` pixels per view are drawn from the hit mask (Gumbel top-k, reader.py:176-182) and only
+those are marched.  Eval mode marches every hit ray (full-frame rendering).
+"""
+import torch
+import torch.nn as nn
+
+TINY = 1e-9
+
+
+def sampling_without_replacement(logp, k):
+    u = torch.rand_like(logp)
+    g = -torch.log(-torch.log(u + TINY) + TINY)
+    return (logp + g).topk(k, dim=-1)[1]
+
+
+class NSVFPipeline(nn.Module):
+    def __init__(self, encoder, field, renderer, pixel_per_view=0, bg_depth=5.0):
+        super().__init__()
+        self.encoder, self.field, self.raymarcher = encoder, field, renderer
+        self.pixel_per_view = pixel_per_view
+        self.bg_depth = bg_depth
+
+    def intersecting(self, ray_start, ray_dir, encoder_states):
+        S, V, P, _ = ray_dir.size()
+        sampled = None
+        if self.training and self.pixel_per_view > 0:
+            # `--no-sampling-at-reader`: pixels are drawn from the hit mask of ALL rays (nsvf.py:48-60).  The
+            # reference materialises [V*P, max_hits] x 3 hit lists for every ray and then gathers the sampled rows;
+            # the hit mask alone decides the draw, so we run the any-hit kernel on all rays and the full
+            # intersection only on the sampled ones — identical outputs, no [V*P, max_hits] tensors.
+            if self.encoder.use_octree:
+                ray_start, ray_dir, inter, hits = self.encoder.ray_intersect(ray_start, ray_dir, encoder_states)
+            else:
+                ray_start, ray_dir, hits = self.encoder.ray_hit_mask(ray_start, ray_dir, encoder_states)
+                inter = None
+            mask = hits.reshape(S, V, P).float()
+            probs = mask / (mask.sum() + 1e-8)
+            sampled = sampling_without_replacement(torch.log(probs + TINY), self.pixel_per_view)   # [S,V,k]
+            flat = (sampled + torch.arange(V, device=sampled.device)[None, :, None] * P).reshape(S, -1)
+            flat, _ = flat.sort(-1)                                     # boolean-mask order of the reference
+            take = lambda t: torch.gather(t, 1, flat[..., None].expand(-1, -1, t.size(-1)))
+            ray_start, ray_dir = take(ray_start), take(ray_dir)
+            if inter is None:
+                ray_start, ray_dir, inter, hits = self.encoder.ray_intersect(
+                    ray_start.unsqueeze(1), ray_dir.unsqueeze(1), encoder_states)
+            else:
+                inter = {k: take(v) for k, v in inter.items()}
+                hits = torch.gather(hits, 1, flat)
+            sampled = flat
+        else:
+            ray_start, ray_dir, inter, hits = self.encoder.ray_intersect(ray_start, ray_dir, encoder_states)
+        min_depth, max_depth, pts_idx = inter["min_depth"], inter["max_depth"], inter["intersected_voxel_idx"]
+        dists = (max_depth - min_depth).masked_fill(pts_idx.eq(-1), 0)        # nsvf.py:65-74
+        inter["probs"] = dists / dists.sum(dim=-1, keepdim=True)
+        inter["steps"] = dists.sum(-1) / self.encoder.step_size
+        return ray_start, ray_dir, inter, hits, sampled
+
+    def forward(self, ray_start, ray_dir):
+        S, V, P, _ = ray_dir.size()
+        assert S == 1, "single object only, like the reference (fairnr_model.py:144)"
+        encoder_states = self.encoder.precompute(id=torch.zeros(1, dtype=torch.long, device=ray_dir.device))
+        ray_start, ray_dir, inter, hits, sampled = self.intersecting(ray_start, ray_dir, encoder_states)
+        n_rays = ray_dir.size(1)
+        hits_flat = hits.reshape(-1)
+        inter = {k: v.reshape(-1, *v.shape[2:])[hits_flat] for k, v in inter.items()}
+        rs, rd = ray_start.reshape(-1, 3)[hits_flat], ray_dir.reshape(-1, 3)[hits_flat]
+        encoder_states = {k: v.reshape(-1, v.size(-1)) for k, v in encoder_states.items()}
+        dev = ray_dir.device
+        colors = torch.zeros(n_rays, 3, device=dev)
+        missed = torch.ones(n_rays, device=dev)
+        depths = torch.zeros(n_rays, device=dev)
+        results = {"ae": 0}
+        if rs.size(0) > 0:
+            samples = self.encoder.ray_sample(inter)
+            r = self.raymarcher(self.encoder, self.field, rs, rd, samples, encoder_states)
+            # fill_in (geometry.py:303-317) + background blend (nsvf.py:89-104)
+            where = hits_flat.nonzero(as_tuple=True)[0]
+            colors = colors.index_put((where,), r["colors"])
+            missed = missed.index_put((where,), r["missed"])
+            depths = depths.index_put((where,), r["depths"])
+            results["ae"] = r["ae"]
+            results["samples"] = samples
+        bg = self.field.bg_color if hasattr(self.field, "bg_color") else torch.ones(3, device=dev)
+        results["colors"] = colors + missed.unsqueeze(-1) * bg
+        results["depths"] = depths + missed * self.bg_depth
+        results["missed"] = missed
+        results["hits"] = hits_flat
+        results["sampled"] = sampled
+        return results

@@ -183,3 +183,48 @@ def test_svo_level2_wrapper_matches_reference_wrapper(cuda, ref_ext):
     mine = clib.svo_ray_intersect(0.4, 60, centers[None], children[None], rs, rd)
     ref = wrappers.svo_ray_intersect(ref_ext, 0.4, 60, centers[None], children[None], rs, rd)
     _cmp3(mine, ref, "Level-2 svo_ray_intersect")
+
+
+@pytest.mark.parametrize("times,n_max,n_rays", [(0, 60, 4096), (1, 90, 4096), (2, 135, 4096), (2, 20, 2048)])
+def test_aabb_sorted_and_hit_mask_match_reference_postprocessing(cuda, ref_ext, times, n_max, n_rays):
+    """The fused epilogue == SparseVoxelEncoder.ray_intersect's masked_fill + sort + gather + any (encoder.py:519-524)
+    applied to the reference kernel's output; the any-hit kernel == its `hits`."""
+    pts0 = synthetic.carve_shell(synthetic.bbox_voxels([-2.4] * 3, [2.4] * 3, 0.4))
+    p, vs = synthetic.split_points(pts0, 0.4, times)
+    pts = torch.from_numpy(p).to(cuda)
+    rs, rd = synthetic.camera_rays(64, 64, 1, device=cuda)
+    rs = rs.expand_as(rd)[:, :n_rays].contiguous()
+    rd = rd[:, :n_rays].contiguous()
+    ref = ref_ext.aabb_intersect(rs, rd, pts[None].contiguous(), vs, n_max)
+    r_idx, r_min, r_max, r_hits = wrappers.sort_hits(*ref)
+    idx, dmin, dmax, hits = ours.aabb_intersect_sorted(rs, rd, pts[None].contiguous(), vs, n_max, 10000.0)
+    assert torch.equal(hits, r_hits)
+    assert torch.equal(dmin, r_min), "sorted min_depth differs"
+    # torch.sort is not stable: rows with equal entry depths may permute in the reference; compare the rest exactly
+    ties = (r_min[..., 1:] == r_min[..., :-1]) & (r_idx[..., 1:] != -1)
+    clean = ~ties.any(-1)
+    assert clean.float().mean() > 0.9
+    assert torch.equal(idx[clean], r_idx[clean]) and torch.equal(dmax[clean], r_max[clean])
+    assert torch.equal(idx.sort(-1)[0], r_idx.sort(-1)[0])
+    assert torch.equal(ours.aabb_hit_mask(rs, rd, pts, vs, shared_points=True), r_hits)
+    if n_max >= 135:
+        assert int((idx >= 0).sum(-1).max()) > 32      # exercises the bitonic path
+
+
+def test_encoder_ray_intersect_matches_reference_pipeline(cuda, ref_ext):
+    """SparseVoxelEncoder.ray_intersect (mirror) == reference wrapper + reference post-processing, incl. the x shift."""
+    from nsvf_b200.encoder import SparseVoxelEncoder
+    scene = synthetic.make_scene("C1")
+    enc = SparseVoxelEncoder(scene.points, scene.voxel_size, max_hits=60).to(cuda)
+    st = enc.precompute(id=torch.zeros(1, dtype=torch.long, device=cuda))
+    assert torch.equal(st["voxel_center_xyz"][0, :, 0], enc.points[:, 0] + enc.voxel_size / 10)
+    rs, rd = synthetic.camera_rays(40, 40, 2, radius=3.0, device=cuda)
+    rs, rd = rs[None, :, None, 0, :].contiguous(), rd[None].contiguous()
+    ray_start, ray_dir, inter, hits = enc.ray_intersect(rs, rd, st)
+    ref = wrappers.aabb_ray_intersect(ref_ext, float(enc.voxel_size), int(enc.max_hits), st["voxel_center_xyz"],
+                                      ray_start, ray_dir)
+    r_idx, r_min, r_max, r_hits = wrappers.sort_hits(*ref)
+    assert torch.equal(hits, r_hits) and torch.equal(inter["min_depth"], r_min)
+    assert torch.equal(inter["intersected_voxel_idx"].sort(-1)[0], r_idx.sort(-1)[0])
+    _, _, h2 = enc.ray_hit_mask(rs, rd, st)
+    assert torch.equal(h2, r_hits)

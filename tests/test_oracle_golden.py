@@ -1,0 +1,146 @@
+"""CPU tests (no GPU): the oracle is pinned against golden vectors produced by the reference itself —
+gpu_*.npz from the reference's CUDA kernels (tests/golden/make_gpu_golden.py, run on a B200) and cpu_*.npz from the
+reference's Python modules + C++ octree builder (tests/golden/make_cpu_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import wrappers
+from nsvf_b200 import synthetic
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+load = lambda name: np.load(os.path.join(G, name))
+
+
+@pytest.mark.parametrize("name", ["gpu_aabb_nmax12.npz", "gpu_aabb_nmax3.npz"])
+def test_oracle_aabb_matches_reference_cuda(name):
+    z = load(name)
+    idx, dmin, dmax = oracle.aabb_intersect(z["ray_start"][None], z["ray_dir"][None], z["points"], float(z["voxel_size"]),
+                                            int(z["n_max"]), z["inv_dir"][None])
+    assert np.array_equal(idx[0], z["idx"])
+    assert np.array_equal(dmin[0], z["min_depth"]) and np.array_equal(dmax[0], z["max_depth"])
+    assert (z["idx"] >= 0).sum() > 500
+    # with IEEE reciprocals instead of the GPU's: identical on this margin-safe set except for grazing rays
+    idx2, _, _ = oracle.aabb_intersect(z["ray_start"][None], z["ray_dir"][None], z["points"], float(z["voxel_size"]),
+                                       int(z["n_max"]))
+    assert (idx2[0] != z["idx"]).any(-1).mean() < 0.02
+
+
+@pytest.mark.parametrize("name", ["gpu_svo_nmax20.npz", "gpu_svo_nmax2.npz"])
+def test_oracle_svo_matches_reference_cuda(name):
+    z = load(name)
+    idx, dmin, dmax = oracle.svo_intersect(z["ray_start"][None], z["ray_dir"][None], z["centers"], z["children"],
+                                           float(z["voxel_size"]), int(z["n_max"]), z["inv_dir"][None])
+    assert np.array_equal(idx[0], z["idx"])
+    assert np.array_equal(dmin[0], z["min_depth"]) and np.array_equal(dmax[0], z["max_depth"])
+    assert (z["idx"] >= 0).sum() > 200
+
+
+@pytest.mark.parametrize("name", ["gpu_inverse_cdf_auto.npz", "gpu_inverse_cdf_fixed.npz"])
+def test_oracle_inverse_cdf_matches_reference_cuda(name):
+    z = load(name)
+    si, sd, ss = oracle.inverse_cdf_sampling(z["pts_idx"], z["min_depth"], z["max_depth"], z["noise"], z["probs"],
+                                             z["steps"], float(z["fixed_step_size"]))
+    assert np.array_equal(si, z["sampled_idx"])
+    assert np.array_equal(sd, z["sampled_depth"]) and np.array_equal(ss, z["sampled_dists"])
+    assert (si != -1).sum() > 5000
+
+
+def test_oracle_uniform_matches_reference_cuda():
+    z = load("gpu_uniform.npz")
+    si, sd, ss = oracle.uniform_ray_sampling(z["pts_idx"], z["min_depth"], z["max_depth"], z["noise"],
+                                             float(z["step_size"]), int(z["max_steps"]))
+    assert np.array_equal(si, z["sampled_idx"])
+    valid = si != -1    # beyond the compacted prefix the reference leaves stale values of its in-place merge (B10)
+    assert np.array_equal(sd[valid], z["sampled_depth"][valid]) and np.array_equal(ss[valid], z["sampled_dists"][valid])
+    assert valid.sum() > 5000
+
+
+def test_oracle_octree_matches_reference_builder():
+    z = load("cpu_octree.npz")
+    coords = z["coords"].astype(np.int64)
+    rng = coords.max(0) - coords.min(0)
+    depth = int(np.ceil(np.log2(rng.max()))) - 1
+    center = (coords.max(0) + coords.min(0)) / 2
+    centers, children = oracle.build_octree(center, coords, depth)
+    assert np.array_equal(children, z["children"])
+    pts = z["points"]
+    half = np.float32(z["half_voxel"])
+    residual = (pts - coords.astype(np.float32) * half).astype(np.float64).mean(0, keepdims=True).astype(np.float32)
+    np.testing.assert_allclose(centers.astype(np.float32) * half + residual, z["centers"], rtol=0, atol=2e-6)
+    assert (children[:, 8] == 1).sum() == len(pts)      # leaf k == voxel k
+    assert np.array_equal(centers[:len(pts)], coords.astype(np.int32))
+
+
+def test_oracle_octree_kat5():
+    """KAT-5: 9^3 grid -> T = 1314, size histogram {1:729, 2:512, 4:64, 8:8, 16:1}."""
+    pts = np.stack(np.meshgrid(*[np.arange(0, 17, 2)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    centers, children = oracle.build_octree(np.array([8, 8, 8]), pts, 3)
+    assert centers.shape == (1314, 3)
+    sizes, counts = np.unique(children[:, 8], return_counts=True)
+    assert dict(zip(sizes.tolist(), counts.tolist())) == {1: 729, 2: 512, 4: 64, 8: 8, 16: 1}
+    assert children[-1].tolist() == [1312, 1311, 1310, 1309, 1308, 1307, 1306, 1305, 16]
+
+
+def test_oracle_trilinear_matches_reference_python():
+    z = load("cpu_trilinear.npz")
+    emb = oracle.trilinear_fwd(z["vox"], z["xyz"], z["feats"], z["points"], z["values"], float(z["voxel_size"]))
+    np.testing.assert_allclose(emb, z["emb"], rtol=1e-5, atol=1e-6)
+    gv, gx = oracle.trilinear_bwd(z["vox"], z["xyz"], z["feats"], z["points"], z["values"], float(z["voxel_size"]),
+                                  z["grad_out"])
+    assert np.abs(gv - z["grad_values"]).max() <= 1e-5 * np.abs(z["grad_values"]).max()
+    assert np.abs(gx - z["grad_xyz"]).max() <= 1e-5 * np.abs(z["grad_xyz"]).max()
+
+
+def _fake_field_np(emb):
+    return emb[:, 0] * 6 + emb[:, 5] * 3 + 0.5, np.tanh(emb[:, 1:4] * 2)
+
+
+def test_oracle_interp_plus_composite_matches_reference_renderer():
+    """oracle trilinear + oracle compositing reproduce VolumeRenderer.forward_chunk (reference, eval, no early stop)."""
+    z, t = load("cpu_renderer.npz"), load("cpu_trilinear.npz")
+    sidx, sdep, sdist = z["sampled_idx"], z["sampled_depth"], z["sampled_dists"]
+    mask = sidx != -1
+    xyz = (z["ray_start"][:, None] + z["ray_dir"][:, None] * sdep[..., None])[mask]
+    emb = oracle.trilinear_fwd(sidx[mask], xyz, t["feats"], t["points"], t["values"], float(t["voxel_size"]))
+    sigma, tex_c = _fake_field_np(emb)
+    fe = np.zeros_like(sdep)
+    fe[mask] = np.maximum(sigma, 0) * sdist[mask] * np.float32(7.0)
+    tex = np.zeros(sdep.shape + (3,), np.float32)
+    tex[mask] = tex_c
+    probs, depth, missed, colors = oracle.composite_fwd(fe, tex, sdep)
+    for a, b in ((probs, z["plain_probs"]), (depth, z["plain_depths"]), (1 - missed, 1 - z["plain_missed"]),
+                 (colors, z["plain_colors"])):
+        assert np.abs(a - b).max() <= 1e-5 * np.abs(b).max()
+    assert int(z["plain_ae"]) == int(mask.sum())
+
+
+def test_host_corner_keys_match_reference_encoder():
+    """KAT-1: 512 voxels, 729 keys; voxel index = iy*(nx*nz) + ix*nz + iz; keys in lexicographic order."""
+    z = load("cpu_kat1_encoder.npz")
+    pts = synthetic.bbox_voxels([-0.875] * 3, [0.875] * 3, 0.25)
+    assert np.array_equal(pts, z["points"]) and pts.shape == (512, 3)
+    feats, keys = synthetic.corner_keys(pts, 0.25)
+    assert np.array_equal(feats, z["feats"]) and np.array_equal(keys, z["keys"]) and keys.shape == (729, 3)
+    assert float(z["step_size"]) == 0.03125 and float(z["max_hits"]) == 60.0
+
+
+def test_oracle_properties():
+    """Size-independent properties: hits ascending & truncated, samples inside their bins, probs + missed = 1."""
+    scene = synthetic.make_scene("C1")
+    o, d = synthetic.random_rays(512, seed=3)
+    idx, dmin, dmax = oracle.aabb_intersect(o[None], d[None], scene.points, scene.voxel_size, 60)
+    idx = idx[0]
+    valid = idx >= 0
+    nxt = np.where(valid[:, 1:], idx[:, 1:], 10 ** 9)
+    assert (np.where(valid[:, :-1], idx[:, :-1], -1) < nxt).all()            # ascending voxel index, -1 tail
+    cut = oracle.aabb_intersect(o[None], d[None], scene.points, scene.voxel_size, 5)[0][0]
+    assert np.array_equal(cut, idx[:, :5])
+    assert (dmax[0][valid] >= dmin[0][valid]).all()
+    fe = np.abs(np.random.RandomState(0).randn(64, 50)).astype(np.float32) * 0.1
+    probs, depth, missed, colors = oracle.composite_fwd(fe, None, np.ones_like(fe))
+    np.testing.assert_allclose(probs.sum(-1) + missed, 1.0, atol=1e-6)
+    np.testing.assert_allclose(missed, np.exp(-fe.sum(-1)), atol=1e-6)     # 1 - sum(probs): eps(1.0)-level error
