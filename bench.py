@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-frame", action="store_true", help="skip the C3 full-frame extra")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stages", action="store_true", help="skip the informational per-stage timings")
     ap.add_argument("--cpu-fraction", type=int, default=16, help="CPU arms run 1/FRACTION of the rays per step")
     return ap.parse_args()
 
@@ -182,7 +183,7 @@ def run_ours(args):
         for i in range(n):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); b.record()                                    # materialise the cudaEvent_t handles
-            _lib.check(L.nsvf_profile_kernel(b"aabb_intersect_kernel", a.cuda_event, b.cuda_event))
+            _lib.check(L.nsvf_profile_kernel(b"aabb_hit_mask_kernel", a.cuda_event, b.cuda_event))
             if from_host:
                 hb = host[i % len(host)]
                 for d, s in zip(staging, hb):
@@ -218,7 +219,10 @@ def run_ours(args):
     e2e_value = world * rays_marched * args.steps / (ms_e2e / 1e3)
     h2d = sum(t.numel() * t.element_size() for t in host[0])
 
-    # roofline of the dominant hand-written kernel: algorithmic bytes = 24 B/ray in + 12*P B/ray out (+ scene once)
+    # roofline of the dominant hand-written kernel of the step (largest share of device time among ours, see
+    # profiles/): the any-hit intersection over all V*H*W rays.  Algorithmic bytes = 24 B/ray in + 1 B/ray out
+    # (+ 12 B/voxel once).  It is ALU/issue-bound by design (intersection is not HBM-bound), so the
+    # HBM fraction is expected to be small; the HBM-bound kernels are reported under "roofline_at_scale".
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -226,10 +230,10 @@ def run_ours(args):
         pass
     peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") else (6650.0, "fallback")
     P = scene.max_hits
-    alg_bytes = rays_intersected * (24 + 12 * P) + 12 * scene.n
+    alg_bytes = rays_intersected * (24 + 1) + 12 * scene.n
     k_ms = float(np.mean(kms))
     achieved = alg_bytes / (k_ms / 1e3) / 1e9
-    roofline = {"kernel": "aabb_intersect_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
+    roofline = {"kernel": "aabb_hit_mask_kernel (aabb_intersect_kernel<NL, any-hit>)", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                 "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_launch": alg_bytes,
                 "share_of_step": round(k_ms / (ms / args.steps), 4)}
@@ -250,7 +254,11 @@ def run_ours(args):
         "roofline": roofline, "loss": round(loss_val, 5),
     }
 
-    if rank == 0:
+    if rank == 0 and not args.no_stages:
+        try:
+            line["roofline_at_scale"] = roofline_at_scale(dev, peak)
+        except Exception as e:
+            line["roofline_at_scale"] = {"error": repr(e)[:200]}
         try:
             line["stages_ms"] = stage_times(dev, pipe, resident[0])
         except Exception as e:   # informational only
@@ -285,6 +293,50 @@ def _time(fn, n=5, warm=2):
     e1.record()
     torch.cuda.synchronize()
     return round(e0.elapsed_time(e1) / n, 4)
+
+
+def roofline_at_scale(dev, peak):
+    """The HBM-bound kernels at full-frame sizes (C3 scene, 40 M samples / 262144 x 256 rays x samples), timed with
+    CUDA events around the C-ABI calls.  Algorithmic bytes per unit are SURVEY.md §8d's figures."""
+    from nsvf_b200 import synthetic, _lib
+    L, p = _lib.load(), _lib.ptr
+    scene = synthetic.make_scene("C3")
+    pts = torch.from_numpy(scene.points).to(dev)
+    feats = torch.from_numpy(scene.feats).int().to(dev)
+    values = torch.from_numpy(scene.values).to(dev)
+    M = 40_000_000
+    g = torch.Generator(device=dev).manual_seed(0)
+    vox = torch.randint(0, scene.n, (M // 6 + 1,), device=dev, generator=g).repeat_interleave(6)[:M].int().contiguous()
+    xyz = (pts[vox.long()] + (torch.rand(M, 3, device=dev, generator=g) - 0.5) * scene.voxel_size).contiguous()
+    out = torch.empty(M, 32, device=dev)
+    gv = torch.zeros_like(values)
+    st = torch.cuda.current_stream().cuda_stream
+    res = {}
+
+    def rec(name, fn, nbytes):
+        ms = _time(fn, n=5, warm=2)
+        res[name] = {"ms": ms, "achieved_GBs": round(nbytes / ms / 1e6, 1), "frac": round(nbytes / ms / 1e6 / peak, 4),
+                     "algorithmic_bytes": nbytes}
+    rec("trilinear_fwd (40M samples, 144 B/sample)",
+        lambda: L.nsvf_trilinear_embed_fwd(st, M, 32, p(vox), p(xyz), p(feats), p(pts), p(values), scene.voxel_size, p(out)),
+        M * 144)
+    rec("trilinear_bwd (40M samples, 144 B/sample)",
+        lambda: L.nsvf_trilinear_embed_bwd(st, M, 32, p(vox), p(xyz), p(feats), p(pts), p(values), scene.voxel_size,
+                                           p(out), p(gv), None), M * 144)
+    del out, xyz, vox
+    B, K = 262144, 256
+    fe = torch.rand(B, K, device=dev) * 0.1
+    tex = torch.rand(B, K, 3, device=dev)
+    dep = torch.rand(B, K, device=dev)
+    probs, od, om, oc = (torch.empty(B, K, device=dev), torch.empty(B, device=dev), torch.empty(B, device=dev),
+                         torch.empty(B, 3, device=dev))
+    rec("composite_fwd (262144 x 256, 28 B/sample)",
+        lambda: L.nsvf_composite_fwd(st, B, K, p(fe), p(tex), p(dep), p(probs), p(od), p(om), p(oc)), B * K * 28 + B * 20)
+    gfe, gtex = torch.empty(B, K, device=dev), torch.empty(B, K, 3, device=dev)
+    rec("composite_bwd (262144 x 256, 36 B/sample)",
+        lambda: L.nsvf_composite_bwd(st, B, K, p(fe), p(tex), p(dep), None, p(od), p(om), p(oc), p(gfe), p(gtex)),
+        B * K * 36 + B * 20)
+    return res
 
 
 def stage_times(dev, pipe, batch):

@@ -405,7 +405,9 @@ static int aabb_launch(cudaStream_t stream, dim3 grid, size_t smem, const AabbTr
                                       200 * 1024));
     attr_set = true;
   }
-  NSVF_TIMED_LAUNCH("aabb_intersect_kernel", stream,
+  const char* kname = MODE == kModeAnyHit ? "aabb_hit_mask_kernel"
+                      : (MODE == kModeDepthSorted ? "aabb_intersect_sorted_kernel" : "aabb_intersect_kernel");
+  NSVF_TIMED_LAUNCH(kname, stream,
                     (aabb_intersect_kernel<NL, MODE><<<grid, kAabbWarps * 32, smem, stream>>>(
                         tree, tree_stride_box, rays_per_tree, n_max, sort_slots, empty_depth, ray_start, ray_dir, idx,
                         dmin, dmax, hit)));

@@ -207,6 +207,159 @@ trilinear_bwd_generic_kernel(long long M, int D, const int* __restrict__ sampled
   }
 }
 
+// ---- D == 32, second generation ---------------------------------------------------------------------------
+// A warp takes 32 consecutive samples.  Phase A: one lane per sample computes the 8 corner weights once (the
+// first-generation kernel recomputed them in all 8 lanes of a sample's group, IEEE divisions included) and parks
+// {weights, corner keys, voxel id} in shared memory.  Phase B: the four 8-lane groups each walk 8 CONSECUTIVE
+// samples, one float4 (4 dims) per lane; the 8 corner rows stay in registers while the voxel id does not change
+// (ray-marched samples arrive in ray order, ~8 per voxel at step = voxel/8), so most samples cost 4 LDS.128,
+// 32 FMAs and one coalesced 128-byte store.
+constexpr int kTriRow = 20;   // words per staged sample: 8 weights, 8 keys, voxel id, 3 pad (80 B, 16-B aligned)
+
+struct TriSample { int v; float x, y, z; };
+
+__device__ __forceinline__ TriSample tri_load(long long s, long long M, const int* __restrict__ sampled_idx,
+                                              const float* __restrict__ xyz) {
+  TriSample t;
+  t.v = -1; t.x = t.y = t.z = 0.f;
+  if (s < M) {
+    t.v = __ldcs(sampled_idx + s);
+    t.x = __ldcs(xyz + s * 3 + 0);
+    t.y = __ldcs(xyz + s * 3 + 1);
+    t.z = __ldcs(xyz + s * 3 + 2);
+  }
+  return t;
+}
+
+__device__ __forceinline__ void tri_phase_a(const TriSample& t, const int* __restrict__ feats,
+                                            const float* __restrict__ centres, float voxel_size, float* row) {
+  float w[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int4 k0 = make_int4(0, 0, 0, 0), k1 = make_int4(0, 0, 0, 0);
+  if (t.v >= 0) {
+    const float cx = __ldg(centres + (long long)t.v * 3 + 0), cy = __ldg(centres + (long long)t.v * 3 + 1),
+                cz = __ldg(centres + (long long)t.v * 3 + 2);
+    k0 = __ldg(reinterpret_cast<const int4*>(feats + (long long)t.v * 8));
+    k1 = __ldg(reinterpret_cast<const int4*>(feats + (long long)t.v * 8) + 1);
+    const float px = __fadd_rn(__fdiv_rn(__fsub_rn(t.x, cx), voxel_size), 0.5f);
+    const float py = __fadd_rn(__fdiv_rn(__fsub_rn(t.y, cy), voxel_size), 0.5f);
+    const float pz = __fadd_rn(__fdiv_rn(__fsub_rn(t.z, cz), voxel_size), 0.5f);
+    corner_weights(px, py, pz, w);
+  }
+  reinterpret_cast<float4*>(row)[0] = make_float4(w[0], w[1], w[2], w[3]);
+  reinterpret_cast<float4*>(row)[1] = make_float4(w[4], w[5], w[6], w[7]);
+  reinterpret_cast<int4*>(row)[2] = k0;
+  reinterpret_cast<int4*>(row)[3] = k1;
+  reinterpret_cast<int*>(row)[16] = t.v;
+}
+
+__global__ void __launch_bounds__(256, 3)
+trilinear_fwd_d32_v2_kernel(long long M, const int* __restrict__ sampled_idx, const float* __restrict__ xyz,
+                            const int* __restrict__ feats, const float* __restrict__ centres,
+                            const float* __restrict__ values, float voxel_size, float* __restrict__ out) {
+  __shared__ __align__(16) float stage[8][32 * kTriRow];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
+  float* st = stage[warp];
+  const long long n_chunks = (M + 31) / 32;
+  const long long c_first = (long long)blockIdx.x * 8 + warp, c_step = (long long)gridDim.x * 8;
+  TriSample cur = tri_load(c_first * 32 + lane, c_first < n_chunks ? M : 0, sampled_idx, xyz);
+  for (long long c = c_first; c < n_chunks; c += c_step) {
+    const long long s0 = c * 32;
+    // software pipeline: the next chunk's index / position loads are in flight during this chunk's work
+    const TriSample nxt = tri_load((c + c_step) * 32 + lane, (c + c_step) < n_chunks ? M : 0, sampled_idx, xyz);
+    tri_phase_a(cur, feats, centres, voxel_size, st + lane * kTriRow);
+    cur = nxt;
+    __syncwarp();
+    int prev = -2;
+    float4 e[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int sl = g * 8 + r;
+      const float* row = st + sl * kTriRow;
+      const int v = reinterpret_cast<const int*>(row)[16];
+      if (v >= 0) {
+        if (v != prev) {
+          const int4 k0 = reinterpret_cast<const int4*>(row)[2], k1 = reinterpret_cast<const int4*>(row)[3];
+          const int key[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            e[j] = __ldg(reinterpret_cast<const float4*>(values + (long long)key[j] * 32) + sub);
+          prev = v;
+        }
+        const float4 w0 = reinterpret_cast<const float4*>(row)[0], w1 = reinterpret_cast<const float4*>(row)[1];
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        float4 acc = make_float4(w[0] * e[0].x, w[0] * e[0].y, w[0] * e[0].z, w[0] * e[0].w);
+#pragma unroll
+        for (int j = 1; j < 8; ++j) {
+          acc.x = fmaf(w[j], e[j].x, acc.x);
+          acc.y = fmaf(w[j], e[j].y, acc.y);
+          acc.z = fmaf(w[j], e[j].z, acc.z);
+          acc.w = fmaf(w[j], e[j].w, acc.w);
+        }
+        __stcs(reinterpret_cast<float4*>(out + (s0 + sl) * 32) + sub, acc);   // streaming store: written once
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256, 3)
+trilinear_bwd_d32_v2_kernel(long long M, const int* __restrict__ sampled_idx, const float* __restrict__ xyz,
+                            const int* __restrict__ feats, const float* __restrict__ centres, float voxel_size,
+                            const float* __restrict__ grad_out, float* __restrict__ grad_values) {
+  __shared__ __align__(16) float stage[8][32 * kTriRow];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
+  float* st = stage[warp];
+  const long long n_chunks = (M + 31) / 32;
+  const long long c_first = (long long)blockIdx.x * 8 + warp, c_step = (long long)gridDim.x * 8;
+  TriSample cur = tri_load(c_first * 32 + lane, c_first < n_chunks ? M : 0, sampled_idx, xyz);
+  for (long long c = c_first; c < n_chunks; c += c_step) {
+    const long long s0 = c * 32;
+    // software pipeline: the next chunk's index / position loads are in flight during this chunk's work
+    const TriSample nxt = tri_load((c + c_step) * 32 + lane, (c + c_step) < n_chunks ? M : 0, sampled_idx, xyz);
+    tri_phase_a(cur, feats, centres, voxel_size, st + lane * kTriRow);
+    cur = nxt;
+    __syncwarp();
+    int prev = -2;
+    int key[8];
+    float4 acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int sl = g * 8 + r;
+      const float* row = st + sl * kTriRow;
+      const int v = reinterpret_cast<const int*>(row)[16];
+      if (v >= 0) {
+        if (v != prev) {
+          if (prev >= 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) red_add_v4(grad_values + (long long)key[j] * 32 + sub * 4, acc[j]);
+          }
+          const int4 k0 = reinterpret_cast<const int4*>(row)[2], k1 = reinterpret_cast<const int4*>(row)[3];
+          key[0] = k0.x; key[1] = k0.y; key[2] = k0.z; key[3] = k0.w;
+          key[4] = k1.x; key[5] = k1.y; key[6] = k1.z; key[7] = k1.w;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          prev = v;
+        }
+        const float4 w0 = reinterpret_cast<const float4*>(row)[0], w1 = reinterpret_cast<const float4*>(row)[1];
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const float4 gq = __ldcs(reinterpret_cast<const float4*>(grad_out + (s0 + sl) * 32) + sub);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j].x = fmaf(w[j], gq.x, acc[j].x);
+          acc[j].y = fmaf(w[j], gq.y, acc[j].y);
+          acc[j].z = fmaf(w[j], gq.z, acc[j].z);
+          acc[j].w = fmaf(w[j], gq.w, acc[j].w);
+        }
+      }
+    }
+    if (prev >= 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red_add_v4(grad_values + (long long)key[j] * 32 + sub * 4, acc[j]);
+    }
+    __syncwarp();
+  }
+}
+
 static int grid_for(long long work_items, int items_per_block, int max_blocks_per_sm) {
   long long want = (work_items + items_per_block - 1) / items_per_block;
   long long cap = (long long)num_sms() * max_blocks_per_sm;
@@ -227,8 +380,11 @@ extern "C" int nsvf_trilinear_embed_fwd(nsvf_stream_t stream_, long long M, int 
   if (D == 32) {
     NSVF_REQUIRE((((uintptr_t)values | (uintptr_t)out | (uintptr_t)feats) & 15) == 0,
                  "trilinear_embed_fwd: values/out/feats must be 16-byte aligned");
-    trilinear_fwd_d32_kernel<<<grid_for(M, 32, 16), 256, 0, stream>>>(M, sampled_idx, sampled_xyz, feats, centres,
-                                                                      values, voxel_size, out);
+    NSVF_REQUIRE(((uintptr_t)values & 15) == 0, "trilinear_embed_fwd: values must be 16-byte aligned");
+    NSVF_TIMED_LAUNCH("trilinear_fwd_kernel", stream,
+                      (trilinear_fwd_d32_v2_kernel<<<grid_for((M + 31) / 32, 8, 8), 256, 0, stream>>>(
+                          M, sampled_idx, sampled_xyz, feats, centres, values, voxel_size, out)));
+    return 0;
   } else {
     trilinear_fwd_generic_kernel<<<grid_for(M, 8, 16), 256, 0, stream>>>(M, D, sampled_idx, sampled_xyz, feats,
                                                                          centres, values, voxel_size, out);
@@ -247,6 +403,12 @@ extern "C" int nsvf_trilinear_embed_bwd(nsvf_stream_t stream_, long long M, int 
   if (D == 32) {
     NSVF_REQUIRE((((uintptr_t)values | (uintptr_t)grad_out | (uintptr_t)grad_values | (uintptr_t)feats) & 15) == 0,
                  "trilinear_embed_bwd: values/grad_out/grad_values/feats must be 16-byte aligned");
+    if (grad_xyz == nullptr) {
+      NSVF_TIMED_LAUNCH("trilinear_bwd_kernel", stream,
+                        (trilinear_bwd_d32_v2_kernel<<<grid_for((M + 31) / 32, 8, 8), 256, 0, stream>>>(
+                            M, sampled_idx, sampled_xyz, feats, centres, voxel_size, grad_out, grad_values)));
+      return 0;
+    }
     const long long runs = (M + kTriRun - 1) / kTriRun;
     trilinear_bwd_d32_kernel<<<grid_for(runs, 32, 16), 256, 0, stream>>>(M, sampled_idx, sampled_xyz, feats, centres,
                                                                          values, voxel_size, grad_out, grad_values,

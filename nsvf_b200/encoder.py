@@ -25,7 +25,8 @@ MAX_DEPTH = 10000.0
 
 class SparseVoxelEncoder(nn.Module):
     def __init__(self, points, voxel_size, max_hits=60, raymarching_stepsize_ratio=0.125, raymarching_stepsize=0.01,
-                 voxel_embed_dim=32, deterministic_step=False, use_octree=False, track_max_probs=False):
+                 voxel_embed_dim=32, deterministic_step=False, use_octree=False, track_max_probs=False,
+                 track_xyz_grad=False):
         super().__init__()
         fine_points = torch.as_tensor(points, dtype=torch.float32)
         half_voxel = voxel_size * .5
@@ -43,6 +44,10 @@ class SparseVoxelEncoder(nn.Module):
         self.deterministic_step = deterministic_step
         self.use_octree = use_octree
         self.track_max_probs = track_max_probs
+        # The reference marks every sample position as requiring grad (encoder.py:568) so that fields which use
+        # surface normals can differentiate sigma w.r.t. position; nsvf_base does not, and the flag then only
+        # buys a wasted d/dxyz in every backward.  Set True for normal-based fields.
+        self.track_xyz_grad = track_xyz_grad
         self._runtime_caches = {"flatten_centers": None, "flatten_children": None, "max_voxel_probs": None}
         self.values = nn.Embedding(int(self.num_keys), voxel_embed_dim)
         nn.init.normal_(self.values.weight, mean=0, std=voxel_embed_dim ** -0.5)   # module_utils.py:23-26
@@ -174,7 +179,9 @@ class SparseVoxelEncoder(nn.Module):
         point_xyz = encoder_states["voxel_center_xyz"]
         values = encoder_states["voxel_vertex_emb"]
         sampled_idx = samples["sampled_point_voxel_idx"]
-        sampled_xyz = samples["sampled_point_xyz"].requires_grad_(True)
+        sampled_xyz = samples["sampled_point_xyz"]
+        if self.track_xyz_grad:
+            sampled_xyz = sampled_xyz.requires_grad_(True)
         inputs = {"pos": sampled_xyz, "ray": samples["sampled_point_ray_direction"],
                   "dists": samples["sampled_point_distance"]}
         if values is not None:

@@ -98,8 +98,8 @@ class VolumeRenderer(nn.Module):
             tolerance = -math.log(tolerance)
         hits = sampled_idx.ne(-1)
         col_counts = hits.sum(0).tolist()        # ONE device->host copy (the reference syncs once per column)
-        fe_full = torch.zeros(B * K, dtype=torch.float32, device=dev)
-        tex_full = torch.zeros(B * K, 3, dtype=torch.float32, device=dev) if "texture" in output_types else None
+        want_tex = "texture" in output_types
+        flats, fes, texs = [], [], []           # compacted per-chunk outputs; scattered to [B,K] ONCE at the end
         early_stop, acc_fe, evals = None, None, 0
         size_so_far, start = 0, 0
         for i in range(K + 1):
@@ -110,20 +110,31 @@ class VolumeRenderer(nn.Module):
                                            noise=None if noise_fn is None else noise_fn(start, i))
                 if out is not None:
                     evals += n
+                    flats.append(out["flat"])
                     if "free_energy" in out:
-                        fe_full = fe_full.index_put((out["flat"],), out["free_energy"].float())
+                        fes.append(out["free_energy"].float())
                         if tolerance > 0:
-                            chunk_fe = fe_full.view(B, K)[:, start:i].sum(1)
+                            # per-ray free energy of this chunk (reference: _outputs['free_energy'].sum(1))
+                            chunk_fe = torch.zeros(B, dtype=torch.float32, device=dev).index_add_(
+                                0, torch.div(out["flat"], K, rounding_mode="floor"), fes[-1].detach())
                             acc_fe = chunk_fe if acc_fe is None else acc_fe + chunk_fe
                             early_stop = acc_fe > tolerance
                             hits = hits & ~early_stop[:, None]
                             col_counts = hits.sum(0).tolist()   # the schedule depends on who stopped
                     if "texture" in out:
-                        tex_full = tex_full.index_put((out["flat"],), out["texture"].float())
+                        texs.append(out["texture"].float())
                 start, size_so_far = i, 0
             if i < K:
                 size_so_far += col_counts[i]
 
+        fe_full = torch.zeros(B * K, dtype=torch.float32, device=dev)
+        tex_full = torch.zeros(B * K, 3, dtype=torch.float32, device=dev) if want_tex else None
+        if flats:
+            flat = torch.cat(flats) if len(flats) > 1 else flats[0]
+            if fes:
+                fe_full = fe_full.index_put((flat,), torch.cat(fes) if len(fes) > 1 else fes[0])
+            if texs:
+                tex_full = tex_full.index_put((flat,), torch.cat(texs) if len(texs) > 1 else texs[0])
         fe = fe_full.view(B, K)
         tex = tex_full.view(B, K, 3) if tex_full is not None else None
         probs, depth, missed, colors = ops.composite(fe, tex, sampled_depth)
