@@ -175,6 +175,12 @@ NSVF_API int nsvf_compact_fill(nsvf_stream_t stream, long long B, int K, int col
                                const long long* offsets_incl, int* out_vox, float* out_xyz, float* out_dir,
                                float* out_dists, long long* out_flat);
 
+/* counts i32 [col1 - col0] (fully written): counts[k - col0] = number of rays with sampled_idx[ray,k] != -1 and
+ * early_stop[ray] == 0, k in [col0, col1) — the per-column totals VolumeRenderer.forward_chunk's chunk scheduler
+ * needs (fairnr/modules/renderer.py:158,187: one `hits[:, i].sum()` host sync per column in the reference). */
+NSVF_API int nsvf_masked_col_counts(nsvf_stream_t stream, long long B, int K, int col0, int col1,
+                                    const int* sampled_idx, const unsigned char* early_stop, int* counts);
+
 /* ---- half-voxel splitting --------------------------------------------------------------------------------
  * Replaces splitting_points, fairnr/data/geometry.py:250-274 (+ discretize_points :241-247, offset_points
  * :229-238), called by SparseVoxelEncoder.splitting, fairnr/modules/encoder.py:656-676.

@@ -7,8 +7,9 @@ Same interface — forward(input_fn, field_fn, ray_start, ray_dir, samples, enco
 reach the field is identical to the reference's, including under raymarching_tolerance > 0.
 
 What changes underneath:
-  * the schedule is computed from ONE device->host copy of per-column sample counts (plus one per chunk only
-    when early termination is on), instead of one `.sum()` host sync per sample column (K+1 syncs);
+  * the schedule is computed from windowed device->host copies of per-column sample counts (48 columns per copy;
+    re-fetched after a chunk only when early termination changed who is alive), instead of one `.sum()` host sync
+    per sample column (K+1 syncs);
   * boolean-mask compaction of five tensors + masked_scatter back (renderer.py:100,109-114) become the
     compaction kernels (csrc/compact.cu) and one index_put per output;
   * compositing (renderer.py:193-218) is the fused ops.composite kernel with its own backward.
@@ -24,12 +25,38 @@ _L = _lib.load()
 _p = _lib.ptr
 
 
+class _ColumnCounts:
+    """Lazy per-column valid-sample counts for the chunk scheduler: fetched in windows of `window` columns (one small
+    kernel + one D2H copy per window) and invalidated when the early-stop mask changes."""
+
+    def __init__(self, sampled_idx, window=48):
+        self.idx, self.window = sampled_idx, window
+        self.B, self.K = sampled_idx.shape
+        self.es, self.cache, self.lo = None, [], 0
+
+    def set_early_stop(self, early_stop, col0):
+        self.es = early_stop.to(torch.uint8).contiguous()
+        self.cache, self.lo = [], col0
+
+    def __getitem__(self, k):
+        if not (self.lo <= k < self.lo + len(self.cache)):
+            lo, hi = k, min(self.K, k + self.window)
+            dev = self.idx.device
+            counts = torch.empty(hi - lo, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(_L.nsvf_masked_col_counts(_lib.current_stream(dev), self.B, self.K, lo, hi, _p(self.idx),
+                                                     _p(self.es), _p(counts)))
+            self.cache, self.lo = counts.tolist(), lo
+        return self.cache[k - self.lo]
+
+
 def compact_samples(sampled_idx, sampled_depth, sampled_dists, ray_start, ray_dir, col0, col1, early_stop=None,
                     total=None):
     """Row-major compaction of the valid samples of columns [col0, col1).  Returns
     (vox i32 [M], xyz f32 [M,3], dir f32 [M,3], dists f32 [M], flat i64 [M]); `total` (host int) avoids a sync."""
     B, K = sampled_idx.shape
     dev = sampled_idx.device
+    # no-ops when forward_chunk already prepared them (it does so once, not once per chunk)
     sampled_idx = sampled_idx.int().contiguous()
     sampled_depth = sampled_depth.float().contiguous()
     sampled_dists = sampled_dists.float().contiguous()
@@ -88,6 +115,11 @@ class VolumeRenderer(nn.Module):
 
     def forward_chunk(self, input_fn, field_fn, ray_start, ray_dir, samples, encoder_states,
                       output_types=("sigma", "texture"), global_weights=None, noise_fn=None):
+        # dense, typed copies ONCE per call (the sampler returns [:, :max_len] views)
+        samples = {"sampled_point_depth": samples["sampled_point_depth"].float().contiguous(),
+                   "sampled_point_distance": samples["sampled_point_distance"].float().contiguous(),
+                   "sampled_point_voxel_idx": samples["sampled_point_voxel_idx"].int().contiguous()}
+        ray_start, ray_dir = ray_start.float().contiguous(), ray_dir.float().contiguous()
         sampled_depth = samples["sampled_point_depth"]
         sampled_idx = samples["sampled_point_voxel_idx"]
         B, K = sampled_idx.shape
@@ -96,8 +128,7 @@ class VolumeRenderer(nn.Module):
         chunk_size = self.chunk_size if self.training else self.valid_chunk_size
         if tolerance > 0:
             tolerance = -math.log(tolerance)
-        hits = sampled_idx.ne(-1)
-        col_counts = hits.sum(0).tolist()        # ONE device->host copy (the reference syncs once per column)
+        col_counts = _ColumnCounts(sampled_idx)   # windowed D2H copies (reference: one host sync per column)
         want_tex = "texture" in output_types
         flats, fes, texs = [], [], []           # compacted per-chunk outputs; scattered to [B,K] ONCE at the end
         early_stop, acc_fe, evals = None, None, 0
@@ -119,8 +150,7 @@ class VolumeRenderer(nn.Module):
                                 0, torch.div(out["flat"], K, rounding_mode="floor"), fes[-1].detach())
                             acc_fe = chunk_fe if acc_fe is None else acc_fe + chunk_fe
                             early_stop = acc_fe > tolerance
-                            hits = hits & ~early_stop[:, None]
-                            col_counts = hits.sum(0).tolist()   # the schedule depends on who stopped
+                            col_counts.set_early_stop(early_stop, i)   # the schedule depends on who stopped
                     if "texture" in out:
                         texs.append(out["texture"].float())
                 start, size_so_far = i, 0
@@ -137,6 +167,9 @@ class VolumeRenderer(nn.Module):
                 tex_full = tex_full.index_put((flat,), torch.cat(texs) if len(texs) > 1 else texs[0])
         fe = fe_full.view(B, K)
         tex = tex_full.view(B, K, 3) if tex_full is not None else None
+        hits = sampled_idx.ne(-1)
+        if early_stop is not None:
+            hits = hits & ~early_stop[:, None]
         probs, depth, missed, colors = ops.composite(fe, tex, sampled_depth)
         if global_weights is not None:   # rarely used; falls back to re-reducing with torch
             probs = probs * global_weights
@@ -145,7 +178,7 @@ class VolumeRenderer(nn.Module):
             colors = (tex * probs.unsqueeze(-1)).sum(-2) if tex is not None else colors
         results = {
             "probs": probs, "depths": depth,
-            "max_depths": sampled_depth.masked_fill(~hits, -1).max(1).values,
+            "max_depths": sampled_depth.masked_fill(~hits, -1).max(1).values,   # hits after early stop (renderer.py:210)
             "min_depths": sampled_depth.min(1).values,
             "missed": missed, "ae": evals,
         }
