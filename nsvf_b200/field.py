@@ -32,10 +32,26 @@ class _PosEnc(nn.Module):
         return torch.cat([y, x], -1) if self.cat_input else y
 
 
+class _LayerNormReLU(nn.Module):
+    """LayerNorm([o]) + ReLU with the same parameters as nn.LayerNorm, written as a non-affine layer_norm followed by
+    an explicit scale/shift: torch's fused affine backward (GammaBetaBackwardCUDAKernel) is pathologically slow for
+    tall [65536, 256] activations (0.5 ms per call, 30 % of the whole training step); a plain column reduction is not."""
+
+    def __init__(self, dim, eps=1e-5):
+        super().__init__()
+        self.dim, self.eps = (dim,), eps
+        self.weight = nn.Parameter(torch.ones(dim))
+        self.bias = nn.Parameter(torch.zeros(dim))
+
+    def forward(self, x):
+        return torch.relu(torch.addcmul(self.bias, torch.nn.functional.layer_norm(x, self.dim, None, None, self.eps),
+                                        self.weight))
+
+
 def _fc(i, o):
     lin = nn.Linear(i, o)
     nn.init.kaiming_normal_(lin.weight, a=0.0, nonlinearity="relu", mode="fan_in")
-    return nn.Sequential(lin, nn.LayerNorm([o]), nn.ReLU())
+    return nn.Sequential(lin, _LayerNormReLU(o))
 
 
 class RadianceField(nn.Module):
