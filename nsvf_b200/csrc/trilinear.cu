@@ -11,6 +11,8 @@
 //   w_j   = (q_jx ? p_x : 1 - p_x) * (q_jy ? p_y : 1 - p_y) * (q_jz ? p_z : 1 - p_z),  j = 4*qx + 2*qy + qz
 //           (p*q + (1-p)*(1-q) with q in {0,1} reduces to exactly these values)
 //   emb   = sum_j w_j * values[feats[idx][j]]
+#include <cstdlib>
+
 #include "common.cuh"
 #include "nsvf_b200.h"
 
@@ -252,28 +254,38 @@ __device__ __forceinline__ void tri_phase_a(const TriSample& t, const int* __res
   reinterpret_cast<int*>(row)[16] = t.v;
 }
 
-__global__ void __launch_bounds__(256, 3)
+// SPL = samples per lane in phase A: a warp takes 32*SPL consecutive samples and every 8-lane group walks 8*SPL
+// CONSECUTIVE ones, so corner rows (fwd) / corner gradients (bwd) are reused across longer voxel runs.
+template <int SPL, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 trilinear_fwd_d32_v2_kernel(long long M, const int* __restrict__ sampled_idx, const float* __restrict__ xyz,
                             const int* __restrict__ feats, const float* __restrict__ centres,
                             const float* __restrict__ values, float voxel_size, float* __restrict__ out) {
-  __shared__ __align__(16) float stage[8][32 * kTriRow];
+  __shared__ __align__(16) float stage[WARPS][32 * SPL * kTriRow];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
   float* st = stage[warp];
-  const long long n_chunks = (M + 31) / 32;
-  const long long c_first = (long long)blockIdx.x * 8 + warp, c_step = (long long)gridDim.x * 8;
-  TriSample cur = tri_load(c_first * 32 + lane, c_first < n_chunks ? M : 0, sampled_idx, xyz);
+  constexpr int CH = 32 * SPL;
+  const long long n_chunks = (M + CH - 1) / CH;
+  const long long c_first = (long long)blockIdx.x * WARPS + warp, c_step = (long long)gridDim.x * WARPS;
+  TriSample cur[SPL];
+#pragma unroll
+  for (int q = 0; q < SPL; ++q)
+    cur[q] = tri_load(c_first * CH + q * 32 + lane, c_first < n_chunks ? M : 0, sampled_idx, xyz);
   for (long long c = c_first; c < n_chunks; c += c_step) {
-    const long long s0 = c * 32;
-    // software pipeline: the next chunk's index / position loads are in flight during this chunk's work
-    const TriSample nxt = tri_load((c + c_step) * 32 + lane, (c + c_step) < n_chunks ? M : 0, sampled_idx, xyz);
-    tri_phase_a(cur, feats, centres, voxel_size, st + lane * kTriRow);
-    cur = nxt;
+    const long long s0 = c * CH;
+#pragma unroll
+    for (int q = 0; q < SPL; ++q) {
+      // software pipeline: the next chunk's index / position loads are in flight during this chunk's work
+      const TriSample nxt = tri_load((c + c_step) * CH + q * 32 + lane, (c + c_step) < n_chunks ? M : 0, sampled_idx, xyz);
+      tri_phase_a(cur[q], feats, centres, voxel_size, st + (q * 32 + lane) * kTriRow);
+      cur[q] = nxt;
+    }
     __syncwarp();
     int prev = -2;
     float4 e[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int sl = g * 8 + r;
+#pragma unroll 2
+    for (int r = 0; r < 8 * SPL; ++r) {
+      const int sl = g * 8 * SPL + r;
       const float* row = st + sl * kTriRow;
       const int v = reinterpret_cast<const int*>(row)[16];
       if (v >= 0) {
@@ -302,27 +314,50 @@ trilinear_fwd_d32_v2_kernel(long long M, const int* __restrict__ sampled_idx, co
   }
 }
 
-__global__ void __launch_bounds__(256, 3)
+// Backward: same two phases, with the chunk's grad_out rows (32 consecutive samples x 128 B = one contiguous 4 KiB
+// block) brought into shared memory by a TMA bulk copy (cp.async.bulk + mbarrier), double-buffered so the next
+// chunk streams in while this one is reduced.  Each 8-lane group keeps the 8 corner gradients of the current voxel
+// in registers across a run of samples and flushes them with red.global.add.v4.f32.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 trilinear_bwd_d32_v2_kernel(long long M, const int* __restrict__ sampled_idx, const float* __restrict__ xyz,
                             const int* __restrict__ feats, const float* __restrict__ centres, float voxel_size,
                             const float* __restrict__ grad_out, float* __restrict__ grad_values) {
-  __shared__ __align__(16) float stage[8][32 * kTriRow];
+  __shared__ __align__(16) float stage[WARPS][32 * kTriRow];
+  __shared__ __align__(128) float gbuf[WARPS][2][32 * 32];
+  __shared__ __align__(8) uint64_t bars[WARPS][2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
   float* st = stage[warp];
   const long long n_chunks = (M + 31) / 32;
-  const long long c_first = (long long)blockIdx.x * 8 + warp, c_step = (long long)gridDim.x * 8;
-  TriSample cur = tri_load(c_first * 32 + lane, c_first < n_chunks ? M : 0, sampled_idx, xyz);
-  for (long long c = c_first; c < n_chunks; c += c_step) {
+  const long long c_first = (long long)blockIdx.x * WARPS + warp, c_step = (long long)gridDim.x * WARPS;
+  if (lane == 0) {
+    mbar_init(&bars[warp][0], 1);
+    mbar_init(&bars[warp][1], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  auto issue = [&](long long c, int slot) {   // lane 0 only
     const long long s0 = c * 32;
-    // software pipeline: the next chunk's index / position loads are in flight during this chunk's work
+    const unsigned bytes = (unsigned)(min((long long)32, M - s0) * 128);
+    mbar_expect_tx(&bars[warp][slot], bytes);
+    tma_bulk_g2s(gbuf[warp][slot], grad_out + s0 * 32, bytes, &bars[warp][slot]);
+  };
+  if (lane == 0 && c_first < n_chunks) issue(c_first, 0);
+  TriSample cur = tri_load(c_first * 32 + lane, c_first < n_chunks ? M : 0, sampled_idx, xyz);
+  int it = 0;
+  for (long long c = c_first; c < n_chunks; c += c_step, ++it) {
+    const int slot = it & 1;
+    if (lane == 0 && c + c_step < n_chunks) issue(c + c_step, slot ^ 1);   // that buffer was released by the
     const TriSample nxt = tri_load((c + c_step) * 32 + lane, (c + c_step) < n_chunks ? M : 0, sampled_idx, xyz);
-    tri_phase_a(cur, feats, centres, voxel_size, st + lane * kTriRow);
+    tri_phase_a(cur, feats, centres, voxel_size, st + lane * kTriRow);       // __syncwarp ending iteration it-1
     cur = nxt;
     __syncwarp();
+    mbar_wait(&bars[warp][slot], (it >> 1) & 1);
+    const float* gb = gbuf[warp][slot];
     int prev = -2;
     int key[8];
     float4 acc[8];
-#pragma unroll
+#pragma unroll 2
     for (int r = 0; r < 8; ++r) {
       const int sl = g * 8 + r;
       const float* row = st + sl * kTriRow;
@@ -342,7 +377,7 @@ trilinear_bwd_d32_v2_kernel(long long M, const int* __restrict__ sampled_idx, co
         }
         const float4 w0 = reinterpret_cast<const float4*>(row)[0], w1 = reinterpret_cast<const float4*>(row)[1];
         const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-        const float4 gq = __ldcs(reinterpret_cast<const float4*>(grad_out + (s0 + sl) * 32) + sub);
+        const float4 gq = reinterpret_cast<const float4*>(gb + sl * 32)[sub];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           acc[j].x = fmaf(w[j], gq.x, acc[j].x);
@@ -358,6 +393,15 @@ trilinear_bwd_d32_v2_kernel(long long M, const int* __restrict__ sampled_idx, co
     }
     __syncwarp();
   }
+}
+
+static int g_tri_variant = -1;   // NSVF_TRI_VARIANT env: tuning knob (SPL*10 + warps/4)
+static int tri_variant() {
+  if (g_tri_variant < 0) {
+    const char* e = getenv("NSVF_TRI_VARIANT");
+    g_tri_variant = e ? atoi(e) : 0;
+  }
+  return g_tri_variant;
 }
 
 static int grid_for(long long work_items, int items_per_block, int max_blocks_per_sm) {
@@ -381,9 +425,27 @@ extern "C" int nsvf_trilinear_embed_fwd(nsvf_stream_t stream_, long long M, int 
     NSVF_REQUIRE((((uintptr_t)values | (uintptr_t)out | (uintptr_t)feats) & 15) == 0,
                  "trilinear_embed_fwd: values/out/feats must be 16-byte aligned");
     NSVF_REQUIRE(((uintptr_t)values & 15) == 0, "trilinear_embed_fwd: values must be 16-byte aligned");
-    NSVF_TIMED_LAUNCH("trilinear_fwd_kernel", stream,
-                      (trilinear_fwd_d32_v2_kernel<<<grid_for((M + 31) / 32, 8, 8), 256, 0, stream>>>(
-                          M, sampled_idx, sampled_xyz, feats, centres, values, voxel_size, out)));
+    switch (tri_variant() == 0 ? 2 : tri_variant()) {
+      case 2:
+        NSVF_TIMED_LAUNCH("trilinear_fwd_kernel", stream,
+                          (trilinear_fwd_d32_v2_kernel<2, 4><<<grid_for((M + 63) / 64, 4, 12), 128, 0, stream>>>(
+                              M, sampled_idx, sampled_xyz, feats, centres, values, voxel_size, out)));
+        break;
+      case 4:
+        NSVF_TIMED_LAUNCH("trilinear_fwd_kernel", stream,
+                          (trilinear_fwd_d32_v2_kernel<4, 4><<<grid_for((M + 127) / 128, 4, 12), 128, 0, stream>>>(
+                              M, sampled_idx, sampled_xyz, feats, centres, values, voxel_size, out)));
+        break;
+      case 1:
+        NSVF_TIMED_LAUNCH("trilinear_fwd_kernel", stream,
+                          (trilinear_fwd_d32_v2_kernel<1, 4><<<grid_for((M + 31) / 32, 4, 12), 128, 0, stream>>>(
+                              M, sampled_idx, sampled_xyz, feats, centres, values, voxel_size, out)));
+        break;
+      default:
+        NSVF_TIMED_LAUNCH("trilinear_fwd_kernel", stream,
+                          (trilinear_fwd_d32_v2_kernel<1, 8><<<grid_for((M + 31) / 32, 8, 8), 256, 0, stream>>>(
+                              M, sampled_idx, sampled_xyz, feats, centres, values, voxel_size, out)));
+    }
     return 0;
   } else {
     trilinear_fwd_generic_kernel<<<grid_for(M, 8, 16), 256, 0, stream>>>(M, D, sampled_idx, sampled_xyz, feats,
@@ -404,8 +466,9 @@ extern "C" int nsvf_trilinear_embed_bwd(nsvf_stream_t stream_, long long M, int 
     NSVF_REQUIRE((((uintptr_t)values | (uintptr_t)grad_out | (uintptr_t)grad_values | (uintptr_t)feats) & 15) == 0,
                  "trilinear_embed_bwd: values/grad_out/grad_values/feats must be 16-byte aligned");
     if (grad_xyz == nullptr) {
+      NSVF_REQUIRE(((uintptr_t)grad_out & 15) == 0, "trilinear_embed_bwd: grad_out must be 16-byte aligned");
       NSVF_TIMED_LAUNCH("trilinear_bwd_kernel", stream,
-                        (trilinear_bwd_d32_v2_kernel<<<grid_for((M + 31) / 32, 8, 8), 256, 0, stream>>>(
+                        (trilinear_bwd_d32_v2_kernel<4><<<grid_for((M + 31) / 32, 4, 5), 128, 0, stream>>>(
                             M, sampled_idx, sampled_xyz, feats, centres, voxel_size, grad_out, grad_values)));
       return 0;
     }
