@@ -15,6 +15,8 @@
 //     reads past the end of the tensor are defined here as -1.
 //   * the trailing loop's stop test reads pts_idx[curr_bin] of ray 0 of the block row.
 //   * a sample that would land at s >= max_steps is dropped (the reference writes out of the row).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "nsvf_b200.h"
 
@@ -206,6 +208,250 @@ inverse_cdf_sampling_kernel(int b, int num_rays, long long valid_rays, int ray_c
   }
 }
 
+// ---- warp-per-ray inverse-CDF sampler -------------------------------------------------------------------------
+// The reference loop is serial per ray, but its result is a MERGE of two monotone sequences: the step samples
+// (cdf_i = (i + noise_i) * step, non-decreasing in i) and the bin boundaries (cumulative probs).  Once the
+// cumulative sums exist — computed sequentially, because `cdf > curr_max_cdf` must see the reference's exact
+// left-to-right float sums — every step sample is independent:
+//   bin b_i   = running max over i' <= i of lower_bound(cum, cdf_i')         (the bin pointer only moves forward)
+//   position  = i + b_i                              (b_i bin-end samples were emitted before it)
+//   z_low     = z_{i-1} if b_{i-1} == b_i else min_depth[b_i]
+// and the bin-end sample of bin j sits at j + #{i : b_i <= j} with z_low = z of the last step sample in bin j (or
+// min_depth[j]).  One warp owns one ray: bins are loaded cooperatively (coalesced), 32 steps are resolved per
+// iteration, outputs are written nearly contiguously.  The handful of samples of the reference's trailing loop
+// (incl. its `(~done)` / next-ray / ray-0 quirks) are replayed serially from the exact state the main loop leaves.
+// Rays whose cumulative sums are not monotone / finite (NaN or negative probs) fall back to the serial machine.
+__device__ __forceinline__ int warp_incl_max(int x, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(NSVF_FULL_MASK, x, o);
+    if (lane >= o) x = max(x, y);
+  }
+  return x;
+}
+__device__ __forceinline__ int warp_incl_sum(int x, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(NSVF_FULL_MASK, x, o);
+    if (lane >= o) x += y;
+  }
+  return x;
+}
+
+constexpr int kCdfWarps = 4;
+
+__global__ void __launch_bounds__(kCdfWarps * 32)
+inverse_cdf_warp_kernel(int b, int num_rays, long long valid_rays, int ray_chunk, int P, int max_steps,
+                        float fixed_step_size, const int* __restrict__ pts_idx, const float* __restrict__ min_depth,
+                        const float* __restrict__ max_depth, const float* __restrict__ noise, float noise_const,
+                        const float* __restrict__ probs, const float* __restrict__ steps,
+                        int* __restrict__ sampled_idx, float* __restrict__ sampled_depth,
+                        float* __restrict__ sampled_dists, int* __restrict__ max_count) {
+  extern __shared__ __align__(16) float cdf_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* base = cdf_smem + (size_t)warp * 6 * P;
+  int* s_idx = reinterpret_cast<int*>(base);
+  float* s_min = base + P;
+  float* s_max = base + 2 * P;
+  float* s_cum = base + 3 * P;
+  int* s_cnt = reinterpret_cast<int*>(base + 4 * P);
+  float* s_zlast = base + 5 * P;
+  int my_max = 0;
+
+  for (long long ray = (long long)blockIdx.x * kCdfWarps + warp; ray < valid_rays;
+       ray += (long long)gridDim.x * kCdfWarps) {
+    const long long H = ray * P, K = ray * max_steps;
+    const long long batch = ray / num_rays;
+    const int r = (int)(ray - batch * num_rays);
+    const int c0 = (r / ray_chunk) * ray_chunk;
+    const long long row0 = batch * num_rays + c0;
+    const int* row0_idx = pts_idx + (row0 < valid_rays ? row0 : 0) * P;
+    long long nxt = -1;
+    if (r + 1 < min(c0 + ray_chunk, num_rays)) nxt = ray + 1;
+    else if (batch + 1 < b) nxt = (batch + 1) * num_rays + c0;
+    const int next_idx0 = nxt >= 0 ? pts_idx[(nxt < valid_rays ? nxt : 0) * P] : -1;
+    const float* noise_row = noise != nullptr ? noise + ray * max_steps : nullptr;
+
+    // 1) bins -> shared memory (coalesced)
+    for (int j = lane; j < P; j += 32) {
+      s_idx[j] = pts_idx[H + j];
+      s_min[j] = min_depth[H + j];
+      s_max[j] = max_depth[H + j];
+      s_cum[j] = probs[H + j];
+      s_cnt[j] = 0;
+    }
+    __syncwarp();
+    // 2) number of usable bins (bin 0 is always used) and the reference's sequential cumulative sums
+    int nb = P;
+    for (int j0 = 0; j0 < P; j0 += 32) {
+      const int j = j0 + lane;
+      const unsigned m = __ballot_sync(NSVF_FULL_MASK, j >= 1 && j < P && s_idx[j] == -1);
+      if (m) { nb = j0 + __ffs(m) - 1; break; }
+    }
+    int ok = 1;
+    if (lane == 0) {
+      float c = s_cum[0];
+      ok = (c == c) && (fabsf(c) <= 3.0e38f);
+      for (int j = 1; j < nb; ++j) {
+        const float n = __fadd_rn(c, s_cum[j]);
+        ok &= (n >= c) && (fabsf(n) <= 3.0e38f);
+        s_cum[j] = n;
+        c = n;
+      }
+    }
+    ok = __shfl_sync(NSVF_FULL_MASK, ok, 0);
+    __syncwarp();
+
+    const float sj = steps[ray];
+    float step_size = __fdiv_rn(1.0f, sj);
+    if (fixed_step_size > 0.0f) step_size = fixed_step_size;
+    const int total_steps = (int)ceilf(sj);
+    int s_end = 0, n_valid = 0;
+
+    if (!ok) {
+      // serial fallback (exact reference loop) on lane 0
+      if (lane == 0) {
+        CdfState st;
+        st.curr_bin = 0; st.s = 0; st.curr_step = 0;
+        st.curr_min_depth = s_min[0]; st.curr_max_depth = s_max[0];
+        st.curr_min_cdf = 0.0f; st.curr_max_cdf = probs[H];
+        st.step_size = step_size; st.z_low = st.curr_min_depth; st.total_steps = total_steps;
+        st.curr_cdf = 0.0f; st.phase = 0;
+        int sidx = 0;
+        while (sidx < max_steps && st.phase != 3) {
+          int oi; float od, oz;
+          if (cdf_next(st, P, max_steps, H, next_idx0, pts_idx, row0_idx, min_depth, max_depth, probs, noise_row,
+                       noise_const, oi, od, oz)) {
+            sampled_idx[K + sidx] = oi; sampled_dists[K + sidx] = od; sampled_depth[K + sidx] = oz;
+            n_valid += (oi != -1);
+            ++sidx;
+          }
+        }
+        s_end = sidx;
+      }
+      s_end = __shfl_sync(NSVF_FULL_MASK, s_end, 0);
+    } else {
+      // 3) step samples, 32 per iteration
+      int carry_b = 0, prev_b = -1, n_in = total_steps;
+      float prev_z = 0.f;
+      bool done = false;
+      for (int i0 = 0; i0 < total_steps && !done; i0 += 32) {
+        const int i = i0 + lane;
+        const bool active = i < total_steps;
+        float cdf = 0.f;
+        int g = 0;
+        if (active) {
+          const int ns = i < max_steps ? i : max_steps - 1;
+          const float nz = noise_row != nullptr ? noise_row[ns] : noise_const;
+          cdf = __fmul_rn(__fadd_rn((float)i, nz), step_size);
+          int lo = 0, hi = nb;   // first j with !(cdf > cum[j]); nb = none
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cdf > s_cum[mid]) lo = mid + 1; else hi = mid;
+          }
+          g = lo;
+        }
+        int bb = max(warp_incl_max(g, lane), carry_b);
+        const unsigned dmask = __ballot_sync(NSVF_FULL_MASK, active && bb >= nb);
+        int first = 32;
+        if (dmask) { first = __ffs(dmask) - 1; n_in = i0 + first; done = true; }
+        const bool act = active && lane < first;
+        float z = 0.f;
+        if (act) {
+          const float cmin = bb > 0 ? s_cum[bb - 1] : 0.0f, cmax = s_cum[bb];
+          const float u = __fdiv_rn(__fsub_rn(cdf, cmin), __fsub_rn(cmax, cmin));
+          z = __fmaf_rn(u, __fsub_rn(s_max[bb], s_min[bb]), s_min[bb]);
+        }
+        float pz = __shfl_up_sync(NSVF_FULL_MASK, z, 1);
+        int pb = __shfl_up_sync(NSVF_FULL_MASK, bb, 1);
+        if (lane == 0) { pz = prev_z; pb = prev_b; }
+        const int nbn = __shfl_down_sync(NSVF_FULL_MASK, bb, 1);
+        const unsigned amask = __ballot_sync(NSVF_FULL_MASK, act);
+        if (act) {
+          const float zlow = (pb == bb) ? pz : s_min[bb];
+          const int pos = i + bb;
+          if (pos < max_steps) {
+            const int oi = s_idx[bb];
+            sampled_idx[K + pos] = oi;
+            sampled_dists[K + pos] = __fsub_rn(z, zlow);
+            sampled_depth[K + pos] = __fmul_rn(__fadd_rn(z, zlow), 0.5f);
+            n_valid += (oi != -1);
+          }
+          atomicAdd(&s_cnt[bb], 1);
+          const bool next_act = lane < 31 && ((amask >> (lane + 1)) & 1u);
+          if (!next_act || nbn != bb) s_zlast[bb] = z;   // the last step sample of a bin (so far)
+        }
+        if (amask) {
+          const int la = 31 - __clz(amask);
+          carry_b = __shfl_sync(NSVF_FULL_MASK, bb, la);
+          prev_z = __shfl_sync(NSVF_FULL_MASK, z, la);
+          prev_b = carry_b;
+        }
+        __syncwarp();
+      }
+      const int b_last = done ? nb : (n_in > 0 ? carry_b : 0);
+      // 4) bin-end samples of the bins crossed by the main loop
+      int cbase = 0;
+      for (int j0 = 0; j0 < b_last; j0 += 32) {
+        const int j = j0 + lane;
+        const bool a = j < b_last;
+        const int cnt = a ? s_cnt[j] : 0;
+        const int incl = warp_incl_sum(cnt, lane) + cbase;
+        if (a) {
+          const int pos = j + incl;
+          if (pos < max_steps) {
+            const float zlow = cnt > 0 ? s_zlast[j] : s_min[j];
+            const int oi = s_idx[j];
+            sampled_idx[K + pos] = oi;
+            sampled_dists[K + pos] = __fsub_rn(s_max[j], zlow);
+            sampled_depth[K + pos] = __fmul_rn(__fadd_rn(s_max[j], zlow), 0.5f);
+            n_valid += (oi != -1);
+          }
+        }
+        cbase = __shfl_sync(NSVF_FULL_MASK, incl, 31);
+      }
+      // 5) the reference's trailing loop, replayed from the exact state (uniform scalar code; lane 0 writes)
+      int curr_bin, sidx = n_in + b_last;
+      float curr_max, zl;
+      if (done) {
+        curr_bin = nb;
+        curr_max = s_max[nb - 1];
+        zl = s_cnt[nb - 1] > 0 ? s_zlast[nb - 1] : s_min[nb - 1];
+      } else {
+        curr_bin = b_last;
+        curr_max = s_max[curr_bin];
+        zl = n_in > 0 ? prev_z : s_min[0];
+      }
+      while (zl < curr_max) {
+        const int oi = curr_bin < P ? s_idx[curr_bin] : next_idx0;
+        if (sidx < max_steps && lane == 0) {
+          sampled_idx[K + sidx] = oi;
+          sampled_dists[K + sidx] = __fsub_rn(curr_max, zl);
+          sampled_depth[K + sidx] = __fmul_rn(__fadd_rn(curr_max, zl), 0.5f);
+          n_valid += (oi != -1);
+        }
+        ++curr_bin;
+        ++sidx;
+        if (curr_bin >= P || row0_idx[curr_bin] == -1) break;
+        curr_max = s_max[curr_bin];
+        zl = s_min[curr_bin];
+      }
+      s_end = min(sidx, max_steps);
+    }
+    // 6) padding
+    for (int t = s_end + lane; t < max_steps; t += 32) {
+      sampled_idx[K + t] = -1;
+      sampled_depth[K + t] = 0.0f;
+      sampled_dists[K + t] = 0.0f;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_valid += __shfl_xor_sync(NSVF_FULL_MASK, n_valid, o);
+    my_max = max(my_max, n_valid);
+    __syncwarp();
+  }
+  if (max_count != nullptr && lane == 0 && my_max > 0) atomicMax(max_count, my_max);
+}
+
 // Faithful restatement of the two-phase uniform sampler (dead code in the live model path: no caller
 // in fairnr/modules/encoder.py). One thread per ray, in-place in global memory like the reference;
 // the kernel pre-fills its own row (idx -1, depth 0, dists 0) instead of relying on host fills.
@@ -292,6 +538,27 @@ extern "C" int nsvf_inverse_cdf_sampling(nsvf_stream_t stream_, int b, int num_r
   if (valid_rays < 0 || valid_rays > total_rays) valid_rays = total_rays;
   if (ray_chunk <= 0 || ray_chunk > num_rays) ray_chunk = num_rays;
   if (valid_rays == 0) return 0;
+  {  // warp-per-ray kernel whenever its per-warp bin tables fit in shared memory
+    const size_t smem = (size_t)kCdfWarps * 6 * max_hits * sizeof(float);
+    if (smem <= 160 * 1024 && getenv("NSVF_SAMPLER_LANE") == nullptr) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        NSVF_CUDA_OK(cudaFuncSetAttribute(inverse_cdf_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          160 * 1024));
+        attr_set = true;
+      }
+      int per_sm = (int)((200 * 1024) / (smem + 1024));
+      per_sm = per_sm < 1 ? 1 : (per_sm > 12 ? 12 : per_sm);
+      long long want = (valid_rays + kCdfWarps - 1) / kCdfWarps, cap = (long long)num_sms() * per_sm;
+      int grid = (int)(want < cap ? want : cap);
+      NSVF_TIMED_LAUNCH("inverse_cdf_sampling_kernel", stream,
+                        (inverse_cdf_warp_kernel<<<grid, kCdfWarps * 32, smem, stream>>>(
+                            b, num_rays, valid_rays, ray_chunk, max_hits, max_steps, fixed_step_size, pts_idx, min_depth,
+                            max_depth, uniform_noise, noise_const, probs, steps, sampled_idx, sampled_depth,
+                            sampled_dists, max_count)));
+      return 0;
+    }
+  }
   const long long groups = (valid_rays + 31) / 32;
   long long want = (groups + kSampWarps - 1) / kSampWarps;
   long long cap = (long long)num_sms() * 8;
