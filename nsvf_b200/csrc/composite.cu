@@ -41,10 +41,23 @@ composite_fwd_kernel(long long B, int K, const float* __restrict__ fe, const flo
        ray += (long long)gridDim.x * kCompWarps) {
     const long long row = ray * K;
     float carry = 0.f, s_p = 0.f, s_d = 0.f, s_r = 0.f, s_g = 0.f, s_b = 0.f;
+    // software pipeline: chunk k0+32's inputs are in flight while chunk k0 is scanned
+    float nx = 0.f, nd = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f;
+    if (lane < K) {
+      nx = fe[row + lane];
+      nd = depth[row + lane];
+      if (tex != nullptr) { n0 = tex[(row + lane) * 3 + 0]; n1 = tex[(row + lane) * 3 + 1]; n2 = tex[(row + lane) * 3 + 2]; }
+    }
     for (int k0 = 0; k0 < K; k0 += 32) {
       const int k = k0 + lane;
       const bool ok = k < K;
-      const float x = ok ? fe[row + k] : 0.f;
+      const float x = ok ? nx : 0.f, dk = nd, t0 = n0, t1 = n1, t2 = n2;
+      const int kn = k + 32;
+      if (kn < K) {
+        nx = fe[row + kn];
+        nd = depth[row + kn];
+        if (tex != nullptr) { n0 = tex[(row + kn) * 3 + 0]; n1 = tex[(row + kn) * 3 + 1]; n2 = tex[(row + kn) * 3 + 2]; }
+      }
       const float incl = warp_incl_scan(x, lane);
       float excl = __shfl_up_sync(NSVF_FULL_MASK, incl, 1);
       if (lane == 0) excl = 0.f;
@@ -54,11 +67,11 @@ composite_fwd_kernel(long long B, int K, const float* __restrict__ fe, const flo
         const float p = (1.0f - expf(-x)) * expf(-excl);
         if (probs != nullptr) probs[row + k] = p;
         s_p += p;
-        s_d = fmaf(depth[row + k], p, s_d);
+        s_d = fmaf(dk, p, s_d);
         if (tex != nullptr) {
-          s_r = fmaf(tex[(row + k) * 3 + 0], p, s_r);
-          s_g = fmaf(tex[(row + k) * 3 + 1], p, s_g);
-          s_b = fmaf(tex[(row + k) * 3 + 2], p, s_b);
+          s_r = fmaf(t0, p, s_r);
+          s_g = fmaf(t1, p, s_g);
+          s_b = fmaf(t2, p, s_b);
         }
       }
     }
@@ -92,12 +105,27 @@ composite_bwd_kernel(long long B, int K, const float* __restrict__ fe, const flo
     const float gm = g_missed ? g_missed[ray] : 0.f;
     float gc0 = 0.f, gc1 = 0.f, gc2 = 0.f;
     if (g_colors && tex) { gc0 = g_colors[ray * 3 + 0]; gc1 = g_colors[ray * 3 + 1]; gc2 = g_colors[ray * 3 + 2]; }
-    // pass 1 (forward): probs, G, first term, q = G * probs
+    // pass 1 (forward): probs, G, first term, q = G * probs.  Inputs of chunk k0+32 are loaded while chunk k0 is
+    // scanned (the carry makes the chunks sequential, the loads need not be).
     float carry = 0.f;
+    float nx = 0.f, nd = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, ngp = 0.f;
+    if (lane < K) {
+      nx = fe[row + lane];
+      nd = depth[row + lane];
+      if (tex) { n0 = tex[(row + lane) * 3 + 0]; n1 = tex[(row + lane) * 3 + 1]; n2 = tex[(row + lane) * 3 + 2]; }
+      if (g_probs) ngp = g_probs[row + lane];
+    }
     for (int k0 = 0; k0 < K; k0 += 32) {
       const int k = k0 + lane;
       const bool ok = k < K;
-      const float x = ok ? fe[row + k] : 0.f;
+      const float x = ok ? nx : 0.f, dk = nd, t0 = n0, t1 = n1, t2 = n2, gp = ngp;
+      const int kn = k + 32;
+      if (kn < K) {
+        nx = fe[row + kn];
+        nd = depth[row + kn];
+        if (tex) { n0 = tex[(row + kn) * 3 + 0]; n1 = tex[(row + kn) * 3 + 1]; n2 = tex[(row + kn) * 3 + 2]; }
+        if (g_probs) ngp = g_probs[row + kn];
+      }
       const float incl = warp_incl_scan(x, lane);
       float excl = __shfl_up_sync(NSVF_FULL_MASK, incl, 1);
       if (lane == 0) excl = 0.f;
@@ -106,9 +134,8 @@ composite_bwd_kernel(long long B, int K, const float* __restrict__ fe, const flo
       if (ok) {
         const float e = expf(-x), bk = expf(-excl);
         const float p = (1.0f - e) * bk;
-        float G = (g_probs ? g_probs[row + k] : 0.f) + gd * depth[row + k] - gm;
+        float G = gp + gd * dk - gm;
         if (tex) {
-          const float t0 = tex[(row + k) * 3 + 0], t1 = tex[(row + k) * 3 + 1], t2 = tex[(row + k) * 3 + 2];
           G += gc0 * t0 + gc1 * t1 + gc2 * t2;
           if (g_tex) {
             g_tex[(row + k) * 3 + 0] = gc0 * p;
