@@ -16,6 +16,8 @@
 //     shared memory once per persistent CTA with TMA bulk copies (cp.async.bulk + mbarrier).
 //   * Hits are collected in shared memory and each ray's row [n_max] x {idx,min,max} is written once,
 //     coalesced, including the -1 / 0 fill that the reference gets from torch::zeros + a per-thread loop.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "nsvf_b200.h"
 
@@ -393,6 +395,84 @@ aabb_intersect_kernel(const __grid_constant__ AabbTree tree, long long tree_stri
   }
 }
 
+// ---- small voxel sets: one thread per ray over ALL voxels, boxes broadcast from shared memory ---------------------
+// For a few hundred voxels (the first phase of training: 343-512 voxels) no hierarchy pays for itself: consecutive
+// index groups straddle grid rows, so almost every node is hit.  The reference's linear scan is the right
+// algorithm there; this is that scan with everything around it fixed: exact voxel boxes (c -+ hv) staged once
+// per CTA as 32-byte records, every lane of a warp reads the SAME box (two LDS.128 broadcasts, no conflicts), 1/dir
+// hoisted out of the loop, the branch-free min/max form of the slab test for regular rays (~17 instructions per
+// test instead of ~40), rows pre-filled with coalesced stores by the whole CTA.
+constexpr int kSmallThreads = 256;
+constexpr int kSmallMaxVoxels = 1024;
+
+template <int MODE>
+__global__ void __launch_bounds__(kSmallThreads)
+aabb_small_kernel(const __grid_constant__ AabbTree tree, long long tree_stride_box, long long rays_per_tree, int n,
+                  int n_max, const float* __restrict__ ray_start, const float* __restrict__ ray_dir,
+                  int* __restrict__ out_idx, float* __restrict__ out_min, float* __restrict__ out_max,
+                  unsigned char* __restrict__ out_hit) {
+  // stage the exact voxel boxes as 32-byte records {lo.xyz, hi.x | hi.yz, -, -}: one test = two LDS.128 broadcasts
+  const float* gbox = tree.box + (long long)blockIdx.y * tree_stride_box;
+  float4* sbox = reinterpret_cast<float4*>(aabb_smem);
+  for (int k = threadIdx.x; k < n; k += kSmallThreads) {
+    const float* g = gbox + k;
+    const long long st = tree.total;
+    sbox[2 * k] = make_float4(g[0], g[st], g[2 * st], g[3 * st]);
+    sbox[2 * k + 1] = make_float4(g[4 * st], g[5 * st], 0.f, 0.f);
+  }
+  __syncthreads();
+  const long long ray_base = (long long)blockIdx.y * rays_per_tree;
+
+  for (long long tile = (long long)blockIdx.x * kSmallThreads; tile < rays_per_tree;
+       tile += (long long)gridDim.x * kSmallThreads) {
+    const long long tile_rays = min((long long)kSmallThreads, rays_per_tree - tile);
+    if constexpr (MODE != kModeAnyHit) {   // coalesced pre-fill of this tile's rows
+      const long long base = (ray_base + tile) * n_max, cells = tile_rays * n_max;
+      for (long long c = threadIdx.x; c < cells; c += kSmallThreads) {
+        out_idx[base + c] = -1;
+        out_min[base + c] = 0.0f;
+        out_max[base + c] = 0.0f;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x < tile_rays) {
+      const long long ray = ray_base + tile + threadIdx.x;
+      const float ox = ray_start[ray * 3 + 0], oy = ray_start[ray * 3 + 1], oz = ray_start[ray * 3 + 2];
+      const float ix = ref_rcp(ray_dir[ray * 3 + 0]), iy = ref_rcp(ray_dir[ray * 3 + 1]),
+                  iz = ref_rcp(ray_dir[ray * 3 + 2]);
+      const bool regular = regular_component(ox, ix) && regular_component(oy, iy) && regular_component(oz, iz);
+      const long long row = ray * n_max;
+      int cnt = 0;
+      const int limit = MODE == kModeAnyHit ? 1 : n_max;
+      for (int k = 0; k < n && cnt < limit; ++k) {
+        float tn, tf;
+        bool hit;
+        const float4 q0 = sbox[2 * k], q1 = sbox[2 * k + 1];
+        if (regular) {
+          const float a0 = __fmul_rn(__fsub_rn(q0.x, ox), ix), b0 = __fmul_rn(__fsub_rn(q0.w, ox), ix);
+          const float a1 = __fmul_rn(__fsub_rn(q0.y, oy), iy), b1 = __fmul_rn(__fsub_rn(q1.x, oy), iy);
+          const float a2 = __fmul_rn(__fsub_rn(q0.z, oz), iz), b2 = __fmul_rn(__fsub_rn(q1.y, oz), iz);
+          tn = fmaxf(fmaxf(0.0f, fminf(a0, b0)), fmaxf(fminf(a1, b1), fminf(a2, b2)));
+          tf = fminf(fminf(100000.0f, fmaxf(a0, b0)), fminf(fmaxf(a1, b1), fmaxf(a2, b2)));
+          hit = tn <= tf;
+        } else {
+          hit = slab_exact(ox, oy, oz, ix, iy, iz, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tn, tf);
+        }
+        if (hit) {
+          if constexpr (MODE != kModeAnyHit) {
+            out_idx[row + cnt] = k;
+            out_min[row + cnt] = tn;
+            out_max[row + cnt] = tf;
+          }
+          ++cnt;
+        }
+      }
+      if constexpr (MODE == kModeAnyHit) out_hit[ray] = cnt > 0;
+    }
+    if constexpr (MODE != kModeAnyHit) __syncthreads();
+  }
+}
+
 static size_t aabb_tree_floats(int n) { return (size_t)6 * aabb_layout(n).total; }
 
 template <int NL, int MODE>
@@ -516,6 +596,22 @@ static int aabb_run(cudaStream_t stream, int mode, int b, int n, int m, float vo
   int gx = (int)(want < cap ? want : cap);
   if (gx < 1) gx = 1;
   dim3 grid(gx, n_trees);
+  if (n <= kSmallMaxVoxels && mode != kModeDepthSorted && getenv("NSVF_AABB_NO_SMALL") == nullptr) {
+    const size_t sm = (size_t)8 * n * sizeof(float);
+    long long want_s = (rays_per_tree + kSmallThreads - 1) / kSmallThreads, cap_s = (long long)num_sms() * 8;
+    if (n_trees > 1) cap_s = (cap_s + n_trees - 1) / n_trees;
+    dim3 gs((unsigned)(want_s < cap_s ? want_s : cap_s), n_trees);
+    if (mode == kModeAnyHit) {
+      NSVF_TIMED_LAUNCH("aabb_hit_mask_kernel", stream,
+                        (aabb_small_kernel<kModeAnyHit><<<gs, kSmallThreads, sm, stream>>>(
+                            tree, tree_stride_box, rays_per_tree, n, 1, ray_start, ray_dir, idx, min_depth, max_depth, hit)));
+    } else {
+      NSVF_TIMED_LAUNCH("aabb_intersect_kernel", stream,
+                        (aabb_small_kernel<kModeIndexOrder><<<gs, kSmallThreads, sm, stream>>>(
+                            tree, tree_stride_box, rays_per_tree, n, n_max, ray_start, ray_dir, idx, min_depth, max_depth, hit)));
+    }
+    return 0;
+  }
   const int nm = mode == kModeAnyHit ? 0 : n_max;
   switch (mode) {
     case kModeIndexOrder:
