@@ -72,6 +72,12 @@ NSVF_API int nsvf_aabb_intersect_sorted(nsvf_stream_t stream, int b, int n, int 
                                         float* min_depth, float* max_depth, unsigned char* hits, void* workspace,
                                         size_t workspace_bytes);
 
+/* The same post-processing as a stand-alone, in-place pass over hit lists produced by any intersection routine
+ * (used after nsvf_svo_intersect): idx i32 / min_depth, max_depth f32 [rays, n_max] are rewritten sorted by entry
+ * depth with -1 / empty_depth in the unused slots; hits u8 [rays] optional. */
+NSVF_API int nsvf_sort_hits_by_depth(nsvf_stream_t stream, long long rays, int n_max, float empty_depth, int* idx,
+                                     float* min_depth, float* max_depth, unsigned char* hits);
+
 /* Any-hit query: hits u8 [b, m] = 1 iff nsvf_aabb_intersect would report at least one hit for the ray.  Lets
  * the training path (`--no-sampling-at-reader`, fairnr/models/nsvf.py:48-60) draw pixels from the hit mask of
  * all V x H x W rays without materialising [rays, n_max] x 3 outputs for rays it will not march. */

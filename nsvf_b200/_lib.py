@@ -24,6 +24,7 @@ SIGNATURES = {
                                     c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
     "nsvf_aabb_intersect_sorted": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_int, c_float, c_void_p, c_void_p,
                                            c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
+    "nsvf_sort_hits_by_depth": (c_int, [c_void_p, c_ll, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nsvf_aabb_hit_mask": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_ll,
                                    c_void_p, c_void_p, c_size_t]),
     "nsvf_svo_workspace_bytes": (c_size_t, [c_int, c_int]),

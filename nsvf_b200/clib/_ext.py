@@ -99,6 +99,19 @@ def aabb_intersect_sorted(ray_start, ray_dir, points, voxelsize, n_max, empty_de
     return idx, dmin, dmax, hits.bool()
 
 
+def sort_hits_by_depth(idx, min_depth, max_depth, empty_depth=10000.0):
+    """Extension: in-place masked_fill + sort-by-entry-depth + any() of encoder.py:519-524 on [.., n_max] hit lists.
+    Returns hits bool [..]."""
+    _check(dict(min_depth=min_depth, max_depth=max_depth), dict(idx=idx))
+    n_max = idx.shape[-1]
+    rays = idx.numel() // max(n_max, 1)
+    hits = torch.empty(idx.shape[:-1], dtype=torch.uint8, device=idx.device)
+    with torch.cuda.device(idx.device):
+        _lib.check(_L.nsvf_sort_hits_by_depth(_lib.current_stream(idx.device), rays, n_max, float(empty_depth),
+                                              _p(idx), _p(min_depth), _p(max_depth), _p(hits)))
+    return hits.bool()
+
+
 def aabb_hit_mask(ray_start, ray_dir, points, voxelsize, shared_points=False):
     """Extension: hits bool [B,M] = any(aabb_intersect(...).idx != -1) without producing the hit lists."""
     b, m, n, stride, trees = _aabb_args(ray_start, ray_dir, points, shared_points)

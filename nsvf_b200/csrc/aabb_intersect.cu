@@ -267,11 +267,65 @@ __device__ __noinline__ void aabb_traverse_irregular(const AabbTree& tree, const
   }
 }
 
-// Warp-level stable sort of the first `cnt` hits by entry depth (ties keep ascending voxel index).
-// perm[] (ints, in shared memory, >= pow2(cnt) entries) receives the source slot of every sorted position.
-__device__ __forceinline__ void aabb_sort_by_depth(const float* h_min, int cnt, int* perm) {
+// Warp-level stable sort of the first `cnt` hits by entry depth (ties keep ascending slot = ascending voxel
+// index).  Bitonic network held in REGISTERS: element t = r*32 + lane, R elements per lane; partners at distance
+// < 32 are exchanged with __shfl_xor_sync, partners at distance >= 32 live in the same lane.  perm[] (shared
+// memory, >= cnt ints) receives the source slot of every sorted position.
+template <int R>
+__device__ __forceinline__ void aabb_bitonic_regs(const float* h_min, int cnt, int* perm) {
   const int lane = threadIdx.x & 31;
-  if (cnt <= 32) {   // rank sort: one element per lane, keys broadcast from shared memory
+  float d[R];
+  int sl[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int t = r * 32 + lane;
+    sl[r] = t;
+    d[r] = t < cnt ? h_min[t] : INFINITY;
+  }
+#pragma unroll
+  for (int k = 2; k <= 32 * R; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {   // partner in the same lane: r ^ (j / 32)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int q = r ^ (j >> 5);
+          if (q > r) {
+            const int t = r * 32 + lane;
+            const bool up = (t & k) == 0;
+            const bool gt = (d[r] > d[q]) || (d[r] == d[q] && sl[r] > sl[q]);
+            if (gt == up) {
+              const float td = d[r]; d[r] = d[q]; d[q] = td;
+              const int ts = sl[r]; sl[r] = sl[q]; sl[q] = ts;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int t = r * 32 + lane;
+          const float od = __shfl_xor_sync(NSVF_FULL_MASK, d[r], j);
+          const int os = __shfl_xor_sync(NSVF_FULL_MASK, sl[r], j);
+          const bool up = (t & k) == 0;
+          const bool lower = (lane & j) == 0;
+          const bool mine_gt = (d[r] > od) || (d[r] == od && sl[r] > os);
+          // the lower position of the pair keeps the smaller key when sorting up, the larger when sorting down
+          const bool take_other = (up == lower) ? mine_gt : !mine_gt;
+          if (take_other) { d[r] = od; sl[r] = os; }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int t = r * 32 + lane;
+    if (t < cnt) perm[t] = sl[r];
+  }
+}
+
+__device__ __forceinline__ void aabb_sort_by_depth(const float* h_min, int cnt, int* perm) {
+  if (cnt <= 16) {   // rank sort: one element per lane, keys broadcast from shared memory (cnt iterations)
+    const int lane = threadIdx.x & 31;
     if (lane < cnt) {
       const float d = h_min[lane];
       int rank = 0;
@@ -281,8 +335,13 @@ __device__ __forceinline__ void aabb_sort_by_depth(const float* h_min, int cnt, 
       }
       perm[rank] = lane;
     }
-  } else {           // bitonic network over (depth, slot) keys, padded to a power of two with +inf
-    int n2 = 64;
+  } else if (cnt <= 32) aabb_bitonic_regs<1>(h_min, cnt, perm);
+  else if (cnt <= 64) aabb_bitonic_regs<2>(h_min, cnt, perm);
+  else if (cnt <= 128) aabb_bitonic_regs<4>(h_min, cnt, perm);
+  else if (cnt <= 256) aabb_bitonic_regs<8>(h_min, cnt, perm);
+  else {             // very long hit lists: bitonic network in shared memory over (depth, slot) keys
+    const int lane = threadIdx.x & 31;
+    int n2 = 512;
     while (n2 < cnt) n2 <<= 1;
     for (int t = lane; t < n2; t += 32) perm[t] = t;
     __syncwarp();
@@ -473,6 +532,48 @@ aabb_small_kernel(const __grid_constant__ AabbTree tree, long long tree_stride_b
   }
 }
 
+// Stand-alone epilogue for hit lists produced elsewhere (the octree traversal): in-place masked_fill + sort by entry
+// depth + any(), i.e. SparseVoxelEncoder.ray_intersect's post-processing (encoder.py:519-524), one warp per ray.
+__global__ void __launch_bounds__(kAabbWarps * 32)
+sort_hits_kernel(long long rays, int n_max, int sort_slots, float empty_depth, int* __restrict__ idx,
+                 float* __restrict__ dmin, float* __restrict__ dmax, unsigned char* __restrict__ out_hit) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* h = aabb_smem + (size_t)warp * (3 * n_max + sort_slots);
+  int* h_idx = reinterpret_cast<int*>(h);
+  float* h_min = h + n_max;
+  float* h_max = h + 2 * n_max;
+  int* perm = reinterpret_cast<int*>(h + 3 * n_max);
+  for (long long ray = (long long)blockIdx.x * kAabbWarps + warp; ray < rays; ray += (long long)gridDim.x * kAabbWarps) {
+    const long long row = ray * n_max;
+    // compact the valid entries to the front, keeping their order (the reference sorts all slots; -1 slots carry
+    // MAX_DEPTH and end up last)
+    int cnt = 0;
+    for (int l0 = 0; l0 < n_max; l0 += 32) {
+      const int l = l0 + lane;
+      const int v = l < n_max ? idx[row + l] : -1;
+      const unsigned m = __ballot_sync(NSVF_FULL_MASK, v != -1);
+      if (v != -1) {
+        const int r = cnt + __popc(m & ((1u << lane) - 1u));
+        h_idx[r] = v;
+        h_min[r] = dmin[row + l];
+        h_max[r] = dmax[row + l];
+      }
+      cnt += __popc(m);
+    }
+    __syncwarp();
+    aabb_sort_by_depth(h_min, cnt, perm);
+    for (int l = lane; l < n_max; l += 32) {
+      const bool ok = l < cnt;
+      const int src = ok ? perm[l] : 0;
+      idx[row + l] = ok ? h_idx[src] : -1;
+      dmin[row + l] = ok ? h_min[src] : empty_depth;
+      dmax[row + l] = ok ? h_max[src] : empty_depth;
+    }
+    if (out_hit != nullptr && lane == 0) out_hit[ray] = cnt > 0;
+    __syncwarp();
+  }
+}
+
 static size_t aabb_tree_floats(int n) { return (size_t)6 * aabb_layout(n).total; }
 
 template <int NL, int MODE>
@@ -648,4 +749,26 @@ extern "C" int nsvf_aabb_hit_mask(nsvf_stream_t stream, int b, int n, int m, flo
                                   unsigned char* hits, void* workspace, size_t workspace_bytes) {
   return aabb_run((cudaStream_t)stream, kModeAnyHit, b, n, m, voxelsize, 0, 0.0f, ray_start, ray_dir, points,
                   points_batch_stride, nullptr, nullptr, nullptr, hits, workspace, workspace_bytes);
+}
+
+extern "C" int nsvf_sort_hits_by_depth(nsvf_stream_t stream_, long long rays, int n_max, float empty_depth, int* idx,
+                                       float* min_depth, float* max_depth, unsigned char* hits) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSVF_REQUIRE(rays >= 0 && n_max >= 0, "sort_hits_by_depth: negative size");
+  if (rays == 0 || n_max == 0) return 0;
+  int sort_slots = 64;
+  while (sort_slots < n_max) sort_slots <<= 1;
+  const size_t smem = (size_t)kAabbWarps * (3 * n_max + sort_slots) * sizeof(float);
+  NSVF_REQUIRE(smem <= 200 * 1024, "sort_hits_by_depth: n_max=%d needs %zu B of shared memory", n_max, smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    NSVF_CUDA_OK(cudaFuncSetAttribute(sort_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  long long want = (rays + kAabbWarps - 1) / kAabbWarps, cap = (long long)num_sms() * 6;
+  sort_hits_kernel<<<(unsigned)(want < cap ? want : cap), kAabbWarps * 32, smem, stream>>>(rays, n_max, sort_slots,
+                                                                                       empty_depth, idx, min_depth,
+                                                                                       max_depth, hits);
+  NSVF_LAUNCH_OK("sort_hits_kernel");
+  return 0;
 }

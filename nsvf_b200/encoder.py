@@ -131,13 +131,16 @@ class SparseVoxelEncoder(nn.Module):
                 centers, children = centers.unsqueeze(0), children.unsqueeze(0)
             pts_idx, min_depth, max_depth = clib.svo_ray_intersect(
                 self.voxel_size, self.max_hits, centers, children, ray_start, ray_dir)
-            # sort by entry depth (encoder.py:519-524)
-            min_depth.masked_fill_(pts_idx.eq(-1), MAX_DEPTH)
-            max_depth.masked_fill_(pts_idx.eq(-1), MAX_DEPTH)
-            min_depth, sorted_idx = min_depth.sort(dim=-1)
-            max_depth = max_depth.gather(-1, sorted_idx)
-            pts_idx = pts_idx.gather(-1, sorted_idx)
-            hits = pts_idx.ne(-1).any(-1)
+            # masked_fill + sort by entry depth + gather + any() (encoder.py:519-524) as one in-place kernel
+            if min_depth.dtype == torch.float32 and min_depth.is_contiguous() and pts_idx.is_contiguous():
+                hits = clib._ext.sort_hits_by_depth(pts_idx, min_depth, max_depth, MAX_DEPTH)
+            else:
+                min_depth.masked_fill_(pts_idx.eq(-1), MAX_DEPTH)
+                max_depth.masked_fill_(pts_idx.eq(-1), MAX_DEPTH)
+                min_depth, sorted_idx = min_depth.sort(dim=-1)
+                max_depth = max_depth.gather(-1, sorted_idx)
+                pts_idx = pts_idx.gather(-1, sorted_idx)
+                hits = pts_idx.ne(-1).any(-1)
         else:
             # intersection + masked_fill + sort + gather + any() of encoder.py:511-524 in ONE kernel
             pts_idx, min_depth, max_depth, hits = clib._ext.aabb_intersect_sorted(

@@ -228,3 +228,23 @@ def test_encoder_ray_intersect_matches_reference_pipeline(cuda, ref_ext):
     assert torch.equal(inter["intersected_voxel_idx"].sort(-1)[0], r_idx.sort(-1)[0])
     _, _, h2 = enc.ray_hit_mask(rs, rd, st)
     assert torch.equal(h2, r_hits)
+
+
+def test_encoder_octree_ray_intersect_matches_reference_pipeline(cuda, ref_ext):
+    """use_octree=True: svo kernel + the in-place sort kernel == reference svo wrapper + torch post-processing."""
+    from nsvf_b200.encoder import SparseVoxelEncoder
+    pts0 = synthetic.carve_shell(synthetic.bbox_voxels([-2.4] * 3, [2.4] * 3, 0.4))
+    p, vs = synthetic.split_points(pts0, 0.4, 1)
+    enc = SparseVoxelEncoder(p, vs, max_hits=90, use_octree=True).to(cuda)
+    st = enc.precompute(id=torch.zeros(1, dtype=torch.long, device=cuda))
+    rs, rd = synthetic.camera_rays(48, 48, 2, radius=4.5, device=cuda)
+    rs, rd = rs[None, :, None, 0, :].contiguous(), rd[None].contiguous()
+    ray_start, ray_dir, inter, hits = enc.ray_intersect(rs, rd, st)
+    ref = wrappers.svo_ray_intersect(ref_ext, float(enc.voxel_size), int(enc.max_hits),
+                                     st["voxel_octree_center_xyz"], st["voxel_octree_children_idx"], ray_start, ray_dir)
+    r_idx, r_min, r_max, r_hits = wrappers.sort_hits(*ref)
+    assert torch.equal(hits, r_hits) and torch.equal(inter["min_depth"], r_min)
+    ties = (r_min[..., 1:] == r_min[..., :-1]) & (r_idx[..., 1:] != -1)
+    clean = ~ties.any(-1)
+    assert torch.equal(inter["intersected_voxel_idx"][clean], r_idx[clean])
+    assert torch.equal(inter["max_depth"][clean], r_max[clean]) and int(hits.sum()) > 1000
