@@ -4,18 +4,21 @@
 // scanning all n voxels) and its host glue fairnr/clib/src/intersect.cpp:49-75.
 //
 // Design (not a port):
-//   * The reference result is "the n_max smallest voxel indices whose slab test hits".  We keep the
-//     slab test bit-identical (common.cuh) but never scan all voxels: an implicit 32-ary hierarchy of
-//     enclosing boxes is built over the voxels IN INDEX ORDER (node j of level l covers voxels
-//     [j*32^l, (j+1)*32^l)), so a depth-first walk in child order emits hits in ascending voxel index
-//     and can stop at n_max exactly like the reference loop does.
-//   * One warp owns one ray.  Each step tests the 32 children of a node, one per lane, with coalesced
-//     SoA loads; __ballot_sync gives the hit mask, __popc of the lower lanes gives each hit's output
-//     rank (ballot/prefix compaction).  Control flow is warp-uniform: no divergence.
-//   * The upper levels of the hierarchy (everything that fits NSVF_AABB_SMEM_NODES) are staged into
-//     shared memory once per persistent CTA with TMA bulk copies (cp.async.bulk + mbarrier).
-//   * Hits are collected in shared memory and each ray's row [n_max] x {idx,min,max} is written once,
-//     coalesced, including the -1 / 0 fill that the reference gets from torch::zeros + a per-thread loop.
+//   * The reference result is "the n_max smallest voxel indices whose slab test hits".  We keep the slab test
+//     bit-identical (common.cuh) but never scan all voxels: an implicit 8-ary hierarchy of enclosing boxes is built
+//     over the voxels IN INDEX ORDER (node j of level l covers voxels [j*8^l, (j+1)*8^l); after a split the 8
+//     children of a voxel are consecutive, so level-1 nodes are exactly the parent voxels).
+//   * One warp owns one ray and walks the hierarchy breadth-first: the hit nodes of a level live in an ascending
+//     list in shared memory; each step takes FOUR of them and tests their 4 x 8 children, one per lane (dense lane
+//     use at every level), `__ballot_sync` + `__popc` append the hit children in ascending order to the next list
+//     (ballot/prefix compaction).  At the leaf level the same step emits hits in ascending voxel index and stops at
+//     n_max exactly like the reference's linear scan.  Control flow is warp-uniform: no divergence.
+//   * The upper levels of the hierarchy (everything that fits kAabbSmemNodes) are staged into shared memory once
+//     per persistent CTA with TMA bulk copies (cp.async.bulk + mbarrier).
+//   * Hits are collected in shared memory and each ray's row [n_max] x {idx,min,max} is written once, coalesced,
+//     including the -1 / 0 fill that the reference gets from torch::zeros + a per-thread loop; optionally sorted by
+//     entry depth first (a register bitonic network), which replaces encoder.py:519-524.
+//   * Few hundred voxels: a thread-per-ray scan over shared-memory boxes (aabb_small_kernel) beats any hierarchy.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -23,9 +26,10 @@
 
 namespace nsvf {
 
-constexpr int kAabbMaxLevels = 5;          // up to 32^5 = 33.5 M voxels
+constexpr int kAabbMaxLevels = 11;         // 8^10 * 32 > 2^31 voxels
 constexpr int kAabbSmemNodes = 4096;       // nodes staged per CTA: 6 * 4096 * 4 B = 96 KiB
 constexpr int kAabbWarps = 8;
+constexpr int kAabbListCap = 256;          // hit nodes kept per level and ray (continuation pass beyond that)
 
 struct AabbTree {
   const float* box;    // SoA: 6 arrays of `total` floats: lo.x lo.y lo.z hi.x hi.y hi.z
@@ -50,12 +54,11 @@ static AabbLayout aabb_layout(int n) {
     o += (c + 31) / 32 * 32;
     ++l;
     if (c <= 32) break;
-    c = (c + 31) / 32;
+    c = (c + 7) / 8;
   }
   L.nlevels = l;
   L.total = o;
-  // stage the largest suffix of levels that fits
-  L.stage_from = L.total;
+  L.stage_from = L.total;   // stage the largest suffix of levels that fits
   for (int k = l - 1; k >= 0; --k) {
     if (L.total - L.off[k] <= kAabbSmemNodes) L.stage_from = L.off[k];
     else break;
@@ -64,207 +67,85 @@ static AabbLayout aabb_layout(int n) {
 }
 
 // ---- hierarchy build ----------------------------------------------------------------------------
-// level 0 + level 1 in one pass: one warp per level-1 node reads 32 voxel centres, writes their exact
-// boxes (c - hv, c + hv: the reference's first rounding) and the strictly enclosing parent box.
-__global__ void aabb_build_l01_kernel(const float* __restrict__ points, long long tree_stride_pts, int n,
-                                      float half_voxel, float* __restrict__ box_all, long long tree_stride_box,
-                                      int total, int off1, int has_l1) {
+// level 0: exact voxel boxes (c - hv, c + hv: the reference's first rounding), padding zeroed
+__global__ void aabb_build_leaves_kernel(const float* __restrict__ points, long long tree_stride_pts, int n,
+                                         float half_voxel, float* __restrict__ box_all, long long tree_stride_box,
+                                         int total) {
   const float* pts = points + (long long)blockIdx.y * tree_stride_pts;
   float* box = box_all + (long long)blockIdx.y * tree_stride_box;
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  int n1 = (n + 31) / 32;
-  if (warp >= n1) return;
-  int i = warp * 32 + lane;
-  float lo[3], hi[3];
-  bool valid = i < n;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_pad = (n + 31) / 32 * 32;
+  if (i >= n_pad) return;
+  const bool valid = i < n;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    float c = valid ? pts[(long long)i * 3 + a] : 0.0f;
-    lo[a] = __fsub_rn(c, half_voxel);
-    hi[a] = __fadd_rn(c, half_voxel);
-    box[(long long)a * total + i] = valid ? lo[a] : 0.0f;
-    box[(long long)(3 + a) * total + i] = valid ? hi[a] : 0.0f;
-    if (!valid) { lo[a] = INFINITY; hi[a] = -INFINITY; }
-  }
-  if (!has_l1) return;
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-      lo[a] = fminf(lo[a], __shfl_xor_sync(NSVF_FULL_MASK, lo[a], s));
-      hi[a] = fmaxf(hi[a], __shfl_xor_sync(NSVF_FULL_MASK, hi[a], s));
-    }
-  }
-  if (lane < 3) {
-    box[(long long)lane * total + off1 + warp] = nextafterf(lo[lane], -INFINITY);
-    box[(long long)(3 + lane) * total + off1 + warp] = nextafterf(hi[lane], INFINITY);
-  }
-  if (warp == n1 - 1) {  // zero the level-1 padding (it is staged by TMA, never tested)
-    int pad_end = (n1 + 31) / 32 * 32;
-    for (int j = n1 + lane; j < pad_end; j += 32)
-      for (int a = 0; a < 6; ++a) box[(long long)a * total + off1 + j] = 0.0f;
+    const float c = valid ? pts[(long long)i * 3 + a] : 0.0f;
+    box[(long long)a * total + i] = valid ? __fsub_rn(c, half_voxel) : 0.0f;
+    box[(long long)(3 + a) * total + i] = valid ? __fadd_rn(c, half_voxel) : 0.0f;
   }
 }
 
-// level l >= 2 from level l-1 (already strict): one warp per node.
+// level l >= 1 from level l-1: one thread per node reduces its 8 children; level 1 is widened by one ulp so that
+// every node box is STRICTLY larger than the voxel boxes it encloses (keeps the NaN cases conservative)
 __global__ void aabb_build_up_kernel(float* __restrict__ box_all, long long tree_stride_box, int total,
-                                     int off_child, int cnt_child, int off_parent, int cnt_parent) {
+                                     int off_child, int cnt_child, int off_parent, int cnt_parent, int widen) {
   float* box = box_all + (long long)blockIdx.y * tree_stride_box;
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (warp >= cnt_parent) return;
-  int i = warp * 32 + lane;
-  bool valid = i < cnt_child;
-  float lo[3], hi[3];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pad = (cnt_parent + 31) / 32 * 32;
+  if (j >= pad) return;
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  if (j < cnt_parent) {
+    for (int c = j * 8; c < min(j * 8 + 8, cnt_child); ++c) {
 #pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    lo[a] = valid ? box[(long long)a * total + off_child + i] : INFINITY;
-    hi[a] = valid ? box[(long long)(3 + a) * total + off_child + i] : -INFINITY;
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-      lo[a] = fminf(lo[a], __shfl_xor_sync(NSVF_FULL_MASK, lo[a], s));
-      hi[a] = fmaxf(hi[a], __shfl_xor_sync(NSVF_FULL_MASK, hi[a], s));
+      for (int a = 0; a < 3; ++a) {
+        lo[a] = fminf(lo[a], box[(long long)a * total + off_child + c]);
+        hi[a] = fmaxf(hi[a], box[(long long)(3 + a) * total + off_child + c]);
+      }
     }
   }
-  if (lane < 3) {
-    box[(long long)lane * total + off_parent + warp] = lo[lane];
-    box[(long long)(3 + lane) * total + off_parent + warp] = hi[lane];
-  }
-  // zero the padding of the parent level so staged copies never carry uninitialised words
-  if (warp == cnt_parent - 1) {
-    int pad_end = (cnt_parent + 31) / 32 * 32;
-    for (int j = cnt_parent + lane; j < pad_end; j += 32)
-      for (int a = 0; a < 6; ++a) box[(long long)a * total + off_parent + j] = 0.0f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float l = j < cnt_parent ? lo[a] : 0.0f, h = j < cnt_parent ? hi[a] : 0.0f;
+    if (widen && j < cnt_parent) { l = nextafterf(l, -INFINITY); h = nextafterf(h, INFINITY); }
+    box[(long long)a * total + off_parent + j] = l;
+    box[(long long)(3 + a) * total + off_parent + j] = h;
   }
 }
 
 // ---- traversal ------------------------------------------------------------------------------------
-extern __shared__ __align__(128) float aabb_smem[];   // [6][sm_nodes] staged boxes, then per-warp hit buffers
+extern __shared__ __align__(128) float aabb_smem[];   // [6][sm_nodes] staged boxes, then per-warp lists + hit buffers
 
 enum AabbMode { kModeIndexOrder = 0, kModeDepthSorted = 1, kModeAnyHit = 2 };
 
 struct AabbRay {
   float ox, oy, oz, ix, iy, iz;
+  bool regular;
 };
 
-struct AabbWarp {
-  const float* gbox;   // global SoA of this tree
-  int sm_nodes;
-  int hbuf;            // float offset of this warp's hit buffers inside aabb_smem
-  int n_max;
-};
-
-// One step of the fast path (regular rays: no NaN can occur, fmin/fmax ordering == the reference's swap):
-// the 32 lanes test nodes base..base+31 of level L.  `tree` is the __grid_constant__ kernel parameter, so
-// cnt[L] / off[L] with a compile-time L are constant-bank operands.
-template <int L>
-__device__ __forceinline__ unsigned aabb_test32(const AabbTree& tree, const AabbWarp& c, const AabbRay& r, int base,
-                                                float& tn, float& tf) {
-  const int lane = threadIdx.x & 31;
-  const int i = base + lane;
-  const bool valid = i < tree.cnt[L];
-  const int pos = tree.off[L] + (valid ? i : tree.cnt[L] - 1);
+// Slab test of box `pos` of the SoA: exact at the leaves, conservative on enclosing nodes (see common.cuh).
+template <bool LEAF>
+__device__ __forceinline__ bool aabb_test(const AabbTree& tree, const float* __restrict__ gbox, int sm_nodes,
+                                          bool staged, int pos, const AabbRay& r, float& tn, float& tf) {
   float lx, ly, lz, hx, hy, hz;
-  if (tree.off[L] >= tree.stage_from) {   // level staged in shared memory (uniform)
+  if (staged) {
     const float* s = aabb_smem + (pos - tree.stage_from);
-    const int st = c.sm_nodes;
-    lx = s[0]; ly = s[st]; lz = s[2 * st]; hx = s[3 * st]; hy = s[4 * st]; hz = s[5 * st];
+    lx = s[0]; ly = s[sm_nodes]; lz = s[2 * sm_nodes]; hx = s[3 * sm_nodes]; hy = s[4 * sm_nodes]; hz = s[5 * sm_nodes];
   } else {
-    const float* g = c.gbox + pos;
-    const int st = tree.total;
+    const float* g = gbox + pos;
+    const long long st = tree.total;
     lx = __ldg(g); ly = __ldg(g + st); lz = __ldg(g + 2 * st);
-    hx = __ldg(g + 3 * (long long)st); hy = __ldg(g + 4 * (long long)st); hz = __ldg(g + 5 * (long long)st);
+    hx = __ldg(g + 3 * st); hy = __ldg(g + 4 * st); hz = __ldg(g + 5 * st);
   }
-  const float a0 = __fmul_rn(__fsub_rn(lx, r.ox), r.ix), b0 = __fmul_rn(__fsub_rn(hx, r.ox), r.ix);
-  const float a1 = __fmul_rn(__fsub_rn(ly, r.oy), r.iy), b1 = __fmul_rn(__fsub_rn(hy, r.oy), r.iy);
-  const float a2 = __fmul_rn(__fsub_rn(lz, r.oz), r.iz), b2 = __fmul_rn(__fsub_rn(hz, r.oz), r.iz);
-  tn = fmaxf(fmaxf(0.0f, fminf(a0, b0)), fmaxf(fminf(a1, b1), fminf(a2, b2)));
-  tf = fminf(fminf(100000.0f, fmaxf(a0, b0)), fminf(fmaxf(a1, b1), fmaxf(a2, b2)));
-  return __ballot_sync(NSVF_FULL_MASK, valid && (tn <= tf));
-}
-
-template <int L, int MODE>
-__device__ __forceinline__ void aabb_descend(const AabbTree& tree, const AabbWarp& c, const AabbRay& r, int base,
-                                             int& cnt) {
-  float tn, tf;
-  unsigned m = aabb_test32<L>(tree, c, r, base, tn, tf);
-  if constexpr (L == 0) {
-    if constexpr (MODE != kModeAnyHit) {
-      const int lane = threadIdx.x & 31;
-      if ((m >> lane) & 1u) {
-        const int rank = cnt + __popc(m & ((1u << lane) - 1u));
-        if (rank < c.n_max) {
-          float* h = aabb_smem + c.hbuf;
-          reinterpret_cast<int*>(h)[rank] = base + lane;
-          h[c.n_max + rank] = tn;
-          h[2 * c.n_max + rank] = tf;
-        }
-      }
-    }
-    cnt += __popc(m);
-  } else {
-    while (m != 0u && cnt < c.n_max) {
-      const int b = __ffs(m) - 1;
-      m &= m - 1u;
-      aabb_descend<L - 1, MODE>(tree, c, r, (base + b) * 32, cnt);
-    }
+  if (r.regular) {   // no NaN possible: fmin/fmax ordering == the reference's swap, at leaves and nodes alike
+    const float a0 = __fmul_rn(__fsub_rn(lx, r.ox), r.ix), b0 = __fmul_rn(__fsub_rn(hx, r.ox), r.ix);
+    const float a1 = __fmul_rn(__fsub_rn(ly, r.oy), r.iy), b1 = __fmul_rn(__fsub_rn(hy, r.oy), r.iy);
+    const float a2 = __fmul_rn(__fsub_rn(lz, r.oz), r.iz), b2 = __fmul_rn(__fsub_rn(hz, r.oz), r.iz);
+    tn = fmaxf(fmaxf(0.0f, fminf(a0, b0)), fmaxf(fminf(a1, b1), fminf(a2, b2)));
+    tf = fminf(fminf(100000.0f, fmaxf(a0, b0)), fminf(fmaxf(a1, b1), fmaxf(a2, b2)));
+    return tn <= tf;
   }
-}
-
-// Slow path for rays whose slab test can produce NaN (a zero / non-finite direction component, a non-finite
-// origin): exact select-based test at the leaves, conservative fmin/fmax test on the enclosing nodes.
-// Runtime level loop; never on the hot path.
-__device__ __noinline__ void aabb_traverse_irregular(const AabbTree& tree, const AabbWarp& c, const AabbRay& r,
-                                                     int mode, int& cnt) {
-  const int lane = threadIdx.x & 31;
-  unsigned mask[kAabbMaxLevels];
-  int node[kAabbMaxLevels];
-  int L = tree.nlevels - 1;
-  node[L] = 0;
-  bool fresh = true;   // node[L] group not tested yet
-  for (;;) {
-    if (fresh) {
-      const int i = node[L] + lane;
-      bool hit = false;
-      float tn = 0.f, tf = 0.f;
-      if (i < tree.cnt[L]) {
-        const float* g = c.gbox + tree.off[L] + i;
-        const long long st = tree.total;
-        const float lx = g[0], ly = g[st], lz = g[2 * st], hx = g[3 * st], hy = g[4 * st], hz = g[5 * st];
-        if (L == 0) hit = slab_exact(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, lx, ly, lz, hx, hy, hz, tn, tf);
-        else hit = slab_enclosing(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, lx, ly, lz, hx, hy, hz);
-      }
-      const unsigned m = __ballot_sync(NSVF_FULL_MASK, hit);
-      if (L == 0) {
-        if (mode != kModeAnyHit && hit) {
-          const int rank = cnt + __popc(m & ((1u << lane) - 1u));
-          if (rank < c.n_max) {
-            float* h = aabb_smem + c.hbuf;
-            reinterpret_cast<int*>(h)[rank] = i;
-            h[c.n_max + rank] = tn;
-            h[2 * c.n_max + rank] = tf;
-          }
-        }
-        cnt += __popc(m);
-        mask[0] = 0u;
-      } else {
-        mask[L] = m;
-      }
-      fresh = false;
-    }
-    if (cnt >= c.n_max) return;
-    if (L == 0 || mask[L] == 0u) {       // this group is exhausted: go up
-      if (L == tree.nlevels - 1) return;
-      ++L;
-      continue;
-    }
-    const int b = __ffs(mask[L]) - 1;
-    mask[L] &= mask[L] - 1u;
-    node[L - 1] = (node[L] + b) * 32;
-    --L;
-    fresh = true;
-  }
+  if (LEAF) return slab_exact(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, lx, ly, lz, hx, hy, hz, tn, tf);
+  return slab_enclosing(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, lx, ly, lz, hx, hy, hz);
 }
 
 // Warp-level stable sort of the first `cnt` hits by entry depth (ties keep ascending slot = ascending voxel
@@ -364,12 +245,13 @@ __device__ __forceinline__ void aabb_sort_by_depth(const float* h_min, int cnt, 
   __syncwarp();
 }
 
-template <int NL, int MODE>
+template <int MODE>
 __global__ void __launch_bounds__(kAabbWarps * 32)
 aabb_intersect_kernel(const __grid_constant__ AabbTree tree, long long tree_stride_box, long long rays_per_tree,
-                      int n_max, int sort_slots, float empty_depth, const float* __restrict__ ray_start,
-                      const float* __restrict__ ray_dir, int* __restrict__ out_idx, float* __restrict__ out_min,
-                      float* __restrict__ out_max, unsigned char* __restrict__ out_hit) {
+                      int n_max, int sort_slots, int list_cap, float empty_depth,
+                      const float* __restrict__ ray_start, const float* __restrict__ ray_dir,
+                      int* __restrict__ out_idx, float* __restrict__ out_min, float* __restrict__ out_max,
+                      unsigned char* __restrict__ out_hit) {
   __shared__ __align__(8) uint64_t bar;
   const int sm_nodes = tree.total - tree.stage_from;   // multiple of 32
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -392,17 +274,21 @@ aabb_intersect_kernel(const __grid_constant__ AabbTree tree, long long tree_stri
     mbar_wait(&bar, 0);
   }
 
-  AabbWarp c;
-  c.gbox = gbox;
-  c.sm_nodes = sm_nodes;
-  c.n_max = MODE == kModeAnyHit ? 1 : n_max;
-  const int per_warp = 3 * n_max + sort_slots;
-  c.hbuf = 6 * sm_nodes + warp * per_warp;
-  float* h = aabb_smem + c.hbuf;
+  const int hit_words = MODE == kModeAnyHit ? 0 : 3 * n_max + sort_slots;
+  const int per_warp = 2 * list_cap + hit_words;
+  float* wbase = aabb_smem + (size_t)6 * sm_nodes + (size_t)warp * per_warp;
+  int* list_a = reinterpret_cast<int*>(wbase);
+  int* list_b = list_a + list_cap;
+  float* h = wbase + 2 * list_cap;
   int* h_idx = reinterpret_cast<int*>(h);
   float* h_min = h + n_max;
   float* h_max = h + 2 * n_max;
   int* perm = reinterpret_cast<int*>(h + 3 * n_max);
+  const int top = tree.nlevels - 1;
+  const int limit = MODE == kModeAnyHit ? 1 : n_max;
+  // any-hit: keep only one 4-node batch per level, i.e. walk depth-first by batches (the continuation pass resumes
+  // behind the explored subtree), so a ray stops at its first hit instead of finishing whole levels
+  if (MODE == kModeAnyHit) list_cap = 4;
 
   const long long ray_base = (long long)blockIdx.y * rays_per_tree;
   for (long long rr = (long long)blockIdx.x * kAabbWarps + warp; rr < rays_per_tree;
@@ -418,12 +304,90 @@ aabb_intersect_kernel(const __grid_constant__ AabbTree tree, long long tree_stri
     r.ix = ref_rcp(__shfl_sync(NSVF_FULL_MASK, v, 3));
     r.iy = ref_rcp(__shfl_sync(NSVF_FULL_MASK, v, 4));
     r.iz = ref_rcp(__shfl_sync(NSVF_FULL_MASK, v, 5));
-    const bool regular =
-        regular_component(r.ox, r.ix) && regular_component(r.oy, r.iy) && regular_component(r.oz, r.iz);
+    r.regular = regular_component(r.ox, r.ix) && regular_component(r.oy, r.iy) && regular_component(r.oz, r.iz);
 
     int cnt = 0;
-    if (regular) aabb_descend<NL - 1, MODE>(tree, c, r, 0, cnt);
-    else aabb_traverse_irregular(tree, c, r, MODE, cnt);
+    long long leaf_lo = 0;          // leaves below this index are already done (continuation passes)
+    for (;;) {
+      long long next_lo = -1;       // >= 0: some level's list overflowed; leaves from here on need another pass
+      float tn = 0.f, tf = 0.f;
+      // top level: <= 32 nodes, one per lane
+      int n_cur;
+      {
+        const bool valid = lane < tree.cnt[top] && (((long long)(lane + 1)) << (3 * top)) > leaf_lo;
+        bool hit = false;
+        if (valid) {
+          if (top == 0) hit = aabb_test<true>(tree, gbox, sm_nodes, tree.off[0] >= tree.stage_from, tree.off[0] + lane, r, tn, tf);
+          else hit = aabb_test<false>(tree, gbox, sm_nodes, tree.off[top] >= tree.stage_from, tree.off[top] + lane, r, tn, tf);
+        }
+        const unsigned m = __ballot_sync(NSVF_FULL_MASK, hit);
+        if (top == 0) {
+          if (MODE != kModeAnyHit && hit) {
+            const int rank = cnt + __popc(m & ((1u << lane) - 1u));
+            if (rank < n_max) { h_idx[rank] = lane; h_min[rank] = tn; h_max[rank] = tf; }
+          }
+          cnt += __popc(m);
+          n_cur = 0;
+        } else {
+          if (hit) list_a[__popc(m & ((1u << lane) - 1u))] = lane;
+          n_cur = __popc(m);
+        }
+      }
+      __syncwarp();
+      int* cur = list_a;
+      int* nxt = list_b;
+      for (int L = top - 1; L >= 0 && n_cur > 0 && cnt < limit; --L) {
+        const bool staged = tree.off[L] >= tree.stage_from;
+        const int shift = 3 * L;
+        int n_nxt = 0;
+        // (once the next list has overflowed, the remaining nodes of this level lie beyond the continuation bound)
+        for (int base = 0; base < n_cur && cnt < limit && n_nxt <= list_cap; base += 4) {
+          const int p = base + (lane >> 3);
+          const int c = (p < n_cur ? cur[p] : 0) * 8 + (lane & 7);
+          const bool valid = p < n_cur && c < tree.cnt[L] && (((long long)(c + 1)) << shift) > leaf_lo;
+          bool hit = false;
+          if (valid) {
+            if (L == 0) hit = aabb_test<true>(tree, gbox, sm_nodes, staged, tree.off[0] + c, r, tn, tf);
+            else hit = aabb_test<false>(tree, gbox, sm_nodes, staged, tree.off[L] + c, r, tn, tf);
+          }
+          const unsigned m = __ballot_sync(NSVF_FULL_MASK, hit);
+          if (m == 0u) continue;
+          const int rank = __popc(m & ((1u << lane) - 1u));
+          if (L == 0) {
+            if (MODE != kModeAnyHit && hit && c >= leaf_lo && cnt + rank < n_max) {
+              h_idx[cnt + rank] = c;
+              h_min[cnt + rank] = tn;
+              h_max[cnt + rank] = tf;
+            }
+            // (c >= leaf_lo always holds for hits here: valid already filtered on (c+1) > leaf_lo)
+            cnt += __popc(m);
+          } else {
+            if (hit) {
+              const int slot = n_nxt + rank;
+              if (slot < list_cap) nxt[slot] = c;
+              else if (slot == list_cap) next_lo = ((long long)c) << shift;   // first dropped node (ascending order)
+            }
+            const int tot = n_nxt + __popc(m);
+            if (tot > list_cap && n_nxt <= list_cap) {
+              // broadcast the continuation bound computed by the lane that owned slot == list_cap
+              const unsigned owner_mask = __ballot_sync(NSVF_FULL_MASK, hit && (n_nxt + rank) == list_cap);
+              const long long bnd = __shfl_sync(NSVF_FULL_MASK, next_lo, __ffs(owner_mask) - 1);
+              next_lo = bnd;
+            }
+            n_nxt = min(tot, list_cap + 1);
+          }
+        }
+        __syncwarp();
+        if (L > 0) {
+          n_cur = min(n_nxt, list_cap);
+          int* t = cur; cur = nxt; nxt = t;
+        }
+      }
+      // a truncated list only ever dropped nodes whose leaves come AFTER every leaf handled so far, so the
+      // collected hits are exactly the first ones; continue from the first dropped leaf if more are needed
+      if (next_lo < 0 || cnt >= limit) break;
+      leaf_lo = next_lo;
+    }
 
     if constexpr (MODE == kModeAnyHit) {
       if (lane == 0) out_hit[ray] = cnt > 0;
@@ -576,41 +540,24 @@ sort_hits_kernel(long long rays, int n_max, int sort_slots, float empty_depth, i
 
 static size_t aabb_tree_floats(int n) { return (size_t)6 * aabb_layout(n).total; }
 
-template <int NL, int MODE>
+template <int MODE>
 static int aabb_launch(cudaStream_t stream, dim3 grid, size_t smem, const AabbTree& tree, long long tree_stride_box,
-                       long long rays_per_tree, int n_max, int sort_slots, float empty_depth, const float* ray_start,
-                       const float* ray_dir, int* idx, float* dmin, float* dmax, unsigned char* hit) {
+                       long long rays_per_tree, int n_max, int sort_slots, int list_cap, float empty_depth,
+                       const float* ray_start, const float* ray_dir, int* idx, float* dmin, float* dmax,
+                       unsigned char* hit) {
   static bool attr_set = false;
   if (!attr_set) {
-    NSVF_CUDA_OK(cudaFuncSetAttribute(aabb_intersect_kernel<NL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NSVF_CUDA_OK(cudaFuncSetAttribute(aabb_intersect_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       200 * 1024));
     attr_set = true;
   }
   const char* kname = MODE == kModeAnyHit ? "aabb_hit_mask_kernel"
                       : (MODE == kModeDepthSorted ? "aabb_intersect_sorted_kernel" : "aabb_intersect_kernel");
   NSVF_TIMED_LAUNCH(kname, stream,
-                    (aabb_intersect_kernel<NL, MODE><<<grid, kAabbWarps * 32, smem, stream>>>(
-                        tree, tree_stride_box, rays_per_tree, n_max, sort_slots, empty_depth, ray_start, ray_dir, idx,
-                        dmin, dmax, hit)));
+                    (aabb_intersect_kernel<MODE><<<grid, kAabbWarps * 32, smem, stream>>>(
+                        tree, tree_stride_box, rays_per_tree, n_max, sort_slots, list_cap, empty_depth, ray_start,
+                        ray_dir, idx, dmin, dmax, hit)));
   return 0;
-}
-
-template <int MODE>
-static int aabb_dispatch(int nlevels, cudaStream_t stream, dim3 grid, size_t smem, const AabbTree& tree,
-                         long long tree_stride_box, long long rays_per_tree, int n_max, int sort_slots,
-                         float empty_depth, const float* ray_start, const float* ray_dir, int* idx, float* dmin,
-                         float* dmax, unsigned char* hit) {
-#define NSVF_CASE(N)                                                                                              \
-  case N:                                                                                                         \
-    return aabb_launch<N, MODE>(stream, grid, smem, tree, tree_stride_box, rays_per_tree, n_max, sort_slots,       \
-                                empty_depth, ray_start, ray_dir, idx, dmin, dmax, hit);
-  switch (nlevels) {
-    NSVF_CASE(1) NSVF_CASE(2) NSVF_CASE(3) NSVF_CASE(4) NSVF_CASE(5)
-    default:
-      set_error("aabb_intersect: %d hierarchy levels (more than 32^5 voxels) are not supported", nlevels);
-      return 1;
-  }
-#undef NSVF_CASE
 }
 
 }  // namespace nsvf
@@ -657,17 +604,17 @@ static int aabb_run(cudaStream_t stream, int mode, int b, int n, int m, float vo
   const long long tree_stride_box = (long long)6 * L.total;
   const float half_voxel = voxelsize * 0.5f;  // reference: float half_voxel = voxelsize * 0.5 (exact)
 
-  {  // build the hierarchy (O(n), a few small launches)
-    int n1 = (n + 31) / 32;
-    dim3 grid((n1 + 7) / 8, n_trees);
-    aabb_build_l01_kernel<<<grid, 256, 0, stream>>>(points, points_batch_stride, n, half_voxel, box,
-                                                    tree_stride_box, L.total, L.nlevels > 1 ? L.off[1] : 0,
-                                                    L.nlevels > 1);
-    NSVF_LAUNCH_OK("aabb_build_l01_kernel");
-    for (int l = 2; l < L.nlevels; ++l) {
-      dim3 g((L.cnt[l] + 7) / 8, n_trees);
-      aabb_build_up_kernel<<<g, 256, 0, stream>>>(box, tree_stride_box, L.total, L.off[l - 1], L.cnt[l - 1],
-                                                  L.off[l], L.cnt[l]);
+  {  // build the hierarchy (O(n), one small launch per level)
+    const int n_pad = (n + 31) / 32 * 32;
+    dim3 g0((n_pad + 255) / 256, n_trees);
+    aabb_build_leaves_kernel<<<g0, 256, 0, stream>>>(points, points_batch_stride, n, half_voxel, box, tree_stride_box,
+                                                     L.total);
+    NSVF_LAUNCH_OK("aabb_build_leaves_kernel");
+    for (int l = 1; l < L.nlevels; ++l) {
+      const int pad = (L.cnt[l] + 31) / 32 * 32;
+      dim3 g((pad + 255) / 256, n_trees);
+      aabb_build_up_kernel<<<g, 256, 0, stream>>>(box, tree_stride_box, L.total, L.off[l - 1], L.cnt[l - 1], L.off[l],
+                                                  L.cnt[l], l == 1);
       NSVF_LAUNCH_OK("aabb_build_up_kernel");
     }
   }
@@ -686,7 +633,9 @@ static int aabb_run(cudaStream_t stream, int mode, int b, int n, int m, float vo
     sort_slots = 64;
     while (sort_slots < n_max) sort_slots <<= 1;
   }
-  const int per_warp = mode == kModeAnyHit ? 0 : 3 * n_max + sort_slots;
+  int list_cap = kAabbListCap;
+  if (const char* e = getenv("NSVF_AABB_LIST_CAP")) list_cap = atoi(e) < 32 ? 32 : atoi(e);   // test hook (>= 32: the top level writes up to 32 entries)
+  const int per_warp = 2 * list_cap + (mode == kModeAnyHit ? 0 : 3 * n_max + sort_slots);
   size_t smem = ((size_t)6 * sm_nodes + (size_t)kAabbWarps * per_warp) * sizeof(float);
   NSVF_REQUIRE(smem <= 200 * 1024, "aabb_intersect: n_max=%d needs %zu B of shared memory", n_max, smem);
   int blocks_per_sm = (int)((220 * 1024) / (smem + 1024));
@@ -716,14 +665,14 @@ static int aabb_run(cudaStream_t stream, int mode, int b, int n, int m, float vo
   const int nm = mode == kModeAnyHit ? 0 : n_max;
   switch (mode) {
     case kModeIndexOrder:
-      return aabb_dispatch<kModeIndexOrder>(L.nlevels, stream, grid, smem, tree, tree_stride_box, rays_per_tree, nm,
-                                            sort_slots, empty_depth, ray_start, ray_dir, idx, min_depth, max_depth, hit);
+      return aabb_launch<kModeIndexOrder>(stream, grid, smem, tree, tree_stride_box, rays_per_tree, nm, sort_slots,
+                                          list_cap, empty_depth, ray_start, ray_dir, idx, min_depth, max_depth, hit);
     case kModeDepthSorted:
-      return aabb_dispatch<kModeDepthSorted>(L.nlevels, stream, grid, smem, tree, tree_stride_box, rays_per_tree, nm,
-                                             sort_slots, empty_depth, ray_start, ray_dir, idx, min_depth, max_depth, hit);
+      return aabb_launch<kModeDepthSorted>(stream, grid, smem, tree, tree_stride_box, rays_per_tree, nm, sort_slots,
+                                           list_cap, empty_depth, ray_start, ray_dir, idx, min_depth, max_depth, hit);
     default:
-      return aabb_dispatch<kModeAnyHit>(L.nlevels, stream, grid, smem, tree, tree_stride_box, rays_per_tree, nm,
-                                        sort_slots, empty_depth, ray_start, ray_dir, idx, min_depth, max_depth, hit);
+      return aabb_launch<kModeAnyHit>(stream, grid, smem, tree, tree_stride_box, rays_per_tree, nm, sort_slots,
+                                      list_cap, empty_depth, ray_start, ray_dir, idx, min_depth, max_depth, hit);
   }
 }
 
