@@ -122,30 +122,98 @@ struct AabbRay {
   bool regular;
 };
 
-// Slab test of box `pos` of the SoA: exact at the leaves, conservative on enclosing nodes (see common.cuh).
-template <bool LEAF>
-__device__ __forceinline__ bool aabb_test(const AabbTree& tree, const float* __restrict__ gbox, int sm_nodes,
-                                          bool staged, int pos, const AabbRay& r, float& tn, float& tf) {
-  float lx, ly, lz, hx, hy, hz;
-  if (staged) {
-    const float* s = aabb_smem + (pos - tree.stage_from);
-    lx = s[0]; ly = s[sm_nodes]; lz = s[2 * sm_nodes]; hx = s[3 * sm_nodes]; hy = s[4 * sm_nodes]; hz = s[5 * sm_nodes];
-  } else {
-    const float* g = gbox + pos;
-    const long long st = tree.total;
-    lx = __ldg(g); ly = __ldg(g + st); lz = __ldg(g + 2 * st);
-    hx = __ldg(g + 3 * st); hy = __ldg(g + 4 * st); hz = __ldg(g + 5 * st);
+struct AabbWarpState {
+  const float* gbox;      // global SoA of this tree
+  int total, sm_nodes, stage_from;
+  int* h_idx;             // per-warp hit buffers (shared memory)
+  float* h_min;
+  float* h_max;
+  int n_max, list_cap;
+};
+
+// One level of the breadth-first walk: the ascending list `cur` (n_cur hit nodes of level L+1) is consumed four
+// nodes per step, their 4 x 8 children (level L) are tested one per lane, and the hit children are appended in
+// ascending order to `nxt` (L > 0) or emitted as hits (L == 0).  LEAF / STAGED / REGULAR are hoisted out of the
+// loop as template parameters; invalid lanes load a clamped index instead of branching.
+//   lo_node : children below this index hold only leaves that were already handled (continuation passes)
+//   returns the number of entries written to `nxt` (list_cap + 1 if it overflowed; next_lo then holds the first
+//   leaf of the first dropped child)
+template <bool LEAF, bool STAGED, bool REGULAR, int MODE>
+__device__ __forceinline__ int aabb_level(const AabbWarpState& w, const AabbRay& r, int offL, int cntL, int shift,
+                                          int lo_node, const int* cur, int n_cur, int* nxt, int& cnt, int limit,
+                                          long long& next_lo) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & 7, quad = lane >> 3;
+  const unsigned lt = (1u << lane) - 1u;
+  int n_nxt = 0;
+  for (int base = 0; base < n_cur && cnt < limit && n_nxt <= w.list_cap; base += 4) {
+    const int p = base + quad;
+    const int c = cur[min(p, n_cur - 1)] * 8 + sub;
+    const bool valid = p < n_cur && c < cntL && c >= lo_node;
+    const int pos = offL + min(c, cntL - 1);
+    float lx, ly, lz, hx, hy, hz;
+    if (STAGED) {
+      const float* s = aabb_smem + (pos - w.stage_from);
+      const int st = w.sm_nodes;
+      lx = s[0]; ly = s[st]; lz = s[2 * st]; hx = s[3 * st]; hy = s[4 * st]; hz = s[5 * st];
+    } else {
+      const float* g = w.gbox + pos;
+      const int st = w.total;
+      lx = __ldg(g); ly = __ldg(g + st); lz = __ldg(g + 2 * st);
+      hx = __ldg(g + 3 * (long long)st); hy = __ldg(g + 4 * (long long)st); hz = __ldg(g + 5 * (long long)st);
+    }
+    float tn, tf;
+    bool hit;
+    if (REGULAR) {   // no NaN possible: fmin/fmax ordering == the reference's swap, at leaves and nodes alike
+      const float a0 = __fmul_rn(__fsub_rn(lx, r.ox), r.ix), b0 = __fmul_rn(__fsub_rn(hx, r.ox), r.ix);
+      const float a1 = __fmul_rn(__fsub_rn(ly, r.oy), r.iy), b1 = __fmul_rn(__fsub_rn(hy, r.oy), r.iy);
+      const float a2 = __fmul_rn(__fsub_rn(lz, r.oz), r.iz), b2 = __fmul_rn(__fsub_rn(hz, r.oz), r.iz);
+      tn = fmaxf(fmaxf(0.0f, fminf(a0, b0)), fmaxf(fminf(a1, b1), fminf(a2, b2)));
+      tf = fminf(fminf(100000.0f, fmaxf(a0, b0)), fminf(fmaxf(a1, b1), fmaxf(a2, b2)));
+      hit = tn <= tf;
+    } else if (LEAF) {
+      hit = slab_exact(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, lx, ly, lz, hx, hy, hz, tn, tf);
+    } else {
+      hit = slab_enclosing(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, lx, ly, lz, hx, hy, hz);
+    }
+    hit = hit && valid;
+    const unsigned m = __ballot_sync(NSVF_FULL_MASK, hit);
+    if (m == 0u) continue;
+    const int rank = __popc(m & lt);
+    if (LEAF) {
+      if (MODE != kModeAnyHit && hit && cnt + rank < w.n_max) {
+        w.h_idx[cnt + rank] = c;
+        w.h_min[cnt + rank] = tn;
+        w.h_max[cnt + rank] = tf;
+      }
+      cnt += __popc(m);
+    } else {
+      const int slot = n_nxt + rank;
+      if (hit && slot < w.list_cap) nxt[slot] = c;
+      const int tot = n_nxt + __popc(m);
+      if (tot > w.list_cap) {   // overflow: remember the first leaf of the first dropped child (ascending order)
+        const unsigned owner = __ballot_sync(NSVF_FULL_MASK, hit && slot == w.list_cap);
+        const int c_first = __shfl_sync(NSVF_FULL_MASK, c, __ffs(owner) - 1);
+        next_lo = ((long long)c_first) << shift;
+        n_nxt = w.list_cap + 1;
+      } else {
+        n_nxt = tot;
+      }
+    }
   }
-  if (r.regular) {   // no NaN possible: fmin/fmax ordering == the reference's swap, at leaves and nodes alike
-    const float a0 = __fmul_rn(__fsub_rn(lx, r.ox), r.ix), b0 = __fmul_rn(__fsub_rn(hx, r.ox), r.ix);
-    const float a1 = __fmul_rn(__fsub_rn(ly, r.oy), r.iy), b1 = __fmul_rn(__fsub_rn(hy, r.oy), r.iy);
-    const float a2 = __fmul_rn(__fsub_rn(lz, r.oz), r.iz), b2 = __fmul_rn(__fsub_rn(hz, r.oz), r.iz);
-    tn = fmaxf(fmaxf(0.0f, fminf(a0, b0)), fmaxf(fminf(a1, b1), fminf(a2, b2)));
-    tf = fminf(fminf(100000.0f, fmaxf(a0, b0)), fminf(fmaxf(a1, b1), fmaxf(a2, b2)));
-    return tn <= tf;
+  return n_nxt;
+}
+
+template <bool LEAF, int MODE>
+__device__ __forceinline__ int aabb_level_dispatch(const AabbWarpState& w, const AabbRay& r, bool staged, int offL,
+                                                   int cntL, int shift, int lo_node, const int* cur, int n_cur,
+                                                   int* nxt, int& cnt, int limit, long long& next_lo) {
+  if (r.regular) {
+    if (staged) return aabb_level<LEAF, true, true, MODE>(w, r, offL, cntL, shift, lo_node, cur, n_cur, nxt, cnt, limit, next_lo);
+    return aabb_level<LEAF, false, true, MODE>(w, r, offL, cntL, shift, lo_node, cur, n_cur, nxt, cnt, limit, next_lo);
   }
-  if (LEAF) return slab_exact(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, lx, ly, lz, hx, hy, hz, tn, tf);
-  return slab_enclosing(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, lx, ly, lz, hx, hy, hz);
+  if (staged) return aabb_level<LEAF, true, false, MODE>(w, r, offL, cntL, shift, lo_node, cur, n_cur, nxt, cnt, limit, next_lo);
+  return aabb_level<LEAF, false, false, MODE>(w, r, offL, cntL, shift, lo_node, cur, n_cur, nxt, cnt, limit, next_lo);
 }
 
 // Warp-level stable sort of the first `cnt` hits by entry depth (ties keep ascending slot = ascending voxel
@@ -286,9 +354,13 @@ aabb_intersect_kernel(const __grid_constant__ AabbTree tree, long long tree_stri
   int* perm = reinterpret_cast<int*>(h + 3 * n_max);
   const int top = tree.nlevels - 1;
   const int limit = MODE == kModeAnyHit ? 1 : n_max;
+  AabbWarpState w;
+  w.gbox = gbox; w.total = tree.total; w.sm_nodes = sm_nodes; w.stage_from = tree.stage_from;
+  w.h_idx = h_idx; w.h_min = h_min; w.h_max = h_max; w.n_max = n_max;
   // any-hit: keep only one 4-node batch per level, i.e. walk depth-first by batches (the continuation pass resumes
   // behind the explored subtree), so a ray stops at its first hit instead of finishing whole levels
   if (MODE == kModeAnyHit) list_cap = 4;
+  w.list_cap = list_cap;
 
   const long long ray_base = (long long)blockIdx.y * rays_per_tree;
   for (long long rr = (long long)blockIdx.x * kAabbWarps + warp; rr < rays_per_tree;
@@ -310,78 +382,57 @@ aabb_intersect_kernel(const __grid_constant__ AabbTree tree, long long tree_stri
     long long leaf_lo = 0;          // leaves below this index are already done (continuation passes)
     for (;;) {
       long long next_lo = -1;       // >= 0: some level's list overflowed; leaves from here on need another pass
-      float tn = 0.f, tf = 0.f;
-      // top level: <= 32 nodes, one per lane
+      // top level: <= 32 nodes, one per lane; its hits seed list_a (as "parents" of a virtual level: we store the
+      // node ids themselves and let the level routine expand children, so the top is handled by a direct test)
       int n_cur;
       {
-        const bool valid = lane < tree.cnt[top] && (((long long)(lane + 1)) << (3 * top)) > leaf_lo;
-        bool hit = false;
-        if (valid) {
-          if (top == 0) hit = aabb_test<true>(tree, gbox, sm_nodes, tree.off[0] >= tree.stage_from, tree.off[0] + lane, r, tn, tf);
-          else hit = aabb_test<false>(tree, gbox, sm_nodes, tree.off[top] >= tree.stage_from, tree.off[top] + lane, r, tn, tf);
+        const int c = lane;
+        const bool valid = c < tree.cnt[top] && c >= (int)(leaf_lo >> (3 * top));
+        const int pos = tree.off[top] + min(c, tree.cnt[top] - 1);
+        const bool staged = tree.off[top] >= tree.stage_from;
+        float lx, ly, lz, hx, hy, hz;
+        if (staged) {
+          const float* sp = aabb_smem + (pos - tree.stage_from);
+          lx = sp[0]; ly = sp[sm_nodes]; lz = sp[2 * sm_nodes]; hx = sp[3 * sm_nodes]; hy = sp[4 * sm_nodes]; hz = sp[5 * sm_nodes];
+        } else {
+          const float* g = gbox + pos;
+          const long long st = tree.total;
+          lx = g[0]; ly = g[st]; lz = g[2 * st]; hx = g[3 * st]; hy = g[4 * st]; hz = g[5 * st];
         }
+        float tn = 0.f, tf = 0.f;
+        bool hit;
+        if (top == 0) hit = slab_exact(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, lx, ly, lz, hx, hy, hz, tn, tf);
+        else if (r.regular) hit = slab_sorted(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, r.ix < 0.f ? hx : lx, r.iy < 0.f ? hy : ly,
+                                              r.iz < 0.f ? hz : lz, r.ix < 0.f ? lx : hx, r.iy < 0.f ? ly : hy,
+                                              r.iz < 0.f ? lz : hz, tn, tf);
+        else hit = slab_enclosing(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, lx, ly, lz, hx, hy, hz);
+        hit = hit && valid;
         const unsigned m = __ballot_sync(NSVF_FULL_MASK, hit);
+        const int rank = __popc(m & ((1u << lane) - 1u));
         if (top == 0) {
-          if (MODE != kModeAnyHit && hit) {
-            const int rank = cnt + __popc(m & ((1u << lane) - 1u));
-            if (rank < n_max) { h_idx[rank] = lane; h_min[rank] = tn; h_max[rank] = tf; }
-          }
+          if (MODE != kModeAnyHit && hit && cnt + rank < n_max) { h_idx[cnt + rank] = c; h_min[cnt + rank] = tn; h_max[cnt + rank] = tf; }
           cnt += __popc(m);
           n_cur = 0;
         } else {
-          if (hit) list_a[__popc(m & ((1u << lane) - 1u))] = lane;
+          if (hit) list_a[rank] = c;
           n_cur = __popc(m);
         }
       }
       __syncwarp();
       int* cur = list_a;
       int* nxt = list_b;
-      for (int L = top - 1; L >= 0 && n_cur > 0 && cnt < limit; --L) {
-        const bool staged = tree.off[L] >= tree.stage_from;
-        const int shift = 3 * L;
-        int n_nxt = 0;
-        // (once the next list has overflowed, the remaining nodes of this level lie beyond the continuation bound)
-        for (int base = 0; base < n_cur && cnt < limit && n_nxt <= list_cap; base += 4) {
-          const int p = base + (lane >> 3);
-          const int c = (p < n_cur ? cur[p] : 0) * 8 + (lane & 7);
-          const bool valid = p < n_cur && c < tree.cnt[L] && (((long long)(c + 1)) << shift) > leaf_lo;
-          bool hit = false;
-          if (valid) {
-            if (L == 0) hit = aabb_test<true>(tree, gbox, sm_nodes, staged, tree.off[0] + c, r, tn, tf);
-            else hit = aabb_test<false>(tree, gbox, sm_nodes, staged, tree.off[L] + c, r, tn, tf);
-          }
-          const unsigned m = __ballot_sync(NSVF_FULL_MASK, hit);
-          if (m == 0u) continue;
-          const int rank = __popc(m & ((1u << lane) - 1u));
-          if (L == 0) {
-            if (MODE != kModeAnyHit && hit && c >= leaf_lo && cnt + rank < n_max) {
-              h_idx[cnt + rank] = c;
-              h_min[cnt + rank] = tn;
-              h_max[cnt + rank] = tf;
-            }
-            // (c >= leaf_lo always holds for hits here: valid already filtered on (c+1) > leaf_lo)
-            cnt += __popc(m);
-          } else {
-            if (hit) {
-              const int slot = n_nxt + rank;
-              if (slot < list_cap) nxt[slot] = c;
-              else if (slot == list_cap) next_lo = ((long long)c) << shift;   // first dropped node (ascending order)
-            }
-            const int tot = n_nxt + __popc(m);
-            if (tot > list_cap && n_nxt <= list_cap) {
-              // broadcast the continuation bound computed by the lane that owned slot == list_cap
-              const unsigned owner_mask = __ballot_sync(NSVF_FULL_MASK, hit && (n_nxt + rank) == list_cap);
-              const long long bnd = __shfl_sync(NSVF_FULL_MASK, next_lo, __ffs(owner_mask) - 1);
-              next_lo = bnd;
-            }
-            n_nxt = min(tot, list_cap + 1);
-          }
-        }
+      for (int L = top - 1; L >= 1 && n_cur > 0; --L) {
+        const int n_nxt = aabb_level_dispatch<false, MODE>(w, r, tree.off[L] >= tree.stage_from, tree.off[L], tree.cnt[L],
+                                                           3 * L, (int)(leaf_lo >> (3 * L)), cur, n_cur, nxt, cnt, limit,
+                                                           next_lo);
         __syncwarp();
-        if (L > 0) {
-          n_cur = min(n_nxt, list_cap);
-          int* t = cur; cur = nxt; nxt = t;
-        }
+        n_cur = min(n_nxt, w.list_cap);
+        int* t = cur; cur = nxt; nxt = t;
+      }
+      if (top >= 1 && n_cur > 0 && cnt < limit) {
+        aabb_level_dispatch<true, MODE>(w, r, tree.off[0] >= tree.stage_from, tree.off[0], tree.cnt[0], 0,
+                                        (int)leaf_lo, cur, n_cur, nxt, cnt, limit, next_lo);
+        __syncwarp();
       }
       // a truncated list only ever dropped nodes whose leaves come AFTER every leaf handled so far, so the
       // collected hits are exactly the first ones; continue from the first dropped leaf if more are needed
