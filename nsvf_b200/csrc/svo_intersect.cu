@@ -10,7 +10,16 @@
 //   * 1/dir is computed once per ray (reference: 3 MUFU per node visit);
 //   * the DFS stack is an uninitialised per-thread array (reference zero-fills 1 KiB per ray);
 //   * output rows are pre-filled (-1 / 0) with coalesced stores by the whole CTA, then hits are
-//     written in place (reference: 3 cudaMemsets + an uncoalesced per-thread -1 loop).
+//     written in place (reference: 3 cudaMemsets + an uncoalesced per-thread -1 loop);
+//   * TIGHT internal boxes.  The reference octree is loose (node half-extent 2^(depth+1) against a child offset of
+//     2^(depth-1): every node box is twice its true size per axis), so most visited nodes are false positives.  A leaf
+//     is emitted iff it and all its ancestors are hit; when every node box encloses its children's boxes (checked on
+//     the device for each call) the ancestor tests are implied by the leaf test (monotone rounding, common.cuh), so
+//     replacing the internal boxes by the exact union of their leaves' boxes changes neither the emitted set nor
+//     the DFS order — it only prunes subtrees without hit leaves.  Unions are built per call by one climb per leaf
+//     with float atomic min/max.  Irregular rays (NaN paths) and trees that fail the check use the loose boxes.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "nsvf_b200.h"
 
@@ -55,12 +64,91 @@ __global__ void svo_pack_kernel(const float* __restrict__ points, const int* __r
   for (int q = 0; q < 4; ++q) dst[q] = src[q];
 }
 
+// parent pointers + enclosure check of the reference's (loose) boxes; tight boxes start empty for internal nodes
+__global__ void svo_prepare_kernel(const SvoNode* __restrict__ loose, int T, SvoNode* __restrict__ tight,
+                                   int* __restrict__ parent, int* __restrict__ flag_bad) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= T) return;
+  const SvoNode* ln = loose + (long long)blockIdx.y * T;
+  SvoNode* tn = tight + (long long)blockIdx.y * T;
+  int* par = parent + (long long)blockIdx.y * T;
+  SvoNode nd = ln[k];
+  if (!nd.leaf) {
+    bool bad = false;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = nd.child[u];
+      if (c > -1) {
+        if (c >= T || c == k) { bad = true; continue; }
+        const int old = atomicCAS(par + c, -1, k);
+        if (old != -1 && old != k) bad = true;   // reachable from two parents: not a tree, keep the loose boxes
+        const SvoNode cn = ln[c];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) bad |= !(nd.lo[a] <= cn.lo[a]) || !(nd.hi[a] >= cn.hi[a]);
+      }
+    }
+    if (bad) atomicExch(flag_bad + blockIdx.y, 1);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { nd.lo[a] = INFINITY; nd.hi[a] = -INFINITY; }
+  }
+  tn[k] = nd;
+}
+
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+  if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+// every leaf climbs to the root and folds its exact box into its ancestors' unions
+__global__ void svo_climb_kernel(int T, SvoNode* __restrict__ tight, const int* __restrict__ parent,
+                                 int* __restrict__ flag_bad) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= T) return;
+  SvoNode* tn = tight + (long long)blockIdx.y * T;
+  const int* par = parent + (long long)blockIdx.y * T;
+  if (!tn[k].leaf) return;
+  float lo[3], hi[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { lo[a] = tn[k].lo[a] + 0.0f; hi[a] = tn[k].hi[a] + 0.0f; }   // +0: canonical zero
+  int p = par[k], steps = 0;
+  while (p >= 0) {
+    if (++steps > 64) { atomicExch(flag_bad + blockIdx.y, 1); break; }   // cycle or absurd depth
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      atomic_min_float(&tn[p].lo[a], lo[a]);
+      atomic_max_float(&tn[p].hi[a], hi[a]);
+    }
+    p = par[p];
+  }
+}
+
+// widen the unions by one ulp (strict enclosure); internal nodes without any leaf can never be hit
+__global__ void svo_finish_kernel(int T, SvoNode* __restrict__ tight) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= T) return;
+  SvoNode* nd = tight + (long long)blockIdx.y * T + k;
+  if (nd->leaf) return;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float l = nd->lo[a], h = nd->hi[a];
+    if (l <= h) { nd->lo[a] = nextafterf(l, -INFINITY); nd->hi[a] = nextafterf(h, INFINITY); }
+    else { nd->lo[a] = 3.0e38f; nd->hi[a] = 3.0e38f; }
+  }
+}
+
 __global__ void __launch_bounds__(kSvoThreads)
-svo_intersect_kernel(const SvoNode* __restrict__ nodes_all, int T, long long rays_per_tree, int n_max,
+svo_intersect_kernel(const SvoNode* __restrict__ nodes_all, const SvoNode* __restrict__ tight_all,
+                     const int* __restrict__ flag_bad, int T, long long rays_per_tree, int n_max,
                      const float* __restrict__ ray_start, const float* __restrict__ ray_dir,
                      int* __restrict__ out_idx, float* __restrict__ out_min, float* __restrict__ out_max,
                      int* __restrict__ overflow_flag) {
-  const SvoNode* nodes = nodes_all + (long long)blockIdx.y * T;
+  const SvoNode* loose = nodes_all + (long long)blockIdx.y * T;
+  const bool use_tight = tight_all != nullptr && flag_bad[blockIdx.y] == 0;
+  const SvoNode* tight = use_tight ? tight_all + (long long)blockIdx.y * T : loose;
   const long long ray_base = (long long)blockIdx.y * rays_per_tree;
 
   for (long long tile = (long long)blockIdx.x * kSvoThreads; tile < rays_per_tree;
@@ -84,6 +172,7 @@ svo_intersect_kernel(const SvoNode* __restrict__ nodes_all, int T, long long ray
       const float ix = ref_rcp(ray_dir[ray * 3 + 0]), iy = ref_rcp(ray_dir[ray * 3 + 1]),
                   iz = ref_rcp(ray_dir[ray * 3 + 2]);
       const bool regular = regular_component(ox, ix) && regular_component(oy, iy) && regular_component(oz, iz);
+      const SvoNode* nodes = regular ? tight : loose;   // NaN paths keep the reference's own boxes
       const long long row = ray * n_max;
       int stack[kSvoStack];
       int ptr = 0, cnt = 0;
@@ -140,7 +229,9 @@ using namespace nsvf;
 
 extern "C" size_t nsvf_svo_workspace_bytes(int T, int n_trees) {
   if (T <= 0 || n_trees <= 0) return 0;
-  return (size_t)T * n_trees * sizeof(SvoNode) + 128;  // + overflow flag
+  // [flags 128 B + n_trees ints][loose nodes][tight nodes][parent]
+  const size_t flags = 128 + ((size_t)n_trees * 4 + 127) / 128 * 128;
+  return flags + (size_t)T * n_trees * (2 * sizeof(SvoNode) + sizeof(int)) + 256;
 }
 
 extern "C" int nsvf_svo_intersect(nsvf_stream_t stream_, int b, int T, int m, float voxelsize, int n_max,
@@ -159,14 +250,25 @@ extern "C" int nsvf_svo_intersect(nsvf_stream_t stream_, int b, int T, int m, fl
   NSVF_REQUIRE(workspace != nullptr && workspace_bytes >= need, "svo_intersect: workspace too small (%zu < %zu bytes)",
                workspace_bytes, need);
   NSVF_REQUIRE(((uintptr_t)workspace & 127) == 0, "svo_intersect: workspace must be 128-byte aligned");
-  int* flag = (int*)workspace;
-  SvoNode* nodes = (SvoNode*)((char*)workspace + 128);
-  NSVF_CUDA_OK(cudaMemsetAsync(flag, 0, 128, stream));
+  const size_t flag_bytes = 128 + ((size_t)n_trees * 4 + 127) / 128 * 128;
+  int* flag = (int*)workspace;                     // [0] = stack overflow, [32..] = per-tree "not enclosing"
+  int* flag_bad = flag + 32;
+  SvoNode* nodes = (SvoNode*)((char*)workspace + flag_bytes);
+  SvoNode* tight = nodes + (size_t)T * n_trees;
+  int* parent = (int*)(tight + (size_t)T * n_trees);
+  NSVF_CUDA_OK(cudaMemsetAsync(flag, 0, flag_bytes, stream));
+  NSVF_CUDA_OK(cudaMemsetAsync(parent, 0xff, sizeof(int) * (size_t)T * n_trees, stream));
   const float half_voxel = voxelsize * 0.5f;
   {
     dim3 grid((T + 255) / 256, n_trees);
     svo_pack_kernel<<<grid, 256, 0, stream>>>(points, children, tree_batch_stride_nodes, T, half_voxel, nodes);
     NSVF_LAUNCH_OK("svo_pack_kernel");
+    svo_prepare_kernel<<<grid, 256, 0, stream>>>(nodes, T, tight, parent, flag_bad);
+    NSVF_LAUNCH_OK("svo_prepare_kernel");
+    svo_climb_kernel<<<grid, 256, 0, stream>>>(T, tight, parent, flag_bad);
+    NSVF_LAUNCH_OK("svo_climb_kernel");
+    svo_finish_kernel<<<grid, 256, 0, stream>>>(T, tight);
+    NSVF_LAUNCH_OK("svo_finish_kernel");
   }
   const long long rays_per_tree = n_trees == 1 ? rays : m;
   long long want = (rays_per_tree + kSvoThreads - 1) / kSvoThreads;
@@ -175,7 +277,8 @@ extern "C" int nsvf_svo_intersect(nsvf_stream_t stream_, int b, int T, int m, fl
   int gx = (int)(want < cap ? want : cap);
   if (gx < 1) gx = 1;
   dim3 grid(gx, n_trees);
-  NSVF_TIMED_LAUNCH("svo_intersect_kernel", stream, (svo_intersect_kernel<<<grid, kSvoThreads, 0, stream>>>(nodes, T, rays_per_tree, n_max, ray_start, ray_dir, idx,
-                                                         min_depth, max_depth, flag)));
+  NSVF_TIMED_LAUNCH("svo_intersect_kernel", stream, (svo_intersect_kernel<<<grid, kSvoThreads, 0, stream>>>(
+                        nodes, getenv("NSVF_SVO_LOOSE") ? nullptr : tight, flag_bad, T, rays_per_tree, n_max, ray_start,
+                        ray_dir, idx, min_depth, max_depth, flag)));
   return 0;
 }

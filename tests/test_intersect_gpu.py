@@ -248,3 +248,22 @@ def test_encoder_octree_ray_intersect_matches_reference_pipeline(cuda, ref_ext):
     clean = ~ties.any(-1)
     assert torch.equal(inter["intersected_voxel_idx"][clean], r_idx[clean])
     assert torch.equal(inter["max_depth"][clean], r_max[clean]) and int(hits.sum()) > 1000
+
+
+def test_svo_non_enclosing_tree_falls_back_to_reference_boxes(cuda, ref_ext):
+    """The tight-box shortcut is only valid when every node box encloses its children's boxes; a tree that violates
+    this (here: internal centres displaced, size markers shrunk) must still reproduce the reference traversal."""
+    pts0 = synthetic.carve_shell(synthetic.bbox_voxels([-2.4] * 3, [2.4] * 3, 0.4))
+    pts, centers, children = _svo_inputs(pts0, 0.4, cuda)
+    n = pts.shape[0]
+    bad_c, bad_ch = centers.clone(), children.clone()
+    internal = torch.arange(n, centers.shape[0] - 1, device=cuda)
+    bad_c[internal[::3]] += 0.35                       # displaced boxes: some leaves fall outside their ancestors
+    bad_ch[internal[1::5], 8] = torch.clamp(bad_ch[internal[1::5], 8] // 4, min=2)   # shrunken boxes
+    rs, rd = synthetic.camera_rays(48, 48, 1, device=cuda)
+    rs = rs.expand_as(rd).contiguous()
+    mine = ours.svo_intersect(rs, rd, bad_c[None].contiguous(), bad_ch[None].contiguous(), 0.4, 60)
+    ref = ref_ext.svo_intersect(rs, rd, bad_c[None].contiguous(), bad_ch[None].contiguous(), 0.4, 60)
+    _cmp3(mine, ref, "svo on a non-enclosing tree")
+    good = ours.svo_intersect(rs, rd, centers[None].contiguous(), children[None].contiguous(), 0.4, 60)
+    assert not torch.equal(good[0], mine[0])           # the malformed tree really changes the answer
