@@ -23,6 +23,14 @@ P = scene.max_hits
 for rep in range(2):
     if not which or "aabb" in which:
         idx, dmin, dmax = _ext.aabb_intersect(rs, rd, pts, scene.voxel_size, P, shared_points=True)
+    if not which or "aabb" in which:
+        _ext.aabb_intersect_sorted(rs, rd, pts, scene.voxel_size, P, 1e4, shared_points=True)
+        _ext.aabb_hit_mask(rs, rd, pts, scene.voxel_size, shared_points=True)
+from nsvf_b200 import geometry
+centers, children = geometry.build_easy_octree(torch.from_numpy(scene.points).to(dev), scene.voxel_size / 2.0)
+for rep in range(2):
+    if not which or "svo" in which:
+        _ext.svo_intersect(rs, rd, centers.contiguous(), children.contiguous(), scene.voxel_size, P, shared_tree=True)
 torch.cuda.synchronize()
 idx, dmin, dmax = _ext.aabb_intersect(rs, rd, pts, scene.voxel_size, P, shared_points=True)
 idx, dmin, dmax, hits = wrappers.sort_hits(idx[0], dmin[0], dmax[0])
