@@ -220,6 +220,24 @@ NSVF_API int nsvf_prune_lattice_embed(nsvf_stream_t stream, int nv, int v0, int 
 NSVF_API int nsvf_prune_keep(nsvf_stream_t stream, int nv, int L, const float* sigma, float th, unsigned char* keep,
                              float* min_score);
 
+/* ---- per-frame post-processing ------------------------------------------------------------------------------
+ * nsvf_fill_in_blend: replaces fill_in (fairnr/data/geometry.py:303-317) for colors / missed / depths and the
+ * background blend of NSVFModel.postprocessing (fairnr/models/nsvf.py:89-104).
+ *   hits u8 [N]; rank_incl i64 [N] = inclusive prefix sum of hits (row of the hit ray in the compacted results);
+ *   colors f32 [M,3], missed f32 [M], depths f32 [M] (M = number of hit rays); bg_color f32 [3] (device)
+ *   -> out_colors [N,3] = colors_full + missed_full * bg_color, out_missed [N] (1 where not hit),
+ *      out_depths [N] = depths_full + missed_full * bg_depth
+ * nsvf_track_voxel_probs: replaces SparseVoxelEncoder.track_voxel_probs (fairnr/modules/encoder.py:594-603):
+ *   max_probs f32 [n_vox] (>= 0, updated in place) = max(max_probs, per-ray sums of probs per voxel).
+ *   Precondition (true for ray-marched samples: they are depth-ordered and voxels are convex): the samples a ray
+ *   has in one voxel are consecutive; the reference's scatter_add would also merge non-consecutive repeats. */
+NSVF_API int nsvf_fill_in_blend(nsvf_stream_t stream, long long N, const unsigned char* hits,
+                                const long long* rank_incl, const float* colors, const float* missed,
+                                const float* depths, const float* bg_color, float bg_depth, float* out_colors,
+                                float* out_missed, float* out_depths);
+NSVF_API int nsvf_track_voxel_probs(nsvf_stream_t stream, long long B, int K, const int* sampled_idx,
+                                    const float* probs, int n_vox, float* max_probs);
+
 #ifdef __cplusplus
 }
 #endif

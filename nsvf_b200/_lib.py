@@ -51,6 +51,9 @@ SIGNATURES = {
                                          c_void_p]),
     "nsvf_prune_keep": (c_int, [c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p]),
     "nsvf_masked_col_counts": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "nsvf_fill_in_blend": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                   c_void_p, c_void_p, c_void_p]),
+    "nsvf_track_voxel_probs": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "nsvf_compact_count": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "nsvf_compact_fill": (c_int, [c_void_p, c_ll, c_int, c_int, c_int] + [c_void_p] * 12),
 }

@@ -195,18 +195,12 @@ class SparseVoxelEncoder(nn.Module):
 
     @torch.no_grad()
     def track_voxel_probs(self, voxel_idxs, voxel_probs):
-        """Per-voxel running max of sample probabilities (encoder.py:594-603) without the [4096, n+1] scatter."""
-        n = self.max_voxel_probs.size(0)
-        valid = voxel_idxs.ne(-1)
-        # the reference sums the probabilities a ray deposits in the same voxel before taking the max
-        B, K = voxel_idxs.shape
-        ray = torch.arange(B, device=voxel_idxs.device)[:, None].expand(B, K)[valid]
-        key = ray * n + voxel_idxs[valid].long()
-        uniq, inv = torch.unique(key, return_inverse=True)
-        summed = torch.zeros(uniq.numel(), device=voxel_probs.device, dtype=voxel_probs.dtype).scatter_add_(
-            0, inv, voxel_probs[valid])
-        cur = torch.zeros_like(self.max_voxel_probs).scatter_reduce_(0, uniq % n, summed, reduce="amax")
-        self.max_voxel_probs = torch.max(self.max_voxel_probs, cur)
+        """Per-voxel running max of the probability mass a ray deposits in the voxel (encoder.py:594-603); one
+        kernel instead of a [4096, n+1] scatter_add buffer per 4096-ray chunk."""
+        mvp = self.max_voxel_probs
+        if mvp.dtype != torch.float32 or not mvp.is_contiguous():
+            mvp = mvp.float().contiguous()
+        self.max_voxel_probs = ops.track_voxel_probs(mvp, voxel_idxs, voxel_probs)
 
     @torch.no_grad()
     def pruning(self, field_fn, th=0.5, encoder_states=None, train_stats=False, voxel_shard=None):

@@ -117,3 +117,57 @@ class Composite(Function):
 def composite(free_energy, texture, sampled_depth):
     """(probs[B,K], depth[B], missed[B], colors[B,3]) from free energy, rgb and sample depths."""
     return Composite.apply(free_energy, texture, sampled_depth)
+
+
+class FillInBlend(Function):
+    """fill_in x3 + background blend (geometry.py:303-317, nsvf.py:89-104) as one kernel; differentiable w.r.t. the
+    compacted colors / missed / depths (the background colour is a constant, `--background-stop-gradient`)."""
+
+    @staticmethod
+    def forward(ctx, hits, colors, missed, depths, bg_color, bg_depth):
+        _need_cuda(hits=hits, colors=colors, missed=missed, depths=depths)
+        dev = colors.device
+        N = hits.numel()
+        h8 = hits.reshape(-1).to(torch.uint8).contiguous()
+        rank = torch.cumsum(h8, 0, dtype=torch.int64)
+        bg = torch.as_tensor(bg_color, dtype=torch.float32, device=dev).detach().reshape(3).contiguous()
+        out_c = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        out_m = torch.empty(N, dtype=torch.float32, device=dev)
+        out_d = torch.empty(N, dtype=torch.float32, device=dev)
+        c, m, d = colors.detach().float().contiguous(), missed.detach().float().contiguous(), depths.detach().float().contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(_L.nsvf_fill_in_blend(_lib.current_stream(dev), N, _p(h8), _p(rank), _p(c), _p(m), _p(d), _p(bg),
+                                             float(bg_depth), _p(out_c), _p(out_m), _p(out_d)))
+        ctx.save_for_backward(h8, bg)
+        ctx.bg_depth = float(bg_depth)
+        return out_c, out_m, out_d
+
+    @staticmethod
+    def backward(ctx, g_c, g_m, g_d):
+        h8, bg = ctx.saved_tensors
+        where = h8.bool()
+        gc = g_c[where] if g_c is not None else None
+        gd = g_d[where] if g_d is not None else None
+        gm = g_m[where] if g_m is not None else torch.zeros(int(where.sum()), device=h8.device)
+        if gc is not None:
+            gm = gm + (gc * bg).sum(-1)
+        if gd is not None:
+            gm = gm + gd * ctx.bg_depth
+        return None, gc, gm, gd, None, None
+
+
+def fill_in_blend(hits, colors, missed, depths, bg_color, bg_depth):
+    """(colors [N,3], missed [N], depths [N]) for all N rays from the results of the hit rays."""
+    return FillInBlend.apply(hits, colors, missed, depths, bg_color, bg_depth)
+
+
+@torch.no_grad()
+def track_voxel_probs(max_voxel_probs, voxel_idxs, voxel_probs):
+    """In-place max_voxel_probs = max(max_voxel_probs, per-ray sums of voxel_probs per voxel) (encoder.py:594-603)."""
+    idx = voxel_idxs.int().contiguous()
+    pr = voxel_probs.detach().float().contiguous()
+    B, K = idx.shape
+    with torch.cuda.device(idx.device):
+        _lib.check(_L.nsvf_track_voxel_probs(_lib.current_stream(idx.device), B, K, _p(idx), _p(pr),
+                                             max_voxel_probs.numel(), _p(max_voxel_probs)))
+    return max_voxel_probs

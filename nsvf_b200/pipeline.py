@@ -74,24 +74,21 @@ class NSVFPipeline(nn.Module):
         rs, rd = ray_start.reshape(-1, 3)[hits_flat], ray_dir.reshape(-1, 3)[hits_flat]
         encoder_states = {k: v.reshape(-1, v.size(-1)) for k, v in encoder_states.items()}
         dev = ray_dir.device
-        colors = torch.zeros(n_rays, 3, device=dev)
-        missed = torch.ones(n_rays, device=dev)
-        depths = torch.zeros(n_rays, device=dev)
         results = {"ae": 0}
+        bg = self.field.bg_color if hasattr(self.field, "bg_color") else torch.ones(3, device=dev)
         if rs.size(0) > 0:
             samples = self.encoder.ray_sample(inter)
             r = self.raymarcher(self.encoder, self.field, rs, rd, samples, encoder_states)
-            # fill_in (geometry.py:303-317) + background blend (nsvf.py:89-104)
-            where = hits_flat.nonzero(as_tuple=True)[0]
-            colors = colors.index_put((where,), r["colors"])
-            missed = missed.index_put((where,), r["missed"])
-            depths = depths.index_put((where,), r["depths"])
             results["ae"] = r["ae"]
             results["samples"] = samples
-        bg = self.field.bg_color if hasattr(self.field, "bg_color") else torch.ones(3, device=dev)
-        results["colors"] = colors + missed.unsqueeze(-1) * bg
-        results["depths"] = depths + missed * self.bg_depth
-        results["missed"] = missed
+            colors, missed, depths = r["colors"], r["missed"], r["depths"]
+        else:
+            colors, missed, depths = (torch.zeros(0, 3, device=dev), torch.zeros(0, device=dev),
+                                      torch.zeros(0, device=dev))
+        # fill_in (geometry.py:303-317) + background blend (nsvf.py:89-104), one kernel
+        from . import ops
+        results["colors"], results["missed"], results["depths"] = ops.fill_in_blend(
+            hits_flat, colors, missed, depths, bg, self.bg_depth)
         results["hits"] = hits_flat
         results["sampled"] = sampled
         return results

@@ -159,3 +159,47 @@ def composite_torch(free_energy, texture, sampled_depth):
     missed = 1 - probs.sum(-1)
     colors = (texture * probs.unsqueeze(-1)).sum(-2)
     return probs, depth, missed, colors
+
+
+def fill_in_blend_torch(hits, colors, missed, depths, bg_color, bg_depth):
+    """fill_in (fairnr/data/geometry.py:303-317) for missed / colors / depths + the background blend of
+    NSVFModel.postprocessing (fairnr/models/nsvf.py:93-104), plain torch."""
+    n = hits.numel()
+    full_m = missed.new_ones(n).masked_scatter(hits, missed)
+    full_c = colors.new_zeros(n, 3).masked_scatter(hits.unsqueeze(-1).expand(n, 3), colors)
+    full_d = depths.new_zeros(n).masked_scatter(hits, depths)
+    full_c = full_c + full_m.unsqueeze(-1) * bg_color.reshape(1, 3)
+    full_d = full_d + full_m * bg_depth
+    return full_c, full_m, full_d
+
+
+def track_voxel_probs_torch(max_voxel_probs, voxel_idxs, voxel_probs):
+    """SparseVoxelEncoder.track_voxel_probs, fairnr/modules/encoder.py:594-603, plain torch."""
+    n = max_voxel_probs.size(0)
+    voxel_idxs = voxel_idxs.masked_fill(voxel_idxs.eq(-1), n)
+    for start in range(0, voxel_idxs.size(0), 4096):
+        end = min(start + 4096, voxel_idxs.size(0))
+        cur = max_voxel_probs.new_zeros(end - start, n + 1).scatter_add_(
+            dim=-1, index=voxel_idxs[start:end], src=voxel_probs[start:end]).max(0)[0][:-1]
+        max_voxel_probs = torch.max(max_voxel_probs, cur)
+    return max_voxel_probs
+
+
+def uniform_ray_sampling(ext, pts_idx, min_depth, max_depth, step_size, max_ray_length, deterministic=False, noise=None):
+    """UniformRaySampling.forward, clib/__init__.py:178-228 (wrap-padding to a multiple of 256 rows)."""
+    G, N, P = 256, pts_idx.size(0), pts_idx.size(1)
+    H = int(np.ceil(N / G)) * G
+    if H > N:
+        pts_idx = torch.cat([pts_idx, pts_idx[:H - N]], 0)
+        min_depth = torch.cat([min_depth, min_depth[:H - N]], 0)
+        max_depth = torch.cat([max_depth, max_depth[:H - N]], 0)
+    pts_idx, min_depth, max_depth = [t.reshape(G, -1, P) for t in (pts_idx, min_depth, max_depth)]
+    max_steps = int(max_ray_length / step_size) + P * 2
+    if noise is None:
+        noise = min_depth.new_zeros(*min_depth.size()[:-1], max_steps)
+        noise = noise + 0.5 if deterministic else noise.uniform_()
+    sidx, sdepth, sdists = ext.uniform_ray_sampling(pts_idx.contiguous(), min_depth.float().contiguous(),
+                                                    max_depth.float().contiguous(), noise.float(), step_size, max_steps)
+    sidx, sdepth, sdists = [t.reshape(H, -1)[:N] for t in (sidx, sdepth, sdists)]
+    max_len = int(sidx.ne(-1).sum(-1).max())
+    return sidx[:, :max_len], sdepth[:, :max_len], sdists[:, :max_len]

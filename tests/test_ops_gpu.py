@@ -119,3 +119,40 @@ def test_composite_known_answer(cuda):
     assert float((missed - float(np.exp(-x * K))).abs().max()) < 5e-7     # eps(1.0) level, as in the reference
     helpers.assert_close_scaled(colors, (1 - missed)[:, None].expand(B, 3), what="KAT-4 colors")
     assert ops.composite(fe[:0], tex[:0], depth[:0])[0].shape == (0, K)
+
+
+def test_fill_in_blend_and_track_voxel_probs(cuda):
+    """Per-frame post-processing kernels against the plain-torch statement of the reference code."""
+    g = torch.Generator(device="cpu").manual_seed(3)
+    N = 10007
+    hits = (torch.rand(N, generator=g) < 0.6).to(cuda)
+    M = int(hits.sum())
+    colors = (torch.rand(M, 3, generator=g) * 2 - 1).to(cuda).requires_grad_(True)
+    missed = torch.rand(M, generator=g).to(cuda).requires_grad_(True)
+    depths = (torch.rand(M, generator=g) * 4).to(cuda).requires_grad_(True)
+    bg = torch.tensor([1.0, 0.5, -1.0], device=cuda)
+    mine = ops.fill_in_blend(hits, colors, missed, depths, bg, 5.0)
+    c2, m2, d2 = [t.detach().clone().requires_grad_(True) for t in (colors, missed, depths)]
+    ref = wrappers.fill_in_blend_torch(hits, c2, m2, d2, bg, 5.0)
+    for a, b in zip(mine, ref):
+        assert torch.equal(a, b)                       # same mul-then-add per element: bit-identical
+    gs = [torch.randn_like(t) for t in mine]
+    torch.autograd.backward(mine, gs)
+    torch.autograd.backward(ref, gs)
+    for a, b in ((colors, c2), (missed, m2), (depths, d2)):
+        torch.testing.assert_close(a.grad, b.grad, rtol=1e-6, atol=1e-6)
+    empty = ops.fill_in_blend(torch.zeros(5, dtype=torch.bool, device=cuda), colors[:0], missed[:0], depths[:0], bg, 5.0)
+    assert torch.equal(empty[0], bg.expand(5, 3)) and torch.equal(empty[1], torch.ones(5, device=cuda))
+
+    scene = synthetic.make_scene("C1")
+    B, K = 3000, 90
+    # a ray meets a (convex) voxel once: its samples in that voxel are consecutive, voxels do not repeat along a ray
+    runs = torch.stack([torch.randperm(scene.n, generator=g)[: K // 6] for _ in range(B)]).repeat_interleave(6, dim=1)
+    valid = torch.arange(K)[None] < torch.randint(0, K + 1, (B, 1), generator=g)
+    idx = torch.where(valid, runs, torch.full_like(runs, -1)).int().to(cuda)
+    probs = (torch.rand(B, K, generator=g) * 0.05 * valid).to(cuda)
+    start = torch.rand(scene.n, generator=g).to(cuda) * 0.05
+    mine_p = ops.track_voxel_probs(start.clone(), idx, probs)
+    ref_p = wrappers.track_voxel_probs_torch(start.clone(), idx.long(), probs)
+    helpers.assert_close_scaled(mine_p, ref_p, what="max voxel probs")
+    assert bool((mine_p >= start).all()) and bool((mine_p > start).any())

@@ -118,8 +118,15 @@ def test_uniform_level1_vs_reference_and_oracle(cuda, ref_ext, name, n_rays):
     assert int(valid.sum(-1).max()) > 20
 
 
-def test_uniform_level2_wrapper_runs(cuda):
-    scene, idx, dmin, dmax, _, _ = _pipeline(cuda, "C1", 1000, 2)
-    sidx, sdepth, sdist = clib.uniform_ray_sampling(idx, dmin, dmax, scene.step_size, 3.0, True)
-    assert sidx.shape[0] == idx.shape[0] and sidx.shape == sdepth.shape == sdist.shape
-    assert int((sidx != -1).sum(-1).max()) == sidx.shape[1]
+def test_uniform_level2_wrapper_matches_reference_wrapper(cuda, ref_ext):
+    """fairnr.clib.uniform_ray_sampling end to end (wrap padding to 256 block rows, same noise draw, trimming)."""
+    for n_rays, det in ((1000, True), (1500, False)):
+        scene, idx, dmin, dmax, _, _ = _pipeline(cuda, "C1", n_rays, 2)
+        torch.manual_seed(9)
+        sidx, sdepth, sdist = clib.uniform_ray_sampling(idx, dmin, dmax, scene.step_size, 3.0, det)
+        torch.manual_seed(9)
+        r_idx, r_depth, r_dist = wrappers.uniform_ray_sampling(ref_ext, idx, dmin, dmax, scene.step_size, 3.0, det)
+        assert sidx.shape[0] == idx.shape[0] and torch.equal(sidx, r_idx)
+        valid = sidx != -1
+        assert torch.equal(sdepth[valid], r_depth[valid]) and torch.equal(sdist[valid], r_dist[valid])
+        assert int(valid.sum(-1).max()) == sidx.shape[1]
