@@ -277,7 +277,8 @@ def run_ours(args):
             line["frame"] = {"error": repr(e)[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            line["cpu_baseline"] = cpu_arm(steps=2, warmup=1, fraction=args.cpu_fraction)["cpu_baseline"]
+            # bounded sample: ~10-20 s of host-core work (8 steps of 1/4 of the rays each)
+            line["cpu_baseline"] = cpu_arm(steps=8, warmup=1, fraction=max(args.cpu_fraction // 4, 1))["cpu_baseline"]
         except Exception as e:
             line["cpu_baseline"] = {"error": repr(e)[:200]}
     if world > 1:
