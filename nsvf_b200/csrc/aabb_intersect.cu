@@ -596,12 +596,8 @@ static int aabb_launch(cudaStream_t stream, dim3 grid, size_t smem, const AabbTr
                        long long rays_per_tree, int n_max, int sort_slots, int list_cap, float empty_depth,
                        const float* ray_start, const float* ray_dir, int* idx, float* dmin, float* dmax,
                        unsigned char* hit) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    NSVF_CUDA_OK(cudaFuncSetAttribute(aabb_intersect_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      200 * 1024));
-    attr_set = true;
-  }
+  NSVF_CUDA_OK(cudaFuncSetAttribute(aabb_intersect_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    200 * 1024));
   const char* kname = MODE == kModeAnyHit ? "aabb_hit_mask_kernel"
                       : (MODE == kModeDepthSorted ? "aabb_intersect_sorted_kernel" : "aabb_intersect_kernel");
   NSVF_TIMED_LAUNCH(kname, stream,
@@ -760,11 +756,7 @@ extern "C" int nsvf_sort_hits_by_depth(nsvf_stream_t stream_, long long rays, in
   while (sort_slots < n_max) sort_slots <<= 1;
   const size_t smem = (size_t)kAabbWarps * (3 * n_max + sort_slots) * sizeof(float);
   NSVF_REQUIRE(smem <= 200 * 1024, "sort_hits_by_depth: n_max=%d needs %zu B of shared memory", n_max, smem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NSVF_CUDA_OK(cudaFuncSetAttribute(sort_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  NSVF_CUDA_OK(cudaFuncSetAttribute(sort_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   long long want = (rays + kAabbWarps - 1) / kAabbWarps, cap = (long long)num_sms() * 6;
   sort_hits_kernel<<<(unsigned)(want < cap ? want : cap), kAabbWarps * 32, smem, stream>>>(rays, n_max, sort_slots,
                                                                                        empty_depth, idx, min_depth,

@@ -192,11 +192,7 @@ extern "C" int nsvf_composite_bwd(nsvf_stream_t stream_, long long B, int K, con
   if (B == 0 || K == 0) return 0;
   const size_t smem = (size_t)kCompWarps * 2 * K * sizeof(float);
   NSVF_REQUIRE(smem <= 200 * 1024, "composite_bwd: K=%d too large for the shared-memory stash (%zu B)", K, smem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NSVF_CUDA_OK(cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  NSVF_CUDA_OK(cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   long long want = (B + kCompWarps - 1) / kCompWarps;
   int per_sm = (int)((220 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);

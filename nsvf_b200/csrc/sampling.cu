@@ -140,7 +140,7 @@ inverse_cdf_sampling_kernel(int b, int num_rays, long long valid_rays, int ray_c
       const float sj = steps[ray];
       st.step_size = __fdiv_rn(1.0f, sj);  // 1.0 / steps[j] in double then rounded: same value
       st.z_low = st.curr_min_depth;
-      st.total_steps = (int)ceilf(sj);
+      st.total_steps = min((int)ceilf(sj), max_steps);
       if (fixed_step_size > 0.0f) st.step_size = fixed_step_size;
       st.curr_cdf = 0.0f;
       st.phase = 0;
@@ -305,7 +305,8 @@ inverse_cdf_warp_kernel(int b, int num_rays, long long valid_rays, int ray_chunk
     const float sj = steps[ray];
     float step_size = __fdiv_rn(1.0f, sj);
     if (fixed_step_size > 0.0f) step_size = fixed_step_size;
-    const int total_steps = (int)ceilf(sj);
+    // steps beyond max_steps could only produce samples at slots >= max_steps, which are dropped anyway
+    const int total_steps = min((int)ceilf(sj), max_steps);
     int s_end = 0, n_valid = 0;
 
     if (!ok) {
@@ -541,12 +542,8 @@ extern "C" int nsvf_inverse_cdf_sampling(nsvf_stream_t stream_, int b, int num_r
   {  // warp-per-ray kernel whenever its per-warp bin tables fit in shared memory
     const size_t smem = (size_t)kCdfWarps * 6 * max_hits * sizeof(float);
     if (smem <= 160 * 1024 && getenv("NSVF_SAMPLER_LANE") == nullptr) {
-      static bool attr_set = false;
-      if (!attr_set) {
-        NSVF_CUDA_OK(cudaFuncSetAttribute(inverse_cdf_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      NSVF_CUDA_OK(cudaFuncSetAttribute(inverse_cdf_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           160 * 1024));
-        attr_set = true;
-      }
       int per_sm = (int)((200 * 1024) / (smem + 1024));
       per_sm = per_sm < 1 ? 1 : (per_sm > 12 ? 12 : per_sm);
       long long want = (valid_rays + kCdfWarps - 1) / kCdfWarps, cap = (long long)num_sms() * per_sm;

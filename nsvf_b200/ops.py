@@ -46,7 +46,6 @@ class TrilinearEmbed(Function):
         ctx.save_for_backward(idx, xyz, feats32, centres, vals)
         ctx.voxel_size = voxel_size
         ctx.values_shape = values.shape
-        ctx.mark_non_differentiable()
         return out.to(values.dtype)
 
     @staticmethod
