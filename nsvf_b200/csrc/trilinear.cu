@@ -425,10 +425,21 @@ extern "C" int nsvf_trilinear_embed_fwd(nsvf_stream_t stream_, long long M, int 
     NSVF_REQUIRE((((uintptr_t)values | (uintptr_t)out | (uintptr_t)feats) & 15) == 0,
                  "trilinear_embed_fwd: values/out/feats must be 16-byte aligned");
     NSVF_REQUIRE(((uintptr_t)values & 15) == 0, "trilinear_embed_fwd: values must be 16-byte aligned");
+    static int bps = getenv("NSVF_TRI_BPS") ? atoi(getenv("NSVF_TRI_BPS")) : 24;
     switch (tri_variant() == 0 ? 2 : tri_variant()) {
+      case 5:
+        NSVF_TIMED_LAUNCH("trilinear_fwd_kernel", stream,
+                          (trilinear_fwd_d32_v2_kernel<2, 8><<<grid_for((M + 63) / 64, 8, bps), 256, 0, stream>>>(
+                              M, sampled_idx, sampled_xyz, feats, centres, values, voxel_size, out)));
+        break;
+      case 6:
+        NSVF_TIMED_LAUNCH("trilinear_fwd_kernel", stream,
+                          (trilinear_fwd_d32_v2_kernel<2, 2><<<grid_for((M + 63) / 64, 2, bps), 64, 0, stream>>>(
+                              M, sampled_idx, sampled_xyz, feats, centres, values, voxel_size, out)));
+        break;
       case 2:
         NSVF_TIMED_LAUNCH("trilinear_fwd_kernel", stream,
-                          (trilinear_fwd_d32_v2_kernel<2, 4><<<grid_for((M + 63) / 64, 4, 12), 128, 0, stream>>>(
+                          (trilinear_fwd_d32_v2_kernel<2, 4><<<grid_for((M + 63) / 64, 4, bps), 128, 0, stream>>>(
                               M, sampled_idx, sampled_xyz, feats, centres, values, voxel_size, out)));
         break;
       case 4:
