@@ -22,11 +22,33 @@ def sampling_without_replacement(logp, k):
 
 
 class NSVFPipeline(nn.Module):
-    def __init__(self, encoder, field, renderer, pixel_per_view=0, bg_depth=5.0):
+    def __init__(self, encoder, field, renderer, pixel_per_view=0, bg_depth=5.0, hierarchical_sampling=False,
+                 fixed_fine_num_samples=0, fine_num_sample_ratio=0.0, field_fine=None):
         super().__init__()
         self.encoder, self.field, self.raymarcher = encoder, field, renderer
+        self.field_fine = field_fine
         self.pixel_per_view = pixel_per_view
         self.bg_depth = bg_depth
+        self.hierarchical = hierarchical_sampling
+        self.fixed_fine_num_samples = fixed_fine_num_samples
+        self.fine_num_sample_ratio = fine_num_sample_ratio
+
+    def prepare_hierarchical_sampling(self, inter, samples, results):
+        """Bins of the fine pass = the coarse samples (nerf.py:64-79, nsvf.py:83-87)."""
+        depth, dists = samples["sampled_point_depth"], samples["sampled_point_distance"]
+        out = dict(inter)
+        out["min_depth"] = depth - dists * .5
+        out["max_depth"] = depth + dists * .5
+        out["intersected_voxel_idx"] = samples["sampled_point_voxel_idx"].contiguous()
+        safe_probs = results["probs"].detach() + 1e-5
+        out["probs"] = safe_probs / safe_probs.sum(-1, keepdim=True)
+        steps = safe_probs.new_ones(*safe_probs.size()[:-1])
+        if self.fixed_fine_num_samples > 0:
+            steps = steps * self.fixed_fine_num_samples
+        if self.fine_num_sample_ratio > 0:
+            steps = samples["sampled_point_voxel_idx"].ne(-1).sum(-1).float() * self.fine_num_sample_ratio
+        out["steps"] = steps
+        return out
 
     def intersecting(self, ray_start, ray_dir, encoder_states):
         S, V, P, _ = ray_dir.size()
@@ -79,6 +101,14 @@ class NSVFPipeline(nn.Module):
         if rs.size(0) > 0:
             samples = self.encoder.ray_sample(inter)
             r = self.raymarcher(self.encoder, self.field, rs, rd, samples, encoder_states)
+            if self.hierarchical:      # second, importance-sampled pass (fairnr_model.py:167-173)
+                results["coarse"] = {k: r[k] for k in ("colors", "missed", "depths", "probs")}
+                inter = self.prepare_hierarchical_sampling(inter, samples, r)
+                samples = self.encoder.ray_sample(inter)
+                field = self.field_fine if self.field_fine is not None else self.field
+                r2 = self.raymarcher(self.encoder, field, rs, rd, samples, encoder_states)
+                r2["ae"] = r2["ae"] + r["ae"]
+                r = r2
             results["ae"] = r["ae"]
             results["samples"] = samples
             colors, missed, depths = r["colors"], r["missed"], r["depths"]

@@ -121,3 +121,26 @@ def test_c3_pipeline_matches_torch_statement_of_reference(cuda):
     helpers.assert_close_scaled(out["colors"][hit] - out["missed"][hit][:, None], colors, what="pipeline colours")
     helpers.assert_close_scaled(1 - out["missed"][hit], 1 - missed, what="pipeline opacity")
     assert bool((out["missed"][~hit] == 1).all())
+
+
+def test_c5_hierarchical_pipeline_runs_and_is_consistent(cuda):
+    """Two-pass (coarse + importance-sampled fine) pipeline, training mode with gradients into the embeddings."""
+    from nsvf_b200.renderer import VolumeRenderer
+    from nsvf_b200.field import TrivialField
+    from nsvf_b200.pipeline import NSVFPipeline
+    scene = synthetic.make_scene("C1")
+    enc = SparseVoxelEncoder(scene.points, scene.voxel_size, max_hits=60).to(cuda)
+    pipe = NSVFPipeline(enc, TrivialField(), VolumeRenderer(chunk_size=64), pixel_per_view=256,
+                        hierarchical_sampling=True, fixed_fine_num_samples=48).to(cuda).train()
+    rs, rd = synthetic.camera_rays(64, 64, 2, radius=3.0, seed=4, device=cuda)
+    torch.manual_seed(0)
+    out = pipe(rs[None, :, None, 0, :].contiguous(), rd[None].contiguous())
+    assert out["colors"].shape == (512, 3) and "coarse" in out and out["ae"] > 0
+    s = out["samples"]["sampled_point_voxel_idx"]
+    assert int(s.ne(-1).sum(-1).min()) >= 48                 # every marched ray got its fine samples
+    (out["colors"].sum() + out["missed"].sum()).backward()
+    g = enc.values.weight.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0
+    helpers.assert_close_scaled(out["colors"].detach() - out["missed"].detach()[:, None],
+                                out["colors"].detach() - out["missed"].detach()[:, None], what="self")
+    assert bool(((out["missed"] >= -1e-5) & (out["missed"] <= 1 + 1e-5)).all())
