@@ -99,6 +99,18 @@ NSVF_API int nsvf_svo_intersect(nsvf_stream_t stream, int b, int T, int m, float
                        long long tree_batch_stride_nodes, int* idx, float* min_depth, float* max_depth,
                        void* workspace, size_t workspace_bytes);
 
+/* The two clib entry points outside the NSVF path (kept for API completeness of the 7-function module):
+ * ball_intersect, fairnr/clib/src/intersect.cpp:15-44 + intersect_gpu.cu:15-70 (no caller in the reference), and
+ * triangle_intersect, intersect.cpp:120-146 + intersect_gpu.cu:240-347 (mesh encoder):
+ *   face_points f32 [b, n, 9]; depth f32 [b, m, n_max*3] = (t, -cage_near, cage_far) per hit sorted by t;
+ *   uv f32 [b, m, n_max*2].  Batch strides as for nsvf_aabb_intersect (0 = shared). Outputs fully written. */
+NSVF_API int nsvf_ball_intersect(nsvf_stream_t stream, int b, int n, int m, float radius, int n_max,
+                                 const float* ray_start, const float* ray_dir, const float* points,
+                                 long long points_batch_stride, int* idx, float* min_depth, float* max_depth);
+NSVF_API int nsvf_triangle_intersect(nsvf_stream_t stream, int b, int n, int m, float cagesize, float blur, int n_max,
+                                     const float* ray_start, const float* ray_dir, const float* face_points,
+                                     long long faces_batch_stride, int* idx, float* depth, float* uv);
+
 /* ---- ray sampling ---------------------------------------------------------------------------------
  * Replaces inverse_cdf_sampling, fairnr/clib/src/sample.cpp:58-95 + sample_gpu.cu:108-202, and the
  * tiling / padding / noise / trimming glue of InverseCDFRaySampling.forward, fairnr/clib/__init__.py:231-300.

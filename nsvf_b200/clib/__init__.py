@@ -176,9 +176,44 @@ class InverseCDFRaySampling(Function):
 inverse_cdf_sampling = InverseCDFRaySampling.apply
 
 
-def ball_ray_intersect(*args, **kwargs):
-    return _ext.ball_intersect(*args, **kwargs)
+class BallRayIntersect(Function):
+    """fairnr/clib/__init__.py:38-55."""
+
+    @staticmethod
+    def forward(ctx, radius, n_max, points, ray_start, ray_dir):
+        inds, min_depth, max_depth = _ext.ball_intersect(
+            ray_start.float().contiguous(), ray_dir.float().contiguous(), points.float().contiguous(), radius, n_max)
+        min_depth, max_depth = min_depth.type_as(ray_start), max_depth.type_as(ray_start)
+        ctx.mark_non_differentiable(inds, min_depth, max_depth)
+        return inds, min_depth, max_depth
+
+    @staticmethod
+    def backward(ctx, a, b, c):
+        return None, None, None, None, None
 
 
-def triangle_ray_intersect(*args, **kwargs):
-    return _ext.triangle_intersect(None, None, None, None, None, None)
+ball_ray_intersect = BallRayIntersect.apply
+
+
+class TriangleRayIntersect(Function):
+    """fairnr/clib/__init__.py:138-175 (no face replication: the face set is shared by all rays of a shape)."""
+
+    @staticmethod
+    def forward(ctx, cagesize, blur_ratio, n_max, points, faces, ray_start, ray_dir):
+        import torch.nn.functional as F
+        S, N = ray_start.shape[:2]
+        face_points = F.embedding(faces.reshape(-1, 3), points.reshape(-1, 3)).reshape(1, -1, 9)
+        face_points = face_points.expand(S, -1, -1).float().contiguous()
+        inds, depth, uv = _ext.triangle_intersect(ray_start.float().contiguous(), ray_dir.float().contiguous(),
+                                                  face_points, cagesize, blur_ratio, n_max)
+        depth, uv = depth.type_as(ray_start), uv.type_as(ray_start)
+        depth = depth.reshape(S, N, -1, 3)
+        ctx.mark_non_differentiable(inds, depth, uv)
+        return inds, depth, uv
+
+    @staticmethod
+    def backward(ctx, a, b, c):
+        return None, None, None, None, None, None, None
+
+
+triangle_ray_intersect = TriangleRayIntersect.apply

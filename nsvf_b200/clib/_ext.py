@@ -149,13 +149,35 @@ def svo_intersect(ray_start, ray_dir, points, children, voxelsize, n_max, shared
 
 
 def ball_intersect(ray_start, ray_dir, points, radius, n_max):
-    """fairnr/clib/src/intersect.cpp:15-44 — no caller anywhere in the reference: out of scope."""
-    raise NotImplementedError("ball_intersect is outside the NSVF hot path (no caller in the reference)")
+    """fairnr/clib/src/intersect.cpp:15-44 (no caller in the reference; provided for API completeness)."""
+    _check_float_cuda(ray_start=ray_start, ray_dir=ray_dir, points=points)
+    radius, n_max = float(radius), int(n_max)
+    b, m = ray_start.shape[0], ray_start.shape[1]
+    _chk(points.dim() == 3 and points.shape[0] == b, "points must be [B, n, 3] with B == ray_start.size(0)")
+    n = points.shape[1]
+    idx, dmin, dmax = _hit_outputs(ray_start, n_max)
+    with torch.cuda.device(ray_start.device):
+        _lib.check(_L.nsvf_ball_intersect(_lib.current_stream(ray_start.device), b, n, m, radius, n_max, _p(ray_start),
+                                          _p(ray_dir), _p(points), n * 3, _p(idx), _p(dmin), _p(dmax)))
+    return idx, dmin, dmax
 
 
 def triangle_intersect(ray_start, ray_dir, face_points, cagesize, blur, n_max):
-    """fairnr/clib/src/intersect.cpp:120-146 — TriangleMeshEncoder only: not built yet."""
-    raise NotImplementedError("triangle_intersect is outside the NSVF hot path (SURVEY.md §8f, rank 4)")
+    """fairnr/clib/src/intersect.cpp:120-146.  face_points f32 [B, n, 9] -> idx i32 [B,M,n_max],
+    depth f32 [B,M,n_max*3], uv f32 [B,M,n_max*2]."""
+    _check_float_cuda(ray_start=ray_start, ray_dir=ray_dir, face_points=face_points)
+    cagesize, blur, n_max = float(cagesize), float(blur), int(n_max)
+    b, m = ray_start.shape[0], ray_start.shape[1]
+    _chk(face_points.dim() == 3 and face_points.shape[0] == b, "face_points must be [B, n, 9]")
+    n = face_points.shape[1]
+    dev = ray_start.device
+    idx = torch.empty((b, m, n_max), dtype=torch.int32, device=dev)
+    depth = torch.empty((b, m, n_max * 3), dtype=torch.float32, device=dev)
+    uv = torch.empty((b, m, n_max * 2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_L.nsvf_triangle_intersect(_lib.current_stream(dev), b, n, m, cagesize, blur, n_max, _p(ray_start),
+                                              _p(ray_dir), _p(face_points), n * 9, _p(idx), _p(depth), _p(uv)))
+    return idx, depth, uv
 
 
 def uniform_ray_sampling(pts_idx, min_depth, max_depth, uniform_noise, step_size, max_steps):

@@ -267,3 +267,35 @@ def test_svo_non_enclosing_tree_falls_back_to_reference_boxes(cuda, ref_ext):
     _cmp3(mine, ref, "svo on a non-enclosing tree")
     good = ours.svo_intersect(rs, rd, centers[None].contiguous(), children[None].contiguous(), 0.4, 60)
     assert not torch.equal(good[0], mine[0])           # the malformed tree really changes the answer
+
+
+def test_ball_and_triangle_intersect_vs_reference(cuda, ref_ext):
+    """The two clib entry points outside the NSVF path, for API completeness: same outputs as the reference kernels."""
+    scene = synthetic.make_scene("C1")
+    pts, _, _ = helpers.scene_tensors(scene, cuda)
+    o, d = helpers.rays_for("C1", 2048, 31, cuda)
+    rs, rd = o.view(2, -1, 3).contiguous(), d.view(2, -1, 3).contiguous()
+    P = pts[None].expand(2, -1, -1).contiguous()
+    mine = ours.ball_intersect(rs, rd, P, 0.2, 16)
+    ref = ref_ext.ball_intersect(rs, rd, P, 0.2, 16)
+    assert torch.equal(mine[0], ref[0]) and int((mine[0] >= 0).sum()) > 2048
+    torch.testing.assert_close(mine[1], ref[1], rtol=helpers.RTOL, atol=1e-6)
+    torch.testing.assert_close(mine[2], ref[2], rtol=helpers.RTOL, atol=1e-6)
+    # a triangulated box surface: 12 faces per voxel of a small grid
+    g = torch.Generator().manual_seed(0)
+    c = pts[torch.randperm(scene.n, generator=g)[:40]]
+    off = torch.tensor([[a, b, e] for a in (-1., 1.) for b in (-1., 1.) for e in (-1., 1.)], device=cuda) * 0.125
+    corners = (c[:, None] + off[None])                                    # [40, 8, 3]
+    quads = [(0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)]
+    tris = [(q[0], q[1], q[2]) for q in quads] + [(q[0], q[2], q[3]) for q in quads]
+    faces = torch.stack([corners[:, list(t)].reshape(-1, 9) for t in tris], 1).reshape(1, -1, 9)   # [1, 480, 9]
+    F2 = faces.expand(2, -1, -1).contiguous()
+    mine = ours.triangle_intersect(rs, rd, F2, 0.05, 0.01, 12)
+    ref = ref_ext.triangle_intersect(rs, rd, F2, 0.05, 0.01, 12)
+    assert torch.equal(mine[0], ref[0]) and int((mine[0] >= 0).sum()) > 500
+    torch.testing.assert_close(mine[1], ref[1], rtol=helpers.RTOL, atol=1e-6)
+    torch.testing.assert_close(mine[2], ref[2], rtol=helpers.RTOL, atol=1e-6)
+    inds, depth, uv = clib.triangle_ray_intersect(0.05, 0.01, 12, corners.reshape(-1, 3),
+                                                  torch.arange(480 * 3, device=cuda).view(-1, 3) * 0 +
+                                                  torch.tensor([0, 1, 2], device=cuda), rs[:1], rd[:1])
+    assert inds.shape == (1, rs.shape[1], 12) and depth.shape == (1, rs.shape[1], 12, 3)
