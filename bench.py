@@ -436,7 +436,7 @@ def cpu_arm(steps, warmup, fraction):
     pts = scene.points.copy()
     pts[:, 0] += np.float32(scene.voxel_size / 10)
     torch.manual_seed(0)
-    field = RadianceField()
+    field = RadianceField(fused=False)      # the reference composition in plain torch (CPU)
     values = torch.from_numpy(scene.values.copy()).requires_grad_(True)
     opt = torch.optim.Adam(list(p for p in field.parameters() if p.requires_grad) + [values], lr=1e-3)
     pix = RES * RES // fraction

@@ -250,6 +250,21 @@ NSVF_API int nsvf_fill_in_blend(nsvf_stream_t stream, long long N, const unsigne
 NSVF_API int nsvf_track_voxel_probs(nsvf_stream_t stream, long long B, int K, const int* sampled_idx,
                                     const float* probs, int n_vox, float* max_probs);
 
+/* ---- field MLP: the passes around the Linear of an FCLayer ----------------------------------------------------
+ * Replaces, for FCLayer (fairnr/modules/module_utils.py:97-111: nn.Linear -> nn.LayerNorm([N]) -> nn.ReLU), the
+ * LayerNorm + ReLU forward and — in one pass — everything of its backward that is not a GEMM: the ReLU mask, d gamma,
+ * d beta, the layer-norm input gradient dh and the Linear's bias gradient (column sums of dh).  The Linear's
+ * contractions stay on cuBLAS.  N must be 128, 256 or 512; h, y, dy, dh f32 [M, N]; gamma, beta f32 [N];
+ * mean, rstd f32 [M] (biased variance, rstd = rsqrt(var + eps), as at::native::layer_norm).
+ *   fwd: y = max((h - mean) * rstd * gamma + beta, 0); mean / rstd (optional, needed by bwd)
+ *   bwd: dh f32 [M, N]; dgamma, dbeta, dbias f32 [N] (each optional) — deterministic (fixed summation order). */
+NSVF_API int nsvf_ln_relu_fwd(nsvf_stream_t stream, long long M, int N, const float* h, const float* gamma,
+                              const float* beta, float eps, float* y, float* mean, float* rstd);
+NSVF_API size_t nsvf_ln_relu_bwd_workspace_bytes(long long M, int N);
+NSVF_API int nsvf_ln_relu_bwd(nsvf_stream_t stream, long long M, int N, const float* h, const float* dy,
+                              const float* gamma, const float* beta, const float* mean, const float* rstd, float* dh,
+                              float* dgamma, float* dbeta, float* dbias, void* workspace, size_t workspace_bytes);
+
 #ifdef __cplusplus
 }
 #endif

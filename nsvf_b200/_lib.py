@@ -58,6 +58,10 @@ SIGNATURES = {
     "nsvf_fill_in_blend": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                    c_void_p, c_void_p, c_void_p]),
     "nsvf_track_voxel_probs": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "nsvf_ln_relu_fwd": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                 c_void_p]),
+    "nsvf_ln_relu_bwd_workspace_bytes": (c_size_t, [c_ll, c_int]),
+    "nsvf_ln_relu_bwd": (c_int, [c_void_p, c_ll, c_int] + [c_void_p] * 11 + [c_size_t]),
     "nsvf_compact_count": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "nsvf_compact_fill": (c_int, [c_void_p, c_ll, c_int, c_int, c_int] + [c_void_p] * 12),
 }

@@ -217,6 +217,12 @@ trilinear_bwd_generic_kernel(long long M, int D, const int* __restrict__ sampled
 // (ray-marched samples arrive in ray order, ~8 per voxel at step = voxel/8), so most samples cost 4 LDS.128,
 // 32 FMAs and one coalesced 128-byte store.
 constexpr int kTriRow = 20;   // words per staged sample: 8 weights, 8 keys, voxel id, 3 pad (80 B, 16-B aligned)
+// Word offset of staged sample `sl`.  The four 8-lane groups of a warp read rows that are 8 (or 16) samples apart
+// in the same LDS instruction; with a plain 20-word stride those rows start at the same bank (8*20 = 160 = 0 mod 32)
+// and every broadcast read of {weights, voxel id} is a 4-way bank conflict.  Four extra words per 8 rows move the
+// groups to different banks.
+__device__ __forceinline__ int tri_row_off(int sl) { return sl * kTriRow + ((sl >> 3) << 2); }
+constexpr int tri_stage_words(int samples) { return samples * kTriRow + (samples >> 3) * 4; }
 
 struct TriSample { int v; float x, y, z; };
 
@@ -256,12 +262,44 @@ __device__ __forceinline__ void tri_phase_a(const TriSample& t, const int* __res
 
 // SPL = samples per lane in phase A: a warp takes 32*SPL consecutive samples and every 8-lane group walks 8*SPL
 // CONSECUTIVE ones, so corner rows (fwd) / corner gradients (bwd) are reused across longer voxel runs.
-template <int SPL, int WARPS>
+//
+// Run snapping (snap != 0): the boundaries between the four groups' sample ranges are moved forward to the next
+// voxel-run start (ballot of "voxel id differs from the previous sample's"), so a run of same-voxel samples is
+// never cut between two groups: one corner-row gather (fwd) / one flush of 8 red.v4 per lane (bwd) per run and per
+// chunk boundary instead of one per run and per group boundary.
+template <int SPL>
+__device__ __forceinline__ void tri_group_bounds(const int (&v)[SPL], int lane, int g, int snap, int& r0, int& r1) {
+  constexpr int GS = 8 * SPL;   // nominal samples per group
+  r0 = g * GS;
+  r1 = r0 + GS;
+  if (!snap) return;
+  unsigned long long starts = 0ull;
+#pragma unroll
+  for (int q = 0; q < SPL; ++q) {
+    int pv = __shfl_up_sync(NSVF_FULL_MASK, v[q], 1);
+    if (q > 0) {
+      const int last = __shfl_sync(NSVF_FULL_MASK, v[q - 1], 31);
+      if (lane == 0) pv = last;
+    }
+    const unsigned m = __ballot_sync(NSVF_FULL_MASK, (q == 0 && lane == 0) || v[q] != pv);
+    starts |= (unsigned long long)m << (32 * q);
+  }
+  auto bound = [&](int gg) -> int {
+    if (gg == 0) return 0;
+    if (gg >= 4) return 32 * SPL;
+    const unsigned long long mm = starts >> (gg * GS);
+    return mm ? gg * GS + __ffsll((long long)mm) - 1 : 32 * SPL;
+  };
+  r0 = bound(g);
+  r1 = bound(g + 1);
+}
+
+template <int SPL, int WARPS, bool SNAP>
 __global__ void __launch_bounds__(WARPS * 32)
 trilinear_fwd_d32_v2_kernel(long long M, const int* __restrict__ sampled_idx, const float* __restrict__ xyz,
                             const int* __restrict__ feats, const float* __restrict__ centres,
                             const float* __restrict__ values, float voxel_size, float* __restrict__ out) {
-  __shared__ __align__(16) float stage[WARPS][32 * SPL * kTriRow];
+  __shared__ __align__(16) float stage[WARPS][tri_stage_words(32 * SPL)];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
   float* st = stage[warp];
   constexpr int CH = 32 * SPL;
@@ -273,20 +311,25 @@ trilinear_fwd_d32_v2_kernel(long long M, const int* __restrict__ sampled_idx, co
     cur[q] = tri_load(c_first * CH + q * 32 + lane, c_first < n_chunks ? M : 0, sampled_idx, xyz);
   for (long long c = c_first; c < n_chunks; c += c_step) {
     const long long s0 = c * CH;
+    int myv[SPL];
 #pragma unroll
     for (int q = 0; q < SPL; ++q) {
       // software pipeline: the next chunk's index / position loads are in flight during this chunk's work
       const TriSample nxt = tri_load((c + c_step) * CH + q * 32 + lane, (c + c_step) < n_chunks ? M : 0, sampled_idx, xyz);
-      tri_phase_a(cur[q], feats, centres, voxel_size, st + (q * 32 + lane) * kTriRow);
+      tri_phase_a(cur[q], feats, centres, voxel_size, st + tri_row_off(q * 32 + lane));
+      myv[q] = cur[q].v;
       cur[q] = nxt;
     }
+    // compile-time trip count when not snapping: the unrolled loop keeps the next sample's LDS in flight
+    int r0 = g * 8 * SPL, r1 = r0 + 8 * SPL;
+    if (SNAP) tri_group_bounds<SPL>(myv, lane, g, 1, r0, r1);
     __syncwarp();
     int prev = -2;
     float4 e[8];
 #pragma unroll 2
-    for (int r = 0; r < 8 * SPL; ++r) {
-      const int sl = g * 8 * SPL + r;
-      const float* row = st + sl * kTriRow;
+    for (int rr = 0; rr < (SNAP ? r1 - r0 : 8 * SPL); ++rr) {
+      const int sl = r0 + rr;
+      const float* row = st + tri_row_off(sl);
       const int v = reinterpret_cast<const int*>(row)[16];
       if (v >= 0) {
         if (v != prev) {
@@ -318,12 +361,12 @@ trilinear_fwd_d32_v2_kernel(long long M, const int* __restrict__ sampled_idx, co
 // block) brought into shared memory by a TMA bulk copy (cp.async.bulk + mbarrier), double-buffered so the next
 // chunk streams in while this one is reduced.  Each 8-lane group keeps the 8 corner gradients of the current voxel
 // in registers across a run of samples and flushes them with red.global.add.v4.f32.
-template <int WARPS>
+template <int WARPS, bool SNAP>
 __global__ void __launch_bounds__(WARPS * 32)
 trilinear_bwd_d32_v2_kernel(long long M, const int* __restrict__ sampled_idx, const float* __restrict__ xyz,
                             const int* __restrict__ feats, const float* __restrict__ centres, float voxel_size,
                             const float* __restrict__ grad_out, float* __restrict__ grad_values) {
-  __shared__ __align__(16) float stage[WARPS][32 * kTriRow];
+  __shared__ __align__(16) float stage[WARPS][tri_stage_words(32)];
   __shared__ __align__(128) float gbuf[WARPS][2][32 * 32];
   __shared__ __align__(8) uint64_t bars[WARPS][2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
@@ -349,8 +392,11 @@ trilinear_bwd_d32_v2_kernel(long long M, const int* __restrict__ sampled_idx, co
     const int slot = it & 1;
     if (lane == 0 && c + c_step < n_chunks) issue(c + c_step, slot ^ 1);   // that buffer was released by the
     const TriSample nxt = tri_load((c + c_step) * 32 + lane, (c + c_step) < n_chunks ? M : 0, sampled_idx, xyz);
-    tri_phase_a(cur, feats, centres, voxel_size, st + lane * kTriRow);       // __syncwarp ending iteration it-1
+    tri_phase_a(cur, feats, centres, voxel_size, st + tri_row_off(lane));      // __syncwarp ending iteration it-1
+    const int myv[1] = {cur.v};
     cur = nxt;
+    int r0 = g * 8, r1 = r0 + 8;
+    if (SNAP) tri_group_bounds<1>(myv, lane, g, 1, r0, r1);
     __syncwarp();
     mbar_wait(&bars[warp][slot], (it >> 1) & 1);
     const float* gb = gbuf[warp][slot];
@@ -358,9 +404,9 @@ trilinear_bwd_d32_v2_kernel(long long M, const int* __restrict__ sampled_idx, co
     int key[8];
     float4 acc[8];
 #pragma unroll 2
-    for (int r = 0; r < 8; ++r) {
-      const int sl = g * 8 + r;
-      const float* row = st + sl * kTriRow;
+    for (int rr = 0; rr < (SNAP ? r1 - r0 : 8); ++rr) {
+      const int sl = r0 + rr;
+      const float* row = st + tri_row_off(sl);
       const int v = reinterpret_cast<const int*>(row)[16];
       if (v >= 0) {
         if (v != prev) {
@@ -404,6 +450,11 @@ static int tri_variant() {
   return g_tri_variant;
 }
 
+static int tri_snap() {   // NSVF_TRI_SNAP: bit 0 = run snapping in the backward (default on), bit 1 = in the forward
+  static int v = getenv("NSVF_TRI_SNAP") ? atoi(getenv("NSVF_TRI_SNAP")) : 1;
+  return v;
+}
+
 static int grid_for(long long work_items, int items_per_block, int max_blocks_per_sm) {
   long long want = (work_items + items_per_block - 1) / items_per_block;
   long long cap = (long long)num_sms() * max_blocks_per_sm;
@@ -426,36 +477,37 @@ extern "C" int nsvf_trilinear_embed_fwd(nsvf_stream_t stream_, long long M, int 
                  "trilinear_embed_fwd: values/out/feats must be 16-byte aligned");
     NSVF_REQUIRE(((uintptr_t)values & 15) == 0, "trilinear_embed_fwd: values must be 16-byte aligned");
     static int bps = getenv("NSVF_TRI_BPS") ? atoi(getenv("NSVF_TRI_BPS")) : 24;
+    const bool snap = (tri_snap() & 2) != 0;
+#define NSVF_TRI_FWD(SPL, W, GRID)                                                                              \
+  do {                                                                                                          \
+    if (snap) {                                                                                                 \
+      NSVF_TIMED_LAUNCH("trilinear_fwd_kernel", stream,                                                         \
+                        (trilinear_fwd_d32_v2_kernel<SPL, W, true><<<GRID, W * 32, 0, stream>>>(                \
+                            M, sampled_idx, sampled_xyz, feats, centres, values, voxel_size, out)));            \
+    } else {                                                                                                    \
+      NSVF_TIMED_LAUNCH("trilinear_fwd_kernel", stream,                                                         \
+                        (trilinear_fwd_d32_v2_kernel<SPL, W, false><<<GRID, W * 32, 0, stream>>>(               \
+                            M, sampled_idx, sampled_xyz, feats, centres, values, voxel_size, out)));            \
+    }                                                                                                           \
+  } while (0)
     switch (tri_variant() == 0 ? 2 : tri_variant()) {
       case 5:
-        NSVF_TIMED_LAUNCH("trilinear_fwd_kernel", stream,
-                          (trilinear_fwd_d32_v2_kernel<2, 8><<<grid_for((M + 63) / 64, 8, bps), 256, 0, stream>>>(
-                              M, sampled_idx, sampled_xyz, feats, centres, values, voxel_size, out)));
+        NSVF_TRI_FWD(2, 8, grid_for((M + 63) / 64, 8, bps));
         break;
       case 6:
-        NSVF_TIMED_LAUNCH("trilinear_fwd_kernel", stream,
-                          (trilinear_fwd_d32_v2_kernel<2, 2><<<grid_for((M + 63) / 64, 2, bps), 64, 0, stream>>>(
-                              M, sampled_idx, sampled_xyz, feats, centres, values, voxel_size, out)));
+        NSVF_TRI_FWD(2, 2, grid_for((M + 63) / 64, 2, bps));
         break;
       case 2:
-        NSVF_TIMED_LAUNCH("trilinear_fwd_kernel", stream,
-                          (trilinear_fwd_d32_v2_kernel<2, 4><<<grid_for((M + 63) / 64, 4, bps), 128, 0, stream>>>(
-                              M, sampled_idx, sampled_xyz, feats, centres, values, voxel_size, out)));
+        NSVF_TRI_FWD(2, 4, grid_for((M + 63) / 64, 4, bps));
         break;
       case 4:
-        NSVF_TIMED_LAUNCH("trilinear_fwd_kernel", stream,
-                          (trilinear_fwd_d32_v2_kernel<4, 4><<<grid_for((M + 127) / 128, 4, 12), 128, 0, stream>>>(
-                              M, sampled_idx, sampled_xyz, feats, centres, values, voxel_size, out)));
+        NSVF_TRI_FWD(4, 4, grid_for((M + 127) / 128, 4, 12));
         break;
       case 1:
-        NSVF_TIMED_LAUNCH("trilinear_fwd_kernel", stream,
-                          (trilinear_fwd_d32_v2_kernel<1, 4><<<grid_for((M + 31) / 32, 4, 12), 128, 0, stream>>>(
-                              M, sampled_idx, sampled_xyz, feats, centres, values, voxel_size, out)));
+        NSVF_TRI_FWD(1, 4, grid_for((M + 31) / 32, 4, 12));
         break;
       default:
-        NSVF_TIMED_LAUNCH("trilinear_fwd_kernel", stream,
-                          (trilinear_fwd_d32_v2_kernel<1, 8><<<grid_for((M + 31) / 32, 8, 8), 256, 0, stream>>>(
-                              M, sampled_idx, sampled_xyz, feats, centres, values, voxel_size, out)));
+        NSVF_TRI_FWD(1, 8, grid_for((M + 31) / 32, 8, 8));
     }
     return 0;
   } else {
@@ -478,9 +530,15 @@ extern "C" int nsvf_trilinear_embed_bwd(nsvf_stream_t stream_, long long M, int 
                  "trilinear_embed_bwd: values/grad_out/grad_values/feats must be 16-byte aligned");
     if (grad_xyz == nullptr) {
       NSVF_REQUIRE(((uintptr_t)grad_out & 15) == 0, "trilinear_embed_bwd: grad_out must be 16-byte aligned");
-      NSVF_TIMED_LAUNCH("trilinear_bwd_kernel", stream,
-                        (trilinear_bwd_d32_v2_kernel<4><<<grid_for((M + 31) / 32, 4, 5), 128, 0, stream>>>(
-                            M, sampled_idx, sampled_xyz, feats, centres, voxel_size, grad_out, grad_values)));
+      if (tri_snap() & 1) {
+        NSVF_TIMED_LAUNCH("trilinear_bwd_kernel", stream,
+                          (trilinear_bwd_d32_v2_kernel<4, true><<<grid_for((M + 31) / 32, 4, 5), 128, 0, stream>>>(
+                              M, sampled_idx, sampled_xyz, feats, centres, voxel_size, grad_out, grad_values)));
+      } else {
+        NSVF_TIMED_LAUNCH("trilinear_bwd_kernel", stream,
+                          (trilinear_bwd_d32_v2_kernel<4, false><<<grid_for((M + 31) / 32, 4, 5), 128, 0, stream>>>(
+                              M, sampled_idx, sampled_xyz, feats, centres, voxel_size, grad_out, grad_values)));
+      }
       return 0;
     }
     const long long runs = (M + kTriRun - 1) / kTriRun;

@@ -32,32 +32,34 @@ class _PosEnc(nn.Module):
         return torch.cat([y, x], -1) if self.cat_input else y
 
 
-class _LayerNormReLU(nn.Module):
-    """LayerNorm([o]) + ReLU with the same parameters as nn.LayerNorm, written as a non-affine layer_norm followed by
-    an explicit scale/shift: torch's fused affine backward (GammaBetaBackwardCUDAKernel) is pathologically slow for
-    tall [65536, 256] activations (0.5 ms per call, 30 % of the whole training step); a plain column reduction is not."""
+class _FCLayer(nn.Sequential):
+    """FCLayer of the reference (module_utils.py:97-111): Linear -> LayerNorm([o]) -> ReLU, same parameter names
+    ("0.weight", "0.bias", "1.weight", "1.bias").  fused=True (the product path, CUDA only, no fallback) runs the
+    contractions on cuBLAS and everything else in the hand-written kernels of csrc/field_norm.cu: torch's own
+    LayerNorm backward (GammaBetaBackwardCUDAKernel) plus the bias-gradient column reductions cost 0.5 ms per call on
+    tall [65536, 256] activations, 40 % of the whole training step.  fused=False is the reference composition in plain
+    torch, used by bench.py's CPU reference arm and as the comparison in tests."""
 
-    def __init__(self, dim, eps=1e-5):
-        super().__init__()
-        self.dim, self.eps = (dim,), eps
-        self.weight = nn.Parameter(torch.ones(dim))
-        self.bias = nn.Parameter(torch.zeros(dim))
+    def __init__(self, i, o, fused):
+        lin = nn.Linear(i, o)
+        nn.init.kaiming_normal_(lin.weight, a=0.0, nonlinearity="relu", mode="fan_in")
+        super().__init__(lin, nn.LayerNorm([o]), nn.ReLU())
+        self.fused = fused
 
     def forward(self, x):
-        return torch.relu(torch.addcmul(self.bias, torch.nn.functional.layer_norm(x, self.dim, None, None, self.eps),
-                                        self.weight))
-
-
-def _fc(i, o):
-    lin = nn.Linear(i, o)
-    nn.init.kaiming_normal_(lin.weight, a=0.0, nonlinearity="relu", mode="fan_in")
-    return nn.Sequential(lin, _LayerNormReLU(o))
+        if not self.fused:
+            return super().forward(x)
+        from . import ops
+        return ops.linear_layernorm_relu(x, self[0].weight, self[0].bias, self[1].weight, self[1].bias, self[1].eps)
 
 
 class RadianceField(nn.Module):
     def __init__(self, embed_dim=32, feat_dim=256, density_dim=128, texture_dim=256, texture_layers=3,
-                 feature_layers=1, bg_color=(1.0, 1.0, 1.0), sigma_bias=0.0):
+                 feature_layers=1, bg_color=(1.0, 1.0, 1.0), sigma_bias=0.0, fused=True):
         super().__init__()
+
+        def _fc(i, o):
+            return _FCLayer(i, o, fused)
         self.emb_enc = _PosEnc(embed_dim, 6, angular=False, cat_input=True)
         self.ray_enc = _PosEnc(3, 4, angular=True, cat_input=False)
         dims = [self.emb_enc.out_dim] + [feat_dim] * (feature_layers + 2)

@@ -6,7 +6,11 @@
   composite(free_energy, texture, sampled_depth)
         = the compositing block of VolumeRenderer.forward_chunk, fairnr/modules/renderer.py:193-218
 
-Both run on the C ABI (include/nsvf_b200.h); CUDA float32 tensors only, no fallback.
+  linear_layernorm_relu(x, weight, bias, gamma, beta, eps)
+        = FCLayer of the field MLP, fairnr/modules/module_utils.py:97-111 (Linear -> LayerNorm -> ReLU): the
+          contractions stay on cuBLAS, every other pass of forward and backward is one fused kernel each
+
+All run on the C ABI (include/nsvf_b200.h); CUDA float32 tensors only, no fallback.
 """
 import torch
 from torch.autograd import Function
@@ -116,6 +120,57 @@ class Composite(Function):
 def composite(free_energy, texture, sampled_depth):
     """(probs[B,K], depth[B], missed[B], colors[B,3]) from free energy, rgb and sample depths."""
     return Composite.apply(free_energy, texture, sampled_depth)
+
+
+class LinearLayerNormReLU(Function):
+    """y = relu(layer_norm(x @ W^T + b) * gamma + beta).  cuBLAS does the three contractions (h, dx, dW); the
+    LayerNorm + ReLU forward and {relu mask, d gamma, d beta, dh, d b} of the backward are one kernel each."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, eps):
+        _need_cuda(x=x, weight=weight, bias=bias, gamma=gamma, beta=beta)
+        if x.dtype != torch.float32 or weight.dtype != torch.float32:
+            raise RuntimeError("nsvf_b200: linear_layernorm_relu is float32 only")
+        lead = x.shape[:-1]
+        x2 = x.detach().reshape(-1, x.shape[-1])
+        w, b = weight.detach(), bias.detach()
+        g, bt = gamma.detach().contiguous(), beta.detach().contiguous()
+        h = torch.addmm(b, x2, w.t())                                  # cuBLAS
+        M, N = h.shape
+        y = torch.empty_like(h)
+        mean = torch.empty(M, dtype=torch.float32, device=h.device)
+        rstd = torch.empty(M, dtype=torch.float32, device=h.device)
+        with torch.cuda.device(h.device):
+            _lib.check(_L.nsvf_ln_relu_fwd(_lib.current_stream(h.device), M, N, _p(h), _p(g), _p(bt), float(eps), _p(y),
+                                           _p(mean), _p(rstd)))
+        ctx.save_for_backward(x2, w, h, g, bt, mean, rstd)
+        ctx.lead = lead
+        return y.reshape(*lead, N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, h, g, bt, mean, rstd = ctx.saved_tensors
+        M, N = h.shape
+        dev = h.device
+        if M == 0:
+            z = torch.zeros_like
+            return x2.new_zeros(*ctx.lead, x2.shape[-1]), z(w), z(g), z(g), z(g), None
+        dy2 = dy.reshape(M, N).float().contiguous()
+        dh = torch.empty_like(h)
+        sums = torch.empty(3, N, dtype=torch.float32, device=dev)      # d gamma, d beta, d bias
+        with torch.cuda.device(dev):
+            ws_bytes = _L.nsvf_ln_relu_bwd_workspace_bytes(M, N)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _lib.check(_L.nsvf_ln_relu_bwd(_lib.current_stream(dev), M, N, _p(h), _p(dy2), _p(g), _p(bt), _p(mean),
+                                           _p(rstd), _p(dh), _p(sums[0]), _p(sums[1]), _p(sums[2]), _p(ws), ws_bytes))
+        dx = (dh @ w).reshape(*ctx.lead, x2.shape[-1]) if ctx.needs_input_grad[0] else None     # cuBLAS
+        dw = dh.t() @ x2 if ctx.needs_input_grad[1] else None                                    # cuBLAS
+        return dx, dw, sums[2], sums[0], sums[1], None
+
+
+def linear_layernorm_relu(x, weight, bias, gamma, beta, eps=1e-5):
+    """FCLayer forward (module_utils.py:97-111) on cuBLAS + the fused LayerNorm/ReLU kernels."""
+    return LinearLayerNormReLU.apply(x, weight, bias, gamma, beta, eps)
 
 
 class FillInBlend(Function):

@@ -10,8 +10,9 @@ pts = torch.from_numpy(scene.points).to(dev); feats = torch.from_numpy(scene.fea
 values = torch.from_numpy(scene.values).to(dev)
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 40_000_000
 g = torch.Generator(device=dev).manual_seed(0)
-runs = torch.randint(0, scene.n, (M // 6 + 1,), device=dev, generator=g)
-vox = runs.repeat_interleave(6)[:M].int().contiguous()
+RUN = int(sys.argv[2]) if len(sys.argv) > 2 else 6      # consecutive samples per voxel (step = voxel/8 -> 6..10)
+runs = torch.randint(0, scene.n, (M // RUN + 1,), device=dev, generator=g)
+vox = runs.repeat_interleave(RUN)[:M].int().contiguous()
 xyz = (pts[vox.long()] + (torch.rand(M, 3, device=dev, generator=g) - 0.5) * scene.voxel_size).contiguous()
 out = torch.empty(M, 32, device=dev); gout = torch.randn(M, 32, device=dev); gv = torch.zeros_like(values)
 st = torch.cuda.current_stream().cuda_stream
@@ -23,8 +24,10 @@ def t(fn, n=5):
     e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1) / n
 f = lambda: L.nsvf_trilinear_embed_fwd(st, M, 32, p(vox), p(xyz), p(feats), p(pts), p(values), scene.voxel_size, p(out))
 b = lambda: L.nsvf_trilinear_embed_bwd(st, M, 32, p(vox), p(xyz), p(feats), p(pts), p(values), scene.voxel_size, p(gout), p(gv), None)
+print("run length", RUN, "NSVF_TRI_SNAP", os.environ.get("NSVF_TRI_SNAP"), "NSVF_TRI_BWD", os.environ.get("NSVF_TRI_BWD"))
 ms = t(f); print("trilinear fwd  M=%d: %.3f ms  %.0f GB/s (144 B/sample)" % (M, ms, M * 144 / ms / 1e6))
 ms = t(b); print("trilinear bwd  M=%d: %.3f ms  %.0f GB/s (144 B/sample)" % (M, ms, M * 144 / ms / 1e6))
+if os.environ.get("TRI_ONLY"): sys.exit(0)
 B, K = 262144, 256
 fe = torch.rand(B, K, device=dev) * 0.1; tex = torch.rand(B, K, 3, device=dev); dep = torch.rand(B, K, device=dev)
 probs = torch.empty(B, K, device=dev); od = torch.empty(B, device=dev); om = torch.empty(B, device=dev); oc = torch.empty(B, 3, device=dev)
