@@ -26,10 +26,16 @@ __device__ __forceinline__ void corner_weights(float px, float py, float pz, flo
   for (int j = 0; j < 8; ++j) w[j] = __fmul_rn(__fmul_rn(ax[(j >> 2) & 1], ay[(j >> 1) & 1]), az[j & 1]);
 }
 
+#ifdef NSVF_TRI_EXPERIMENT_NO_RED   // measurement-only build: drop the reductions (results wrong) to bound their cost
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+  if (v.x == 123456.789f) *addr = v.y;
+}
+#else
 __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
+#endif
 
 // D == 32: 8 lanes per sample, one float4 (4 dims) per lane; a warp handles 4 samples per step.
 __global__ void __launch_bounds__(256)
@@ -358,16 +364,21 @@ trilinear_fwd_d32_v2_kernel(long long M, const int* __restrict__ sampled_idx, co
 }
 
 // Backward: same two phases, with the chunk's grad_out rows (32 consecutive samples x 128 B = one contiguous 4 KiB
-// block) brought into shared memory by a TMA bulk copy (cp.async.bulk + mbarrier), double-buffered so the next
-// chunk streams in while this one is reduced.  Each 8-lane group keeps the 8 corner gradients of the current voxel
-// in registers across a run of samples and flushes them with red.global.add.v4.f32.
-template <int WARPS, bool SNAP>
-__global__ void __launch_bounds__(WARPS * 32)
+// block) brought into shared memory by a TMA bulk copy (cp.async.bulk + mbarrier).  NBUF = 2 double-buffers it (the
+// next chunk streams in while this one is reduced); NBUF = 1 issues the next chunk's copy right after the last read
+// of the buffer, so it lands under the next phase A — half the shared memory, 7 resident CTAs per SM instead of 5,
+// which measured 5 % faster.  Each 8-lane group keeps the 8 corner gradients of the current voxel in registers
+// across a run of samples and flushes them with red.global.add.v4.f32.
+// Measured bound (NSVF_TRI_EXPERIMENT_NO_RED build): 1.14 ms without the reductions vs 1.69 ms with them at 40 M
+// samples; the 240 M reduction sectors (7.7 GB, 171 B/sample at 6 samples per voxel run) move over the 64 B/clk
+// SM -> L2 port (0.41 ms at 148 SMs), the same port every load request uses, so they do not overlap with the rest.
+template <int WARPS, bool SNAP, int NBUF, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 trilinear_bwd_d32_v2_kernel(long long M, const int* __restrict__ sampled_idx, const float* __restrict__ xyz,
                             const int* __restrict__ feats, const float* __restrict__ centres, float voxel_size,
                             const float* __restrict__ grad_out, float* __restrict__ grad_values) {
   __shared__ __align__(16) float stage[WARPS][tri_stage_words(32)];
-  __shared__ __align__(128) float gbuf[WARPS][2][32 * 32];
+  __shared__ __align__(128) float gbuf[WARPS][NBUF][32 * 32];
   __shared__ __align__(8) uint64_t bars[WARPS][2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
   float* st = stage[warp];
@@ -389,8 +400,8 @@ trilinear_bwd_d32_v2_kernel(long long M, const int* __restrict__ sampled_idx, co
   TriSample cur = tri_load(c_first * 32 + lane, c_first < n_chunks ? M : 0, sampled_idx, xyz);
   int it = 0;
   for (long long c = c_first; c < n_chunks; c += c_step, ++it) {
-    const int slot = it & 1;
-    if (lane == 0 && c + c_step < n_chunks) issue(c + c_step, slot ^ 1);   // that buffer was released by the
+    const int slot = NBUF == 2 ? (it & 1) : 0;
+    if (NBUF == 2 && lane == 0 && c + c_step < n_chunks) issue(c + c_step, slot ^ 1);   // buffer released by the
     const TriSample nxt = tri_load((c + c_step) * 32 + lane, (c + c_step) < n_chunks ? M : 0, sampled_idx, xyz);
     tri_phase_a(cur, feats, centres, voxel_size, st + tri_row_off(lane));      // __syncwarp ending iteration it-1
     const int myv[1] = {cur.v};
@@ -398,7 +409,7 @@ trilinear_bwd_d32_v2_kernel(long long M, const int* __restrict__ sampled_idx, co
     int r0 = g * 8, r1 = r0 + 8;
     if (SNAP) tri_group_bounds<1>(myv, lane, g, 1, r0, r1);
     __syncwarp();
-    mbar_wait(&bars[warp][slot], (it >> 1) & 1);
+    mbar_wait(&bars[warp][slot], NBUF == 2 ? ((it >> 1) & 1) : (it & 1));
     const float* gb = gbuf[warp][slot];
     int prev = -2;
     int key[8];
@@ -438,6 +449,8 @@ trilinear_bwd_d32_v2_kernel(long long M, const int* __restrict__ sampled_idx, co
       for (int j = 0; j < 8; ++j) red_add_v4(grad_values + (long long)key[j] * 32 + sub * 4, acc[j]);
     }
     __syncwarp();
+    // single buffer: every lane has read this chunk's rows; the next chunk streams in under its phase A
+    if (NBUF == 1 && lane == 0 && c + c_step < n_chunks) issue(c + c_step, 0);
   }
 }
 
@@ -530,13 +543,20 @@ extern "C" int nsvf_trilinear_embed_bwd(nsvf_stream_t stream_, long long M, int 
                  "trilinear_embed_bwd: values/grad_out/grad_values/feats must be 16-byte aligned");
     if (grad_xyz == nullptr) {
       NSVF_REQUIRE(((uintptr_t)grad_out & 15) == 0, "trilinear_embed_bwd: grad_out must be 16-byte aligned");
-      if (tri_snap() & 1) {
+      // single grad_out buffer + <= 73 registers: 7 CTAs / SM (1.69 ms vs 1.78 ms for the double-buffered, 5-CTA shape
+      // at 40 M samples); NSVF_TRI_BWD=2 selects the double-buffered shape, NSVF_TRI_SNAP=0 the unsnapped groups
+      static int bwd_gen = getenv("NSVF_TRI_BWD") ? atoi(getenv("NSVF_TRI_BWD")) : 1;
+      if (bwd_gen == 2 && (tri_snap() & 1)) {
         NSVF_TIMED_LAUNCH("trilinear_bwd_kernel", stream,
-                          (trilinear_bwd_d32_v2_kernel<4, true><<<grid_for((M + 31) / 32, 4, 5), 128, 0, stream>>>(
+                          (trilinear_bwd_d32_v2_kernel<4, true, 2, 5><<<grid_for((M + 31) / 32, 4, 5), 128, 0, stream>>>(
+                              M, sampled_idx, sampled_xyz, feats, centres, voxel_size, grad_out, grad_values)));
+      } else if (bwd_gen == 2) {
+        NSVF_TIMED_LAUNCH("trilinear_bwd_kernel", stream,
+                          (trilinear_bwd_d32_v2_kernel<4, false, 2, 5><<<grid_for((M + 31) / 32, 4, 5), 128, 0, stream>>>(
                               M, sampled_idx, sampled_xyz, feats, centres, voxel_size, grad_out, grad_values)));
       } else {
         NSVF_TIMED_LAUNCH("trilinear_bwd_kernel", stream,
-                          (trilinear_bwd_d32_v2_kernel<4, false><<<grid_for((M + 31) / 32, 4, 5), 128, 0, stream>>>(
+                          (trilinear_bwd_d32_v2_kernel<4, true, 1, 7><<<grid_for((M + 31) / 32, 4, 7), 128, 0, stream>>>(
                               M, sampled_idx, sampled_xyz, feats, centres, voxel_size, grad_out, grad_values)));
       }
       return 0;

@@ -1,0 +1,2 @@
+for gen in 2 4 5 6; do NSVF_TRI_BWD=$gen TRI_ONLY=1 python tests/perf/time_ops.py 40000000 6 2>&1 | tail -1; done
+NSVF_TRI_BWD=5 python -m pytest tests/test_ops_gpu.py -q -x 2>&1 | tail -2
