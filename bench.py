@@ -30,6 +30,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# cuBLAS for the field MLP's fp32 contractions: must be chosen before torch is imported (nsvf_b200/blas.py).
+# --mlp-gemm simt keeps torch's bundled cuBLAS and plain SGEMM; the default runs the same fp32 GEMMs on the BF16
+# tensor cores with cuBLAS 12.9's fp32-accurate BF16x9 algorithm.  The CPU reference arm is not affected.
+from nsvf_b200 import blas as _blas
+if "reference" not in sys.argv[1:] and "simt" not in sys.argv[1:] and "--mlp-gemm=simt" not in sys.argv[1:]:
+    _blas.use_system_cublas()
+
 import numpy as np
 import torch
 
@@ -46,6 +53,9 @@ def parse():
     ap.add_argument("--no-frame", action="store_true", help="skip the C3 full-frame extra")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stages", action="store_true", help="skip the informational per-stage timings")
+    ap.add_argument("--mlp-gemm", default="bf16x9", choices=["bf16x9", "simt"],
+                    help="fp32 GEMMs of the field MLP: cuBLAS 12.9 BF16x9 emulation on tensor cores (fp32-accurate) "
+                         "or torch's bundled cuBLAS SGEMM on the SIMT pipe")
     ap.add_argument("--cpu-fraction", type=int, default=16, help="CPU arms run 1/FRACTION of the rays per step")
     return ap.parse_args()
 
@@ -249,7 +259,8 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C2: nsvf_base training step, 343 voxels (voxel 0.4, step 1/8, max_hits 60), "
                                "4 views x 800x800 rays intersected + 4 x 2048 rays marched per GPU, fwd+bwd+Adam, "
-                               "field MLP fp32 on cuBLAS", "rays_intersected_per_step_per_gpu": rays_intersected,
+                               "field MLP fp32 on cuBLAS", "mlp_gemm": _blas.mode(),
+                   "rays_intersected_per_step_per_gpu": rays_intersected,
                    "rays_marched_per_step_per_gpu": rays_marched, "samples_evaluated_per_step": int(out["ae"]),
                    "l2": "256 MiB memset at the start of every step (inside the timed region)",
                    "parallelism": "dp%d (rays sharded by view, voxel set replicated, NCCL grad all-reduce)" % world},

@@ -4,6 +4,11 @@ device: fp32 for the forward, float64 autograd for the gradients (column sums ov
 itself carries summation-order error, so the yardstick is the float64 value).
 
 Tolerance: helpers.RTOL = 1e-5 relative to the tensor's scale (BASELINE.json north_star)."""
+import json
+import os
+import subprocess
+import sys
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -87,3 +92,20 @@ def test_fused_layer_rejects_cpu_and_half(cuda):
     with pytest.raises(RuntimeError):
         ops.linear_layernorm_relu(torch.randn(3, 8, device=cuda).half(), lin.weight.to(cuda).half(),
                                   lin.bias.to(cuda).half(), torch.ones(128, device=cuda), torch.zeros(128, device=cuda))
+
+
+def test_cublas_bf16x9_emulation_is_fp32_accurate(cuda):
+    """bench.py runs the MLP's fp32 GEMMs through cuBLAS 12.9's BF16x9 algorithm (nsvf_b200/blas.py).  It must be an
+    fp32-accurate replacement: every product within 1e-6 of the float64 result's scale (the SIMT SGEMM is at ~9e-7),
+    and the fused FCLayer gradients within the parity tolerance.  Runs in a fresh interpreter because the cuBLAS choice
+    has to precede `import torch`."""
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "perf", "cublas_emulation_check.py")
+    res = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = json.loads(res.stdout.strip().splitlines()[-1])
+    if not out["emulated"]:
+        pytest.skip("no cuBLAS >= 12.9 on this machine: " + out["mode"])
+    for r in out["gemm"]:
+        assert r["fwd_err"] < 1e-6 and r["dx_err"] < 1e-6 and r["dw_err"] < 1e-6, r
+    for k, v in out["fc_layer"].items():
+        assert v < helpers.RTOL, (k, v)
