@@ -9,13 +9,18 @@ Synthetic-NeRF-shaped scene (bbox centres +-1.2, voxel 0.4 -> 343 voxels, step =
 4 views x 800x800 rays per GPU intersected (`--no-sampling-at-reader`), 4 x 2048 rays sampled from the hit mask
 and marched (inverse-CDF sampling -> trilinear interpolation -> field MLP -> compositing), loss, backward, Adam.
 Random-init weights, synthetic cameras / targets (no datasets offline).  The field MLP (545 297 parameters,
-fp32) runs on torch/cuBLAS as BASELINE.json prescribes; everything else is the hand-written path.
+fp32): its contractions run on torch/cuBLAS tensor cores as BASELINE.json prescribes (cuBLAS 12.9's fp32-accurate
+BF16x9 algorithm, nsvf_b200/blas.py; --mlp-gemm simt for the plain SGEMM), the LayerNorm/ReLU passes around them
+and everything else are hand-written kernels.
 
   value  = marched rays per second, whole job (all ranks), inputs resident in HBM
   e2e    = same, through the public pipeline call with HOST (pinned) rays + targets copied in every step and the
            loss read back
-  roofline = the dominant hand-written kernel (aabb_intersect_kernel), timed live with CUDA events recorded
-           around the launch inside the timed steps (nsvf_profile_kernel hook)
+  roofline = the hand-written kernel with the largest share of the step's device time (ln_relu_bwd_kernel, the fused
+           LayerNorm+ReLU backward around the MLP's cuBLAS GEMMs), timed live with CUDA events recorded around the
+           launch inside the timed steps (nsvf_profile_kernel hook); roofline_hot_path = the same for the dominant
+           kernel of the ray-marching path itself (the any-hit intersection); roofline_at_scale = the HBM-bound
+           kernels of the path at full-frame sizes
   cpu_baseline = the oracle port (oracle/, C + OpenMP + torch-CPU MLP) on a bounded sample of the same step
   frame  = ms per 800x800 frame on the C3 scene (~112k voxels, eval, early termination 0.01), extra key
 """
@@ -41,6 +46,7 @@ import numpy as np
 import torch
 
 VIEWS, RES, PIX_PER_VIEW = 4, 800, 2048
+LN_BWD_DRAM_TRAFFIC = None     # bytes per launch from ncu (filled in from profiles/r1b_ncu_ln_relu.md)
 METRIC = "rays/s (intersect+sample+composite), nsvf_base training step"
 
 
@@ -184,16 +190,20 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(n, from_host):
-        """n steps; returns (ms total via CUDA events on the launching stream, list of dominant-kernel ms)."""
+    host_ms = [0.0]
+
+    def timed(n, from_host, kname=b"ln_relu_bwd_kernel"):
+        """n steps; returns (ms total via CUDA events on the launching stream, list of the ms of kernel `kname`:
+        its last launch of each step, bracketed by events recorded on the launching stream by the library)."""
         k_evs = []
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t_host0 = time.perf_counter()
         for i in range(n):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); b.record()                                    # materialise the cudaEvent_t handles
-            _lib.check(L.nsvf_profile_kernel(b"aabb_hit_mask_kernel", a.cuda_event, b.cuda_event))
+            _lib.check(L.nsvf_profile_kernel(kname, a.cuda_event, b.cuda_event))
             if from_host:
                 hb = host[i % len(host)]
                 for d, s in zip(staging, hb):
@@ -204,6 +214,7 @@ def run_ours(args):
                 loss, out = step(*resident[i % len(resident)])
             k_evs.append((a, b))
         e1.record()
+        host_ms[0] = (time.perf_counter() - t_host0) * 1e3 / n      # host time to ENQUEUE a step (no sync)
         barrier()
         L.nsvf_profile_kernel(None, None, None)
         ms = e0.elapsed_time(e1)
@@ -219,9 +230,12 @@ def run_ours(args):
     launches0 = L.nsvf_kernel_launches()
     ms, kms, loss_val, out = timed(args.steps, False)
     launches = L.nsvf_kernel_launches() - launches0
+    host_enqueue_ms = host_ms[0]
     clocks = sampler.stop()
+    from nsvf_b200 import ops as _ops
+    ln_M, ln_N = _ops.LAST_LN_BWD_SHAPE      # the launch the events bracketed: first layer of the step's first chunk
     timed(1, True)
-    ms_e2e, _, _, _ = timed(args.steps, True)
+    ms_e2e, kms_hit, _, _ = timed(args.steps, True, b"aabb_hit_mask_kernel")
 
     rays_marched = VIEWS * PIX_PER_VIEW
     rays_intersected = VIEWS * RES * RES
@@ -229,29 +243,44 @@ def run_ours(args):
     e2e_value = world * rays_marched * args.steps / (ms_e2e / 1e3)
     h2d = sum(t.numel() * t.element_size() for t in host[0])
 
-    # roofline of the dominant hand-written kernel of the step (largest share of device time among ours, see
-    # profiles/): the any-hit intersection over all V*H*W rays.  Algorithmic bytes = 24 B/ray in + 1 B/ray out
-    # (+ 12 B/voxel once).  It is ALU/issue-bound by design (intersection is not HBM-bound), so the
-    # HBM fraction is expected to be small; the HBM-bound kernels are reported under "roofline_at_scale".
+    # roofline of the dominant hand-written kernel of the step = the one with the largest share of device time among
+    # ours (profiles/r1b_launches_step.md): ln_relu_bwd_kernel<256>, 63 launches per step.  Algorithmic bytes per
+    # launch: read h and dy, write dh (3 x 4 B per element) + mean/rstd (8 B per row) + the per-CTA
+    # partial column sums.  Timed live: the last launch of every step (M = ln_M rows, the first layer of the first
+    # chunk) between two CUDA events the library records on the launching stream.
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") else (6650.0, "fallback")
-    P = scene.max_hits
-    alg_bytes = rays_intersected * (24 + 1) + 12 * scene.n
+    step_ms = ms / args.steps
+    ln_ws = L.nsvf_ln_relu_bwd_workspace_bytes(ln_M, ln_N)
+    alg_bytes = 12 * ln_M * ln_N + 8 * ln_M + ln_ws + 8 * ln_N
     k_ms = float(np.mean(kms))
     achieved = alg_bytes / (k_ms / 1e3) / 1e9
-    roofline = {"kernel": "aabb_hit_mask_kernel (aabb_intersect_kernel<NL, any-hit>)", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 4),
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture
-                # (profiles/r1_ncu_c2_final.md: 61.5 MB + 0.4 MB), per launch
-                "traffic": 61.9e6, "peak_source": peak_src,
-                "note": "ALU/issue-bound by design (73 % issue-active in ncu, DRAM traffic == algorithmic bytes); the "
-                        "HBM-bound kernels are under roofline_at_scale",
+    roofline = {"kernel": "ln_relu_bwd_kernel<%d> (LayerNorm+ReLU backward of an FCLayer, [%d, %d] fp32)" % (ln_N, ln_M, ln_N),
+                "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4),
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one `ncu --set full`
+                # capture (profiles/r1b_ncu_ln_relu.md), per launch
+                "traffic": LN_BWD_DRAM_TRAFFIC, "peak_source": peak_src,
+                "note": "dy was written by the preceding cuBLAS GEMM and is partly still in the 126 MB L2, so DRAM "
+                        "traffic is below the algorithmic bytes and `achieved` can exceed what DRAM alone delivers",
                 "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_launch": alg_bytes,
-                "share_of_step": round(k_ms / (ms / args.steps), 4)}
+                "launches_per_step": 72, "share_of_step": round(72 * k_ms / step_ms, 4)}
+    # the dominant kernel of the ray-marching path proper: the any-hit intersection over all V*H*W rays,
+    # 24 B/ray in + 1 B/ray out (+ 12 B/voxel once).  ALU/issue-bound by design (intersection is not
+    # HBM-bound); the HBM-bound kernels of the path are measured at full-frame sizes under "roofline_at_scale".
+    P = scene.max_hits
+    hit_bytes = rays_intersected * (24 + 1) + 12 * scene.n
+    hit_ms = float(np.mean(kms_hit))
+    roofline_hot = {"kernel": "aabb_hit_mask_kernel (any-hit intersection of all %d rays)" % rays_intersected,
+                    "bound": "hbm", "achieved": round(hit_bytes / (hit_ms / 1e3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(hit_bytes / (hit_ms / 1e3) / 1e9 / peak, 4), "traffic": 61.9e6,
+                    "note": "ALU/issue-bound by design (73 % issue-active in ncu, DRAM traffic == algorithmic bytes)",
+                    "kernel_ms": round(hit_ms, 4), "algorithmic_bytes_per_launch": hit_bytes,
+                    "share_of_step": round(hit_ms / step_ms, 4)}
 
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
@@ -264,10 +293,10 @@ def run_ours(args):
                    "rays_marched_per_step_per_gpu": rays_marched, "samples_evaluated_per_step": int(out["ae"]),
                    "l2": "256 MiB memset at the start of every step (inside the timed region)",
                    "parallelism": "dp%d (rays sharded by view, voxel set replicated, NCCL grad all-reduce)" % world},
-        "clocks": clocks, "gpu_launches": int(launches),
+        "clocks": clocks, "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
         "e2e": {"value": round(e2e_value, 1), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / args.steps, 4)},
-        "roofline": roofline, "loss": round(loss_val, 5),
+        "roofline": roofline, "roofline_hot_path": roofline_hot, "loss": round(loss_val, 5),
     }
 
     if rank == 0 and not args.no_stages:

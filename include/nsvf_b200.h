@@ -265,6 +265,28 @@ NSVF_API int nsvf_ln_relu_bwd(nsvf_stream_t stream, long long M, int N, const fl
                               const float* gamma, const float* beta, const float* mean, const float* rstd, float* dh,
                               float* dgamma, float* dbeta, float* dbias, void* workspace, size_t workspace_bytes);
 
+/* NeRF positional encoding of the field inputs, NeRFPosEmbLinear(no_linear=True), fairnr/modules/module_utils.py:56-87:
+ *   x f32 [M, C]; freq f32 [L] (device; L = 4, 6 or 10); angular: t = acos(clamp(x, -1+1e-6, 1-1e-6)) else t = x;
+ *   out f32 [M, C*2L (+ C if cat_input)]: per channel c the 2L values sin(f_k t) (k < L) then cos(f_k t), then the C raw
+ *   inputs (module_utils.py:80-86: outer product, cat([sin, cos], -1), view, cat([x, inputs], -1)).
+ *   bwd (non-angular only: ray directions need no gradient): grad_x f32 [M, C]. */
+NSVF_API int nsvf_posenc_fwd(nsvf_stream_t stream, long long M, int C, int L, const float* x, const float* freq,
+                             int angular, int cat_input, float* out);
+NSVF_API int nsvf_posenc_bwd(nsvf_stream_t stream, long long M, int C, int L, const float* x, const float* freq,
+                             int cat_input, const float* grad_out, float* grad_x);
+
+/* The output heads of the field (nn.Linear(128, 1) for sigma, nn.Linear(256, 3) for rgb; fairnr/modules/field.py via
+ * FCBlock's outermost Linear, module_utils.py:114-150): y[M, O] = x[M, K] W[O, K]^T + b with O <= 4 output features.
+ * Supported (K, O): see nsvf_narrow_linear_supported.  bwd: dx f32 [M, K] (optional), dW f32 [O, K], db f32 [O]
+ * (each optional), deterministic. */
+NSVF_API int nsvf_narrow_linear_supported(int K, int O);
+NSVF_API int nsvf_narrow_linear_fwd(nsvf_stream_t stream, long long M, int K, int O, const float* x, const float* W,
+                                    const float* b, float* y);
+NSVF_API size_t nsvf_narrow_linear_bwd_workspace_bytes(long long M, int K, int O);
+NSVF_API int nsvf_narrow_linear_bwd(nsvf_stream_t stream, long long M, int K, int O, const float* x, const float* W,
+                                    const float* dy, float* dx, float* dW, float* db, void* workspace,
+                                    size_t workspace_bytes);
+
 #ifdef __cplusplus
 }
 #endif

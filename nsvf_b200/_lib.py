@@ -62,6 +62,12 @@ SIGNATURES = {
                                  c_void_p]),
     "nsvf_ln_relu_bwd_workspace_bytes": (c_size_t, [c_ll, c_int]),
     "nsvf_ln_relu_bwd": (c_int, [c_void_p, c_ll, c_int] + [c_void_p] * 11 + [c_size_t]),
+    "nsvf_posenc_fwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "nsvf_posenc_bwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "nsvf_narrow_linear_supported": (c_int, [c_int, c_int]),
+    "nsvf_narrow_linear_fwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "nsvf_narrow_linear_bwd_workspace_bytes": (c_size_t, [c_ll, c_int, c_int]),
+    "nsvf_narrow_linear_bwd": (c_int, [c_void_p, c_ll, c_int, c_int] + [c_void_p] * 7 + [c_size_t]),
     "nsvf_compact_count": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "nsvf_compact_fill": (c_int, [c_void_p, c_ll, c_int, c_int, c_int] + [c_void_p] * 12),
 }

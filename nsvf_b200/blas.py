@@ -18,7 +18,7 @@ import ctypes
 import os
 import sys
 
-_STATE = {"mode": "torch-bundled cuBLAS, fp32 SGEMM (SIMT)", "emulated": False}
+_STATE = {"mode": "torch-bundled cuBLAS, fp32 SGEMM (SIMT)", "emulated": False, "configured": False}
 _CANDIDATES = ("/usr/local/cuda/lib64", "/usr/local/cuda/targets/x86_64-linux/lib")
 
 
@@ -26,6 +26,8 @@ def use_system_cublas(emulate_fp32=True):
     """Returns True when torch will run on a cuBLAS with BF16x9 fp32 emulation enabled."""
     if os.environ.get("NSVF_NO_CUBLAS_EMULATION"):
         return False
+    if _STATE["configured"]:
+        return _STATE["emulated"]
     if "torch" in sys.modules:
         raise RuntimeError("nsvf_b200.blas.use_system_cublas() must be called before `import torch`")
     for d in _CANDIDATES:
@@ -37,6 +39,7 @@ def use_system_cublas(emulate_fp32=True):
             lib = ctypes.CDLL(bl, mode=ctypes.RTLD_GLOBAL)
         except OSError:
             continue
+        _STATE["configured"] = True
         if not hasattr(lib, "cublasSetEmulationStrategy"):      # < 12.9: no BF16x9
             _STATE["mode"] = "system cuBLAS without BF16x9 (< 12.9), fp32 SGEMM (SIMT)"
             return False

@@ -101,10 +101,21 @@ class SparseVoxelEncoder(nn.Module):
         return self.keep.long().sum()
 
     # ---- hot path -------------------------------------------------------------------------------------
+    def _kept_rows(self):
+        """Row indices of the kept voxels.  The reference boolean-indexes feats / points in every forward
+        (encoder.py:380-382), which is a nonzero() + host sync per step; the keep mask only changes when the voxels are
+        pruned or split, so the index list is cached against the mask's version counter (no device work, no sync)."""
+        key = (self.keep.data_ptr(), self.keep._version, self.keep.numel())
+        cache = self._runtime_caches.get("kept_rows")
+        if cache is None or cache[0] != key:
+            cache = (key, self.keep.bool().nonzero(as_tuple=True)[0])
+            self._runtime_caches["kept_rows"] = cache
+        return cache[1]
+
     def precompute(self, id=None, *args, **kwargs):
-        keep = self.keep.bool()
-        feats = self.feats[keep]
-        points = self.points[keep]
+        rows = self._kept_rows()
+        feats = self.feats.index_select(0, rows)
+        points = self.points.index_select(0, rows)
         points[:, 0] += (self.voxel_size / 10)      # the reference's HACK (encoder.py:383), kept for parity
         values = self.values.weight[: self.num_keys]
         encoder_states = {"voxel_vertex_idx": feats, "voxel_center_xyz": points, "voxel_vertex_emb": values}

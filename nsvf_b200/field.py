@@ -16,8 +16,12 @@ import torch.nn as nn
 
 
 class _PosEnc(nn.Module):
-    def __init__(self, in_dim, n_freq, angular, cat_input):
+    """NeRFPosEmbLinear(no_linear=True), module_utils.py:56-87.  fused=True: one hand-written kernel each way
+    (csrc/field_misc.cu) instead of outer product + sin + cos + two cats; fused=False: the reference composition."""
+
+    def __init__(self, in_dim, n_freq, angular, cat_input, fused=False):
         super().__init__()
+        self.fused = fused
         freq = torch.exp(torch.arange(n_freq, dtype=torch.float) * math.log(2.0))
         if not angular:
             freq = freq * math.pi
@@ -26,6 +30,9 @@ class _PosEnc(nn.Module):
         self.out_dim = in_dim * n_freq * 2 + (in_dim if cat_input else 0)
 
     def forward(self, x):
+        if self.fused:
+            from . import ops
+            return ops.posenc(x, self.freq, self.angular, self.cat_input)
         y = torch.acos(x.clamp(-1 + 1e-6, 1 - 1e-6)) if self.angular else x
         y = y.unsqueeze(-1) * self.freq
         y = torch.cat([torch.sin(y), torch.cos(y)], dim=-1).flatten(-2)
@@ -53,6 +60,21 @@ class _FCLayer(nn.Sequential):
         return ops.linear_layernorm_relu(x, self[0].weight, self[0].bias, self[1].weight, self[1].bias, self[1].eps)
 
 
+class _Head(nn.Linear):
+    """Output head (Linear with 1 or 3 output features).  fused=True: streaming kernels of csrc/field_misc.cu (cuBLAS
+    has no tensor-core shape for them and spends 130 us on the weight gradient alone); fused=False: nn.Linear."""
+
+    def __init__(self, i, o, fused):
+        super().__init__(i, o)
+        self.fused = fused
+
+    def forward(self, x):
+        if not self.fused:
+            return super().forward(x)
+        from . import ops
+        return ops.narrow_linear(x, self.weight, self.bias)
+
+
 class RadianceField(nn.Module):
     def __init__(self, embed_dim=32, feat_dim=256, density_dim=128, texture_dim=256, texture_layers=3,
                  feature_layers=1, bg_color=(1.0, 1.0, 1.0), sigma_bias=0.0, fused=True):
@@ -60,13 +82,13 @@ class RadianceField(nn.Module):
 
         def _fc(i, o):
             return _FCLayer(i, o, fused)
-        self.emb_enc = _PosEnc(embed_dim, 6, angular=False, cat_input=True)
-        self.ray_enc = _PosEnc(3, 4, angular=True, cat_input=False)
+        self.emb_enc = _PosEnc(embed_dim, 6, angular=False, cat_input=True, fused=fused)
+        self.ray_enc = _PosEnc(3, 4, angular=True, cat_input=False, fused=fused)
         dims = [self.emb_enc.out_dim] + [feat_dim] * (feature_layers + 2)
         self.feature_field = nn.Sequential(*[_fc(a, b) for a, b in zip(dims[:-1], dims[1:])])
-        self.predictor = nn.Sequential(_fc(feat_dim, density_dim), nn.Linear(density_dim, 1))
+        self.predictor = nn.Sequential(_fc(feat_dim, density_dim), _Head(density_dim, 1, fused))
         tdims = [feat_dim + self.ray_enc.out_dim] + [texture_dim] * (texture_layers + 1)
-        self.renderer = nn.Sequential(*[_fc(a, b) for a, b in zip(tdims[:-1], tdims[1:])], nn.Linear(texture_dim, 3))
+        self.renderer = nn.Sequential(*[_fc(a, b) for a, b in zip(tdims[:-1], tdims[1:])], _Head(texture_dim, 3, fused))
         # transparent_background "1,1,1" with min_color -1 -> b*2-1; background_stop_gradient -> no grad
         self.bg_color = nn.Parameter(torch.tensor([b * 2 - 1 for b in bg_color]), requires_grad=False)
         if sigma_bias:

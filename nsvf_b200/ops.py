@@ -156,6 +156,7 @@ class LinearLayerNormReLU(Function):
             z = torch.zeros_like
             return x2.new_zeros(*ctx.lead, x2.shape[-1]), z(w), z(g), z(g), z(g), None
         dy2 = dy.reshape(M, N).float().contiguous()
+        LAST_LN_BWD_SHAPE[:] = [M, N]          # read by bench.py: shape of the most recent ln_relu_bwd launch
         dh = torch.empty_like(h)
         sums = torch.empty(3, N, dtype=torch.float32, device=dev)      # d gamma, d beta, d bias
         with torch.cuda.device(dev):
@@ -169,6 +170,7 @@ class LinearLayerNormReLU(Function):
 
 
 _DW_SPLIT = 16
+LAST_LN_BWD_SHAPE = [0, 0]
 
 
 def _weight_grad(dh, x2):
@@ -190,6 +192,99 @@ def _weight_grad(dh, x2):
 def linear_layernorm_relu(x, weight, bias, gamma, beta, eps=1e-5):
     """FCLayer forward (module_utils.py:97-111) on cuBLAS + the fused LayerNorm/ReLU kernels."""
     return LinearLayerNormReLU.apply(x, weight, bias, gamma, beta, eps)
+
+
+class PosEnc(Function):
+    """NeRFPosEmbLinear(no_linear=True) (module_utils.py:56-87) as one pass; differentiable for the non-angular case."""
+
+    @staticmethod
+    def forward(ctx, x, freq, angular, cat_input):
+        _need_cuda(x=x, freq=freq)
+        if x.dtype != torch.float32:
+            raise RuntimeError("nsvf_b200: posenc is float32 only")
+        lead, C = x.shape[:-1], x.shape[-1]
+        x2 = x.detach().reshape(-1, C).contiguous()
+        f = freq.detach().float().contiguous()
+        M, L = x2.shape[0], f.numel()
+        out = torch.empty(M, C * 2 * L + (C if cat_input else 0), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_L.nsvf_posenc_fwd(_lib.current_stream(x.device), M, C, L, _p(x2), _p(f), int(bool(angular)),
+                                          int(bool(cat_input)), _p(out)))
+        ctx.save_for_backward(x2, f)
+        ctx.meta = (lead, C, bool(angular), bool(cat_input))
+        return out.reshape(*lead, out.shape[-1])
+
+    @staticmethod
+    def backward(ctx, g):
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None
+        x2, f = ctx.saved_tensors
+        lead, C, angular, cat_input = ctx.meta
+        if angular:
+            raise RuntimeError("nsvf_b200: posenc backward is implemented for the non-angular encoding only "
+                               "(ray directions carry no gradient)")
+        M, L = x2.shape[0], f.numel()
+        g2 = g.reshape(M, -1).float().contiguous()
+        gx = torch.empty_like(x2)
+        with torch.cuda.device(x2.device):
+            _lib.check(_L.nsvf_posenc_bwd(_lib.current_stream(x2.device), M, C, L, _p(x2), _p(f), int(cat_input), _p(g2),
+                                          _p(gx)))
+        return gx.reshape(*lead, C), None, None, None
+
+
+def posenc(x, freq, angular=False, cat_input=False):
+    """[..., C] -> [..., C*2L (+C)]: per channel sin(f_k t) (k < L) then cos(f_k t); t = acos(clamp(x)) if angular."""
+    return PosEnc.apply(x, freq, angular, cat_input)
+
+
+class NarrowLinear(Function):
+    """y = x W^T + b for a Linear with 1..4 output features (the sigma / rgb heads): streaming kernels, no GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _need_cuda(x=x, weight=weight)
+        if x.dtype != torch.float32 or weight.dtype != torch.float32:
+            raise RuntimeError("nsvf_b200: narrow_linear is float32 only")
+        lead, K = x.shape[:-1], x.shape[-1]
+        O = weight.shape[0]
+        x2 = x.detach().reshape(-1, K).contiguous()
+        w = weight.detach().contiguous()
+        b = bias.detach().contiguous() if bias is not None else None
+        M = x2.shape[0]
+        y = torch.empty(M, O, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_L.nsvf_narrow_linear_fwd(_lib.current_stream(x.device), M, K, O, _p(x2), _p(w), _p(b), _p(y)))
+        ctx.save_for_backward(x2, w)
+        ctx.meta = (lead, bias is not None)
+        return y.reshape(*lead, O)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        lead, has_bias = ctx.meta
+        M, K = x2.shape
+        O = w.shape[0]
+        dev = x2.device
+        if M == 0:
+            return x2.new_zeros(*lead, K), torch.zeros_like(w), (w.new_zeros(O) if has_bias else None)
+        dy2 = dy.reshape(M, O).float().contiguous()
+        dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w)
+        db = torch.empty(O, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws_bytes = _L.nsvf_narrow_linear_bwd_workspace_bytes(M, K, O)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _lib.check(_L.nsvf_narrow_linear_bwd(_lib.current_stream(dev), M, K, O, _p(x2), _p(w), _p(dy2), _p(dx), _p(dw),
+                                                 _p(db), _p(ws), ws_bytes))
+        return (dx.reshape(*lead, K) if dx is not None else None), dw, (db if has_bias else None)
+
+
+def narrow_linear_supported(in_features, out_features):
+    return bool(_L.nsvf_narrow_linear_supported(int(in_features), int(out_features)))
+
+
+def narrow_linear(x, weight, bias=None):
+    return NarrowLinear.apply(x, weight, bias)
 
 
 class FillInBlend(Function):

@@ -54,6 +54,57 @@ def test_linear_layernorm_relu_forward_backward(cuda, M, I, N):
         assert torch.equal(a, c)
 
 
+@pytest.mark.parametrize("M,C,L,angular,cat", [(70001, 32, 6, False, True), (33333, 3, 4, True, False),
+                                                (1, 32, 6, False, True), (4097, 5, 10, False, False)])
+def test_posenc_matches_reference_composition(cuda, M, C, L, angular, cat):
+    from nsvf_b200.field import _PosEnc
+    plain = _PosEnc(C, L, angular, cat, fused=False).to(cuda)
+    gen = torch.Generator(device=cuda).manual_seed(M)
+    x = torch.randn(M, C, device=cuda, generator=gen) * (0.5 if not angular else 1.0)
+    if angular:
+        x = F.normalize(x, dim=-1)
+    ref = plain(x)
+    out = ops.posenc(x, plain.freq, angular, cat)
+    assert out.shape == ref.shape
+    # same op sequence (one fp32 product, sinf / cosf): values agree to the last ulps of sin / cos of arguments <= 1e3
+    torch.testing.assert_close(out, ref, rtol=0, atol=2e-6)
+    if not angular:
+        g = torch.randn(ref.shape, device=cuda, generator=gen)
+        xr = x.clone().requires_grad_(True)
+        (gx,) = torch.autograd.grad(ops.posenc(xr, plain.freq, angular, cat), xr, g)
+        x64 = x.double().requires_grad_(True)
+        y64 = x64.unsqueeze(-1) * plain.freq.double()
+        y64 = torch.cat([torch.sin(y64), torch.cos(y64)], -1).flatten(-2)
+        y64 = torch.cat([y64, x64], -1) if cat else y64
+        (g64,) = torch.autograd.grad(y64, x64, g.double())
+        # arguments reach 32*pi*|x| ~ 300: the fp32 rounding of f_k*x alone moves sin/cos by ~2e-5, as it does in torch
+        xt = x.clone().requires_grad_(True)
+        (gt,) = torch.autograd.grad(plain(xt), xt, g)
+        err_ours, err_torch = (gx.double() - g64).abs().max(), (gt.double() - g64).abs().max()
+        assert float(err_ours) <= 2.0 * float(err_torch) + 1e-6 * float(g64.abs().max()), (float(err_ours), float(err_torch))
+
+
+@pytest.mark.parametrize("M,K,O", [(70001, 256, 3), (65536, 128, 1), (5, 256, 3), (1, 128, 1), (9999, 256, 4)])
+def test_narrow_linear_forward_backward(cuda, M, K, O):
+    assert ops.narrow_linear_supported(K, O) and not ops.narrow_linear_supported(K, 7)
+    gen = torch.Generator(device=cuda).manual_seed(M + O)
+    x = torch.randn(M, K, device=cuda, generator=gen)
+    w = torch.randn(O, K, device=cuda, generator=gen) * K ** -0.5
+    b = torch.randn(O, device=cuda, generator=gen)
+    dy = torch.randn(M, O, device=cuda, generator=gen)
+    ins = [t.clone().requires_grad_(True) for t in (x, w, b)]
+    y = ops.narrow_linear(*ins)
+    ins64 = [t.double().requires_grad_(True) for t in (x, w, b)]
+    y64 = F.linear(*ins64)
+    helpers.assert_close_scaled(y, y64, what="y")
+    grads = torch.autograd.grad(y, ins, dy)
+    ref = torch.autograd.grad(y64, ins64, dy.double())
+    for name, a, r in zip(("dx", "dW", "db"), grads, ref):
+        helpers.assert_close_scaled(a, r, what=name)
+    again = torch.autograd.grad(ops.narrow_linear(*ins), ins, dy)
+    assert all(torch.equal(a, c) for a, c in zip(grads, again))            # deterministic
+
+
 def test_fused_field_matches_reference_composition(cuda):
     torch.manual_seed(0)
     fused = RadianceField(sigma_bias=0.3).to(cuda)
