@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--mlp-gemm", default="bf16x9", choices=["bf16x9", "simt"],
                     help="fp32 GEMMs of the field MLP: cuBLAS 12.9 BF16x9 emulation on tensor cores (fp32-accurate) "
                          "or torch's bundled cuBLAS SGEMM on the SIMT pipe")
+    ap.add_argument("--no-graphs", action="store_true", help="launch the field MLP kernel by kernel instead of replaying "
+                                                               "one CUDA graph per renderer chunk")
     ap.add_argument("--cpu-fraction", type=int, default=16, help="CPU arms run 1/FRACTION of the rays per step")
     return ap.parse_args()
 
@@ -127,7 +129,8 @@ def make_batches(n_batches, rank, pinned):
     return out
 
 
-def build_model(device, scene_name="C2", train=True, field="mlp", tolerance=0.0, chunk=64, sigma_bias=0.0, seed=0):
+def build_model(device, scene_name="C2", train=True, field="mlp", tolerance=0.0, chunk=64, sigma_bias=0.0, seed=0,
+                graphs=False):
     from nsvf_b200 import synthetic
     from nsvf_b200.encoder import SparseVoxelEncoder
     from nsvf_b200.field import RadianceField, TrivialField
@@ -137,6 +140,9 @@ def build_model(device, scene_name="C2", train=True, field="mlp", tolerance=0.0,
     scene = synthetic.make_scene(scene_name)
     enc = SparseVoxelEncoder(scene.points, scene.voxel_size, max_hits=scene.max_hits)
     fld = RadianceField(sigma_bias=sigma_bias) if field == "mlp" else TrivialField()
+    if graphs and field == "mlp" and train:
+        from nsvf_b200.field import GraphedField
+        fld = GraphedField(fld, rows=1024 * chunk, eager_first=1)   # first chunk eager: live kernel timing
     ren = VolumeRenderer(chunk_size=chunk, discrete_regularization=train, raymarching_tolerance=tolerance)
     pipe = NSVFPipeline(enc, fld, ren, pixel_per_view=PIX_PER_VIEW if train else 0).to(device)
     return pipe.train(train), scene
@@ -165,11 +171,15 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    pipe, scene = build_model(dev)
+    pipe, scene = build_model(dev, graphs=not args.no_graphs)
+    if hasattr(pipe.field, "capture"):
+        pipe.field.capture(dev)          # CUDA graphs of the field's chunk forward / backward, before any eager pass
     model = pipe
     if world > 1:
         from torch.nn.parallel import DistributedDataParallel as DDP
-        model = DDP(pipe, device_ids=[local])   # NCCL all-reduce of values.weight.grad + MLP grads
+        # NCCL all-reduce of values.weight.grad + MLP grads; the voxel buffers are replicated and deterministic, so
+        # DDP's per-forward buffer broadcast is off
+        model = DDP(pipe, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True)
     opt = torch.optim.Adam([p for p in pipe.parameters() if p.requires_grad], lr=1e-3, betas=(0.9, 0.999))
     host = make_batches(2, rank, pinned=True)
     resident = [tuple(t.to(dev) for t in b) for b in host]
@@ -228,8 +238,11 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = L.nsvf_kernel_launches()
+    replays0 = getattr(pipe.field, "graph_replays", 0)
     ms, kms, loss_val, out = timed(args.steps, False)
-    launches = L.nsvf_kernel_launches() - launches0
+    # kernels of libnsvf_b200.so launched in the timed region: from the host + inside the replayed chunk graphs
+    replays = getattr(pipe.field, "graph_replays", 0) - replays0
+    launches = L.nsvf_kernel_launches() - launches0 + replays * getattr(pipe.field, "launches_per_replay", 0)
     host_enqueue_ms = host_ms[0]
     clocks = sampler.stop()
     from nsvf_b200 import ops as _ops
@@ -289,11 +302,14 @@ def run_ours(args):
         "config": {"workload": "C2: nsvf_base training step, 343 voxels (voxel 0.4, step 1/8, max_hits 60), "
                                "4 views x 800x800 rays intersected + 4 x 2048 rays marched per GPU, fwd+bwd+Adam, "
                                "field MLP fp32 on cuBLAS", "mlp_gemm": _blas.mode(),
+                   "mlp_launch": ("one CUDA graph per full renderer chunk (forward + backward), first chunk eager"
+                                  if hasattr(pipe.field, "graph_replays") else "kernel by kernel"),
                    "rays_intersected_per_step_per_gpu": rays_intersected,
                    "rays_marched_per_step_per_gpu": rays_marched, "samples_evaluated_per_step": int(out["ae"]),
                    "l2": "256 MiB memset at the start of every step (inside the timed region)",
                    "parallelism": "dp%d (rays sharded by view, voxel set replicated, NCCL grad all-reduce)" % world},
-        "clocks": clocks, "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
+        "clocks": clocks, "gpu_launches": int(launches), "cuda_graph_replays": int(replays),
+        "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
         "e2e": {"value": round(e2e_value, 1), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / args.steps, 4)},
         "roofline": roofline, "roofline_hot_path": roofline_hot, "loss": round(loss_val, 5),

@@ -41,6 +41,10 @@ static char g_prof_name[64] = "";
 static cudaEvent_t g_prof_ev[2] = {nullptr, nullptr};
 void profile_mark(const char* name, int which, cudaStream_t stream) {
   if (g_prof_name[0] == 0 || strcmp(name, g_prof_name) != 0 || g_prof_ev[which] == nullptr) return;
+  // launches that are being captured into a CUDA graph are not timed: recording a caller's event on a capturing
+  // stream would tie it to the capture (and invalidate it once the event is used outside)
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return;
   cudaEventRecord(g_prof_ev[which], stream);
 }
 

@@ -106,6 +106,95 @@ class RadianceField(nn.Module):
         return inputs
 
 
+class _FieldCore(nn.Module):
+    """Tensor-in / tensor-out view of a RadianceField (what torch.cuda.make_graphed_callables can capture)."""
+
+    def __init__(self, field):
+        super().__init__()
+        self.field = field
+
+    def forward(self, emb, ray):
+        out = self.field({"emb": emb, "ray": ray})
+        return out["sigma"], out["texture"]
+
+
+class GraphedField(nn.Module):
+    """CUDA-graph replay of the field's forward and backward for the full-size chunks of a training step.
+
+    A training step evaluates the field once per renderer chunk (<= chunk_size = 65536 samples, renderer.py:56): nine
+    layers, ~45 kernel launches forward and ~70 backward per chunk, ten chunks per step.  Launched one by one from Python
+    that is ~19 ms of host time per step, as long as the kernels themselves take on a B200, so the step is launch-bound.
+    Every chunk has the same structure, so it is captured once per chunk slot (torch.cuda.make_graphed_callables: one
+    forward and one backward graph per slot, all slots in one memory pool, replayed in capture order fwd 1..k,
+    bwd k..1) on inputs padded to `rows`; the outputs are sliced back, so padding rows get zero gradient.
+    Chunks that are much smaller than `rows` (the last one of a step), extra chunks beyond `slots`, evaluation, and calls
+    that ask for one output only run eagerly on the wrapped field — same kernels, same results."""
+
+    def __init__(self, field, rows=65536, slots=10, min_fill=0.6, eager_first=0):
+        super().__init__()
+        self.field = field
+        self.rows, self.slots, self.min_fill = rows, slots, min_fill
+        self.eager_first = eager_first      # bench.py keeps the first chunk of a step eager: its kernels are then
+        self._calls = 0                     # launched from the host, where the library's event hook can time them
+        self._graphed = None
+        self._next = 0
+        self.graph_replays = 0
+        self.launches_per_replay = 0
+
+    @property
+    def bg_color(self):
+        return self.field.bg_color
+
+    def begin_step(self):
+        self._next = 0
+        self._calls = 0
+
+    def capture(self, dev, embed_dim=32):
+        """Capture the chunk graphs.  Must run before any eager forward of the field whose autograd graph is still alive:
+        such a graph holds AccumulateGrad nodes bound to the default stream, and the engine's stream hand-over to them
+        inside the backward capture would invalidate it (torch warns about exactly this).  bench.py calls it right
+        after building the model; otherwise it runs at the first training call."""
+        if self._graphed is None:
+            self._capture(dev, embed_dim)
+
+    def _capture(self, dev, embed_dim):
+        cores = tuple(_FieldCore(self.field) for _ in range(self.slots))
+        args = tuple((torch.zeros(self.rows, embed_dim, device=dev, requires_grad=True),
+                      torch.nn.functional.normalize(torch.ones(self.rows, 3, device=dev), dim=-1))
+                     for _ in range(self.slots))
+        from . import _lib
+        n0 = _lib.load().nsvf_kernel_launches()
+        warmup = 3
+        self._graphed = torch.cuda.make_graphed_callables(cores, args, num_warmup_iters=warmup)
+        # kernels of this library inside one replayed chunk (forward + backward graph): every slot ran `warmup` eager
+        # iterations and one capture, each launching the same kernels
+        self.launches_per_replay = (_lib.load().nsvf_kernel_launches() - n0) // (self.slots * (warmup + 1))
+
+    def forward(self, inputs, outputs=("sigma", "texture")):
+        emb = inputs.get("emb", None)
+        M = 0 if emb is None else emb.shape[0]
+        use_graph = (self.training and torch.is_grad_enabled() and emb is not None and emb.is_cuda
+                     and inputs.get("feat", None) is None and "sigma" in outputs and "texture" in outputs
+                     and emb.requires_grad and emb.dim() == 2
+                     and self.rows * self.min_fill <= M <= self.rows and self._next < self.slots
+                     and self._calls >= self.eager_first)
+        self._calls += 1
+        if self._graphed is None and self.training and torch.is_grad_enabled() and emb is not None and emb.is_cuda:
+            self._capture(emb.device, emb.shape[1])       # first training call: before any eager graph exists
+        if not use_graph:
+            return self.field(inputs, outputs)
+        pad = self.rows - M
+        ray = inputs["ray"]
+        if pad:
+            emb = torch.nn.functional.pad(emb, (0, 0, 0, pad))
+            ray = torch.nn.functional.pad(ray, (0, 0, 0, pad))
+        sigma, texture = self._graphed[self._next](emb.contiguous(), ray.contiguous())
+        self._next += 1
+        self.graph_replays += 1
+        inputs["sigma"], inputs["texture"] = sigma[:M], texture[:M]
+        return inputs
+
+
 class TrivialField(nn.Module):
     """Stand-in field without any dense contraction: isolates the hand-written path in benches/tests."""
 

@@ -88,6 +88,9 @@ class NSVFPipeline(nn.Module):
     def forward(self, ray_start, ray_dir):
         S, V, P, _ = ray_dir.size()
         assert S == 1, "single object only, like the reference (fairnr_model.py:144)"
+        for f in (self.field, self.field_fine):
+            if hasattr(f, "begin_step"):      # GraphedField: chunk slots are replayed in capture order within a step
+                f.begin_step()
         encoder_states = self.encoder.precompute(id=torch.zeros(1, dtype=torch.long, device=ray_dir.device))
         ray_start, ray_dir, inter, hits, sampled = self.intersecting(ray_start, ray_dir, encoder_states)
         n_rays = ray_dir.size(1)

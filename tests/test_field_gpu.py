@@ -160,3 +160,39 @@ def test_cublas_bf16x9_emulation_is_fp32_accurate(cuda):
         assert r["fwd_err"] < 1e-6 and r["dx_err"] < 1e-6 and r["dw_err"] < 1e-6, r
     for k, v in out["fc_layer"].items():
         assert v < helpers.RTOL, (k, v)
+
+
+def test_graphed_field_replays_match_eager(cuda):
+    """GraphedField (CUDA-graph replay per renderer chunk, padded to `rows`) against the eager field: three chunks per
+    step (two graphed with different fill, one too small -> eager), two steps, so that replays are exercised."""
+    from nsvf_b200.field import GraphedField
+    torch.manual_seed(1)
+    eager = RadianceField(sigma_bias=0.2).to(cuda)
+    graphed = GraphedField(RadianceField().to(cuda), rows=4096, slots=3)
+    graphed.field.load_state_dict(eager.state_dict())
+    graphed.train(); eager.train()
+    for step in range(2):
+        graphed.begin_step()
+        gen = torch.Generator(device=cuda).manual_seed(10 + step)
+        for f in (eager, graphed):
+            f.zero_grad(set_to_none=True)
+        losses = []
+        for f in (eager, graphed):
+            gen.manual_seed(10 + step)
+            total, embs = 0, []
+            for M in (4096, 3000, 700):
+                emb = (torch.randn(M, 32, device=cuda, generator=gen) * 0.2).requires_grad_(True)
+                ray = F.normalize(torch.randn(M, 3, device=cuda, generator=gen), dim=-1)
+                w = torch.randn(M, 4, device=cuda, generator=gen)
+                o = f({"emb": emb, "ray": ray})
+                total = total + (o["sigma"] * w[:, 0]).sum() + (o["texture"] * w[:, 1:]).sum()
+                embs.append(emb)
+            total.backward()
+            losses.append((total.detach(), [e.grad for e in embs]))
+        assert graphed.graph_replays == 2 * (step + 1)
+        helpers.assert_close_scaled(losses[1][0], losses[0][0], rtol=1e-5, what="loss")
+        for a, b in zip(losses[1][1], losses[0][1]):
+            assert torch.equal(a, b) or float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
+        for (k, p), (_, q) in zip(graphed.field.named_parameters(), eager.named_parameters()):
+            if q.grad is not None:
+                helpers.assert_close_scaled(p.grad, q.grad, rtol=1e-5, what=k)
