@@ -46,7 +46,7 @@ import numpy as np
 import torch
 
 VIEWS, RES, PIX_PER_VIEW = 4, 800, 2048
-LN_BWD_DRAM_TRAFFIC = None     # bytes per launch from ncu (filled in from profiles/r1b_ncu_ln_relu.md)
+LN_BWD_DRAM_TRAFFIC = 149.0e6  # bytes per launch: dram read 135 MB + write 14 MB, ncu --set full, [65536, 256] (profiles/r1b_ncu_ln_relu.md)
 METRIC = "rays/s (intersect+sample+composite), nsvf_base training step"
 
 
