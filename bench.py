@@ -486,7 +486,7 @@ def cpu_arm(steps, warmup, fraction):
     import oracle
     from oracle import wrappers
     from nsvf_b200 import synthetic
-    from nsvf_b200.field import RadianceField
+    from oracle.field_ref import ReferenceRadianceField      # the reference's plain-torch composition of the MLP
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
@@ -495,7 +495,7 @@ def cpu_arm(steps, warmup, fraction):
     pts = scene.points.copy()
     pts[:, 0] += np.float32(scene.voxel_size / 10)
     torch.manual_seed(0)
-    field = RadianceField(fused=False)      # the reference composition in plain torch (CPU)
+    field = ReferenceRadianceField()
     values = torch.from_numpy(scene.values.copy()).requires_grad_(True)
     opt = torch.optim.Adam(list(p for p in field.parameters() if p.requires_grad) + [values], lr=1e-3)
     pix = RES * RES // fraction

@@ -1,27 +1,30 @@
-"""The radiance-field MLP of the `nsvf_base` architecture, on torch / cuBLAS tensor cores.
-
-NOT part of the hand-written hot path: BASELINE.json's north_star keeps the field MLP ("a dense
-contraction") on torch/cuBLAS.  It exists so that bench.py can run the named training / rendering step
-with random-init weights of the reference architecture (fairnr/models/nsvf.py:168-211 presets;
-fairnr/modules/field.py:60-279, implicit.py:41-150, module_utils.py:56-111): 545 297 parameters.
+"""The radiance-field MLP of the `nsvf_base` architecture (fairnr/models/nsvf.py:168-211 presets;
+fairnr/modules/field.py:60-279, implicit.py:41-150, module_utils.py:56-150): 545 297 parameters.
 
     density  : emb[32] -> posenc(L=6, cat input) = 416 -> 3 x (Linear 256 + LayerNorm + ReLU) = feat[256]
                -> Linear 128 + LayerNorm + ReLU -> Linear 1 = sigma
     texture  : [feat 256, posenc_angular(ray, L=4) = 24] = 280 -> 4 x (Linear 256 + LN + ReLU) -> Linear 3
+
+BASELINE.json's north_star keeps the field's dense contractions on torch/cuBLAS tensor cores (nsvf_b200/blas.py selects
+cuBLAS 12.9's fp32-accurate BF16x9 algorithm); every other pass — LayerNorm + ReLU forward/backward with the bias /
+gamma / beta reductions, the positional encodings, the 1- and 3-wide output heads — runs in the hand-written kernels of
+csrc/field_norm.cu and csrc/field_misc.cu, and GraphedField replays a whole chunk's forward / backward as CUDA graphs.
+CUDA only, no fallback: the plain-torch composition of the same network is oracle/field_ref.py (test infrastructure).
 """
 import math
 
 import torch
 import torch.nn as nn
 
+from . import ops
+
 
 class _PosEnc(nn.Module):
-    """NeRFPosEmbLinear(no_linear=True), module_utils.py:56-87.  fused=True: one hand-written kernel each way
-    (csrc/field_misc.cu) instead of outer product + sin + cos + two cats; fused=False: the reference composition."""
+    """NeRFPosEmbLinear(no_linear=True), module_utils.py:56-87, as one hand-written kernel each way
+    (csrc/field_misc.cu) instead of outer product + sin + cos + two cats."""
 
-    def __init__(self, in_dim, n_freq, angular, cat_input, fused=False):
+    def __init__(self, in_dim, n_freq, angular, cat_input):
         super().__init__()
-        self.fused = fused
         freq = torch.exp(torch.arange(n_freq, dtype=torch.float) * math.log(2.0))
         if not angular:
             freq = freq * math.pi
@@ -30,65 +33,45 @@ class _PosEnc(nn.Module):
         self.out_dim = in_dim * n_freq * 2 + (in_dim if cat_input else 0)
 
     def forward(self, x):
-        if self.fused:
-            from . import ops
-            return ops.posenc(x, self.freq, self.angular, self.cat_input)
-        y = torch.acos(x.clamp(-1 + 1e-6, 1 - 1e-6)) if self.angular else x
-        y = y.unsqueeze(-1) * self.freq
-        y = torch.cat([torch.sin(y), torch.cos(y)], dim=-1).flatten(-2)
-        return torch.cat([y, x], -1) if self.cat_input else y
+        return ops.posenc(x, self.freq, self.angular, self.cat_input)
 
 
 class _FCLayer(nn.Sequential):
     """FCLayer of the reference (module_utils.py:97-111): Linear -> LayerNorm([o]) -> ReLU, same parameter names
-    ("0.weight", "0.bias", "1.weight", "1.bias").  fused=True (the product path, CUDA only, no fallback) runs the
-    contractions on cuBLAS and everything else in the hand-written kernels of csrc/field_norm.cu: torch's own
-    LayerNorm backward (GammaBetaBackwardCUDAKernel) plus the bias-gradient column reductions cost 0.5 ms per call on
-    tall [65536, 256] activations, 40 % of the whole training step.  fused=False is the reference composition in plain
-    torch, used by bench.py's CPU reference arm and as the comparison in tests."""
+    ("0.weight", "0.bias", "1.weight", "1.bias").  The contraction runs on cuBLAS, everything else in the hand-written
+    kernels of csrc/field_norm.cu: torch's own LayerNorm backward (GammaBetaBackwardCUDAKernel) plus the bias-gradient
+    column reductions cost 0.5 ms per call on tall [65536, 256] activations, 40 % of the whole training step.  CUDA
+    only, no fallback; the plain-torch composition lives in oracle/field_ref.py (test yardstick, CPU reference arm)."""
 
-    def __init__(self, i, o, fused):
+    def __init__(self, i, o):
         lin = nn.Linear(i, o)
         nn.init.kaiming_normal_(lin.weight, a=0.0, nonlinearity="relu", mode="fan_in")
         super().__init__(lin, nn.LayerNorm([o]), nn.ReLU())
-        self.fused = fused
 
     def forward(self, x):
-        if not self.fused:
-            return super().forward(x)
-        from . import ops
         return ops.linear_layernorm_relu(x, self[0].weight, self[0].bias, self[1].weight, self[1].bias, self[1].eps)
 
 
 class _Head(nn.Linear):
-    """Output head (Linear with 1 or 3 output features).  fused=True: streaming kernels of csrc/field_misc.cu (cuBLAS
-    has no tensor-core shape for them and spends 130 us on the weight gradient alone); fused=False: nn.Linear."""
-
-    def __init__(self, i, o, fused):
-        super().__init__(i, o)
-        self.fused = fused
+    """Output head (Linear with 1 or 3 output features): streaming kernels of csrc/field_misc.cu — cuBLAS has no
+    tensor-core shape for them and spends 130 us on the weight gradient alone."""
 
     def forward(self, x):
-        if not self.fused:
-            return super().forward(x)
-        from . import ops
         return ops.narrow_linear(x, self.weight, self.bias)
 
 
 class RadianceField(nn.Module):
     def __init__(self, embed_dim=32, feat_dim=256, density_dim=128, texture_dim=256, texture_layers=3,
-                 feature_layers=1, bg_color=(1.0, 1.0, 1.0), sigma_bias=0.0, fused=True):
+                 feature_layers=1, bg_color=(1.0, 1.0, 1.0), sigma_bias=0.0):
         super().__init__()
-
-        def _fc(i, o):
-            return _FCLayer(i, o, fused)
-        self.emb_enc = _PosEnc(embed_dim, 6, angular=False, cat_input=True, fused=fused)
-        self.ray_enc = _PosEnc(3, 4, angular=True, cat_input=False, fused=fused)
+        _fc = _FCLayer
+        self.emb_enc = _PosEnc(embed_dim, 6, angular=False, cat_input=True)
+        self.ray_enc = _PosEnc(3, 4, angular=True, cat_input=False)
         dims = [self.emb_enc.out_dim] + [feat_dim] * (feature_layers + 2)
         self.feature_field = nn.Sequential(*[_fc(a, b) for a, b in zip(dims[:-1], dims[1:])])
-        self.predictor = nn.Sequential(_fc(feat_dim, density_dim), _Head(density_dim, 1, fused))
+        self.predictor = nn.Sequential(_fc(feat_dim, density_dim), _Head(density_dim, 1))
         tdims = [feat_dim + self.ray_enc.out_dim] + [texture_dim] * (texture_layers + 1)
-        self.renderer = nn.Sequential(*[_fc(a, b) for a, b in zip(tdims[:-1], tdims[1:])], _Head(texture_dim, 3, fused))
+        self.renderer = nn.Sequential(*[_fc(a, b) for a, b in zip(tdims[:-1], tdims[1:])], _Head(texture_dim, 3))
         # transparent_background "1,1,1" with min_color -1 -> b*2-1; background_stop_gradient -> no grad
         self.bg_color = nn.Parameter(torch.tensor([b * 2 - 1 for b in bg_color]), requires_grad=False)
         if sigma_bias:

@@ -53,6 +53,9 @@ def test_no_cpu_fallback():
     with pytest.raises(RuntimeError, match="must be an int tensor"):
         f = torch.zeros(1, 2, 3)
         _ext.inverse_cdf_sampling(f.clone(), f, f, f, f, torch.zeros(1, 2), -1.0)     # pts_idx is float, not int
+    from nsvf_b200.field import RadianceField
+    with pytest.raises(RuntimeError, match="CUDA"):        # the field's fused passes have no CPU path either
+        RadianceField()({"emb": torch.zeros(3, 32), "ray": torch.tensor([[0., 0., 1.]] * 3)})
     import nsvf_b200
     src = "".join(open(os.path.join(os.path.dirname(nsvf_b200.__file__), f)).read()
                   for f in os.listdir(os.path.dirname(nsvf_b200.__file__)) if f.endswith(".py"))

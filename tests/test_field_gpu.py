@@ -1,6 +1,6 @@
-"""GPU numerics of the fused FCLayer passes (csrc/field_norm.cu, ops.linear_layernorm_relu) against the reference
-composition nn.Linear -> nn.LayerNorm -> nn.ReLU (fairnr/modules/module_utils.py:97-111) in plain PyTorch on the same
-device: fp32 for the forward, float64 autograd for the gradients (column sums over ~1e5 rows: the fp32 torch result
+"""GPU numerics of the fused field passes (csrc/field_norm.cu, csrc/field_misc.cu, ops.linear_layernorm_relu / posenc /
+narrow_linear, GraphedField) against the reference composition (oracle/field_ref.py: nn.Linear -> nn.LayerNorm -> nn.ReLU
+etc., fairnr/modules/module_utils.py:56-150) in plain PyTorch on the same device: fp32 for the forward, float64 autograd for the gradients (column sums over ~1e5 rows: the fp32 torch result
 itself carries summation-order error, so the yardstick is the float64 value).
 
 Tolerance: helpers.RTOL = 1e-5 relative to the tensor's scale (BASELINE.json north_star)."""
@@ -15,6 +15,7 @@ import torch.nn.functional as F
 
 from nsvf_b200 import ops
 from nsvf_b200.field import RadianceField
+from oracle.field_ref import PosEnc as RefPosEnc, ReferenceRadianceField
 from tests import helpers
 
 pytestmark = pytest.mark.gpu
@@ -57,8 +58,7 @@ def test_linear_layernorm_relu_forward_backward(cuda, M, I, N):
 @pytest.mark.parametrize("M,C,L,angular,cat", [(70001, 32, 6, False, True), (33333, 3, 4, True, False),
                                                 (1, 32, 6, False, True), (4097, 5, 10, False, False)])
 def test_posenc_matches_reference_composition(cuda, M, C, L, angular, cat):
-    from nsvf_b200.field import _PosEnc
-    plain = _PosEnc(C, L, angular, cat, fused=False).to(cuda)
+    plain = RefPosEnc(C, L, angular, cat).to(cuda)
     gen = torch.Generator(device=cuda).manual_seed(M)
     x = torch.randn(M, C, device=cuda, generator=gen) * (0.5 if not angular else 1.0)
     if angular:
@@ -108,7 +108,7 @@ def test_narrow_linear_forward_backward(cuda, M, K, O):
 def test_fused_field_matches_reference_composition(cuda):
     torch.manual_seed(0)
     fused = RadianceField(sigma_bias=0.3).to(cuda)
-    plain = RadianceField(fused=False).to(cuda)
+    plain = ReferenceRadianceField().to(cuda)
     plain.load_state_dict(fused.state_dict())
     M = 30011
     emb = torch.randn(M, 32, device=cuda) * 0.2
