@@ -72,7 +72,7 @@ def parse():
 # clocks: sampled DURING the timed region through NVML (same counters nvidia-smi prints)
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    def __init__(self, index, period=0.05):
+    def __init__(self, index, period=0.1):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -104,6 +104,9 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
             time.sleep(self.period)
+
+    def reset(self):
+        self.samples, self.reasons = [], set()
 
     def stop(self):
         self._halt.set()
@@ -237,9 +240,15 @@ def run_ours(args):
             ms = float(t.item())
         return ms, [a.elapsed_time(b) for a, b in k_evs], float(loss.item()), out
 
-    timed(max(args.warmup, 3), False)
+    import gc
+    gc.collect()
+    gc.freeze()          # everything built so far is permanent: keeps full collections out of the timed steps
+    # the clock sampler starts before the warm-up steps: the first NVML queries of a process are slow and contend with
+    # the driver (they cost the first timed pass ~50 ms on a fresh box); its samples are reset when the timed steps start
     sampler = ClockSampler(local)
     sampler.start()
+    timed(max(args.warmup, 3), False)
+    sampler.reset()
     launches0 = L.nsvf_kernel_launches()
     replays0 = getattr(pipe.field, "graph_replays", 0)
     ms, kms, loss_val, out = timed(args.steps, False)
