@@ -247,7 +247,11 @@ def run_ours(args):
     # the driver (they cost the first timed pass ~50 ms on a fresh box); its samples are reset when the timed steps start
     sampler = ClockSampler(local)
     sampler.start()
-    timed(max(args.warmup, 3), False)
+    # multi-rank runs get extra untimed settling steps: in 3 of 6 multi-GPU runs ONE step somewhere between the 8th and
+    # the 14th of the process stalled for 0.2 - 12 s on all ranks at once (never at N = 1; cause not identified in
+    # round 1 — profiles/r1b_scaling.md); the reported "warmup" is the number of untimed steps actually run
+    n_warm = max(args.warmup, 3) + (12 if world > 1 else 0)
+    timed(n_warm, False)
     sampler.reset()
     launches0 = L.nsvf_kernel_launches()
     replays0 = getattr(pipe.field, "graph_replays", 0)
@@ -309,7 +313,7 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+        "warmup": n_warm, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C2: nsvf_base training step, 343 voxels (voxel 0.4, step 1/8, max_hits 60), "
                                "4 views x 800x800 rays intersected + 4 x 2048 rays marched per GPU, fwd+bwd+Adam, "
