@@ -240,6 +240,11 @@ def run_ours(args):
             ms = float(t.item())
         return ms, [a.elapsed_time(b) for a, b in k_evs], float(loss.item()), out
 
+    # pre-size the caching allocator: one 12 GiB block, freed back to torch's cache, is split to serve the step's
+    # variable-size requests, so no step after warm-up has to call cudaMalloc (slow and device-synchronising, and much
+    # slower once NCCL has enabled peer access between the GPUs of the box — the suspected cause of the multi-rank stall described below)
+    _reserve = torch.empty(12 << 30, dtype=torch.uint8, device=dev)
+    del _reserve
     import gc
     gc.collect()
     gc.freeze()          # everything built so far is permanent: keeps full collections out of the timed steps
