@@ -240,6 +240,22 @@ def run_ours(args):
             ms = float(t.item())
         return ms, [a.elapsed_time(b) for a, b in k_evs], float(loss.item()), out
 
+    # shape warm-up: the eager chunks of a step (the first one, padded to 65536 rows, and a short last one whose row count
+    # changes every step) can make cuBLAS pick a GEMM kernel it has not used yet, and CUDA loads kernels lazily — a
+    # first use in the middle of the timed steps costs tens of ms (more with several processes on the box).  One eager
+    # forward + backward of the field per row-count bucket, via autograd.grad so that DDP's hooks stay out of it.
+    try:
+        inner = getattr(pipe.field, "field", pipe.field)
+        params = [p for p in inner.parameters() if p.requires_grad]
+        for M in list(range(2048, 65536 + 1, 2048)):
+            emb = torch.zeros(M, 32, device=dev, requires_grad=True)
+            ray = torch.nn.functional.normalize(torch.ones(M, 3, device=dev), dim=-1)
+            o = inner({"emb": emb, "ray": ray})
+            torch.autograd.grad(o["sigma"].sum() + o["texture"].sum(), params + [emb])
+        del emb, ray, o
+        torch.cuda.synchronize()
+    except Exception as e:      # warm-up only: never fatal
+        print("shape warm-up skipped: %r" % (e,), file=sys.stderr)
     # pre-size the caching allocator: one 12 GiB block, freed back to torch's cache, is split to serve the step's
     # variable-size requests, so no step after warm-up has to call cudaMalloc (slow and device-synchronising, and much
     # slower once NCCL has enabled peer access between the GPUs of the box — the suspected cause of the multi-rank stall described below)
