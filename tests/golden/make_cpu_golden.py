@@ -142,7 +142,57 @@ def main():
     e2.pruning(lambda inp, outputs: {"sigma": inp["emb"][:, 0] * 8 - 0.2}, th=0.5)
     save("cpu_prune.npz", points=e2.points.numpy(), feats=e2.feats.numpy().astype(np.int32), values=vals,
          voxel_size=float(e2.voxel_size), min_score=scores.min(-1)[0].detach().numpy(), keep=e2.keep.numpy().astype(np.int8))
+    # ---- the field MLP (RaidanceField, fairnr/modules/field.py:60-279) at the nsvf_base input spec, 128-wide -----
+    # pins oracle/field_ref.py (and through it the fused field passes) to the reference's own modules
+    make_field_fixture(fld, save)
     print("wrote", sorted(f for f in os.listdir(HERE) if f.startswith("cpu_")))
+
+
+def field_name_map(ref_key):
+    """Reference state_dict key -> key of nsvf_b200.field.RadianceField / oracle.field_ref.ReferenceRadianceField."""
+    k = ref_key
+    k = k.replace("den_filters.emb.emb", "emb_enc.freq").replace("tex_filters.ray.emb", "ray_enc.freq")
+    k = k.replace("bg_color.bg_color", "bg_color")
+    k = k.replace("predictor.hidden_layer.net.", "predictor.0.").replace("predictor.output_layer.", "predictor.1.")
+    for name in ("feature_field", "renderer"):
+        if k.startswith(name + ".net."):
+            rest = k[len(name) + 5:]                      # "<i>.net.<j>.weight" or "<i>.weight"
+            k = name + "." + rest.replace(".net.", ".")
+    return k
+
+
+def make_field_fixture(field_mod, save, width=128, M=48):
+    import types
+    args = types.SimpleNamespace(inputs_to_density="emb:6:32", inputs_to_texture="feat:0:%d, ray:4" % width,
+                                 feature_embed_dim=width, density_embed_dim=width, texture_embed_dim=width,
+                                 feature_layers=1, texture_layers=3, background_stop_gradient=True, min_color=-1,
+                                 transparent_background="1.0,1.0,1.0")
+    torch.manual_seed(11)
+    f = field_mod.RaidanceField(args)
+    with torch.no_grad():                                 # non-trivial LayerNorm affine, biases
+        for k, p in f.named_parameters():
+            if k.endswith("net.1.weight"):
+                p.add_(0.2 * torch.randn_like(p))
+            elif k.endswith("bias") and p.requires_grad:
+                p.add_(0.1 * torch.randn_like(p))
+    emb = (torch.randn(M, 32) * 0.2).requires_grad_(True)
+    ray = torch.nn.functional.normalize(torch.randn(M, 3), dim=-1)
+    out = f({"emb": emb, "ray": ray})
+    gs, gt = torch.randn(M), torch.randn(M, 3)
+    f.zero_grad()
+    ((out["sigma"] * gs).sum() + (out["texture"] * gt).sum()).backward()
+    fix = {"width": width, "emb": emb.detach().numpy(), "ray": ray.numpy(), "gs": gs.numpy(), "gt": gt.numpy(),
+           "sigma": out["sigma"].detach().numpy(), "texture": out["texture"].detach().numpy(),
+           "grad_emb": emb.grad.numpy()}
+    for k, v in f.state_dict().items():
+        fix["w:" + field_name_map(k)] = v.detach().numpy()
+    keep = ("feature_field.0.0.weight", "feature_field.0.1.weight", "feature_field.0.1.bias", "feature_field.0.0.bias",
+            "predictor.0.0.weight", "predictor.1.weight", "predictor.1.bias", "renderer.0.0.weight", "renderer.4.weight",
+            "renderer.4.bias")                                    # a gradient per kind of layer keeps the fixture small
+    for k, p in f.named_parameters():
+        if p.grad is not None and field_name_map(k) in keep:
+            fix["g:" + field_name_map(k)] = p.grad.numpy()
+    save("cpu_field.npz", **fix)
 
 
 if __name__ == "__main__":

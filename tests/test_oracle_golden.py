@@ -144,3 +144,30 @@ def test_oracle_properties():
     probs, depth, missed, colors = oracle.composite_fwd(fe, None, np.ones_like(fe))
     np.testing.assert_allclose(probs.sum(-1) + missed, 1.0, atol=1e-6)
     np.testing.assert_allclose(missed, np.exp(-fe.sum(-1)), atol=1e-6)     # 1 - sum(probs): eps(1.0)-level error
+
+
+def test_oracle_field_matches_reference_field_module():
+    """oracle/field_ref.py (the yardstick of the fused field passes, tests/test_field_gpu.py) against the reference's own
+    RaidanceField (fairnr/modules/field.py:60-279) at the nsvf_base input spec, 128-wide: same weights (fixture keys are the
+    reference's state_dict mapped to our names), same inputs -> same sigma / texture and gradients."""
+    from oracle.field_ref import ReferenceRadianceField
+    z = load("cpu_field.npz")
+    w = int(z["width"])
+    f = ReferenceRadianceField(feat_dim=w, density_dim=w, texture_dim=w)
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:")}
+    assert set(sd) == set(f.state_dict()), set(sd) ^ set(f.state_dict())
+    f.load_state_dict(sd)
+    emb = torch.from_numpy(z["emb"]).requires_grad_(True)
+    out = f({"emb": emb, "ray": torch.from_numpy(z["ray"])})
+    assert np.allclose(out["sigma"].detach().numpy(), z["sigma"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(out["texture"].detach().numpy(), z["texture"], rtol=1e-5, atol=1e-6)
+    ((out["sigma"] * torch.from_numpy(z["gs"])).sum() + (out["texture"] * torch.from_numpy(z["gt"])).sum()).backward()
+    assert np.allclose(emb.grad.numpy(), z["grad_emb"], rtol=1e-4, atol=1e-6)
+    grads = dict(f.named_parameters())
+    checked = 0
+    for k in z.files:
+        if k.startswith("g:"):
+            g = grads[k[2:]].grad.numpy()
+            assert np.abs(g - z[k]).max() <= 1e-5 * max(np.abs(z[k]).max(), 1e-30), k
+            checked += 1
+    assert checked >= 8
