@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-frame", action="store_true", help="skip the C3 full-frame extra")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-on-this-GPU legs (child process)")
     ap.add_argument("--no-stages", action="store_true", help="skip the informational per-stage timings")
     ap.add_argument("--mlp-gemm", default="bf16x9", choices=["bf16x9", "simt"],
                     help="fp32 GEMMs of the field MLP: cuBLAS 12.9 BF16x9 emulation on tensor cores (fp32-accurate) "
@@ -178,12 +179,16 @@ def run_ours(args):
     if hasattr(pipe.field, "capture"):
         pipe.field.capture(dev)          # CUDA graphs of the field's chunk forward / backward, before any eager pass
     model = pipe
-    if world > 1:
-        from torch.nn.parallel import DistributedDataParallel as DDP
-        # NCCL all-reduce of values.weight.grad + MLP grads; the voxel buffers are replicated and deterministic, so
-        # DDP's per-forward buffer broadcast is off
-        model = DDP(pipe, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True)
-    opt = torch.optim.Adam([p for p in pipe.parameters() if p.requires_grad], lr=1e-3, betas=(0.9, 0.999))
+    params = [p for p in pipe.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-3, betas=(0.9, 0.999))
+    # gradient exchange: ONE flat fp32 bucket holding values.weight.grad + the MLP grads (2.3 MB), every
+    # parameter's .grad a view into it, one NCCL all-reduce (AVG) per step right after backward.  No DDP: its reducer
+    # hooks / bucket rebuild bought nothing for a 2.3 MB payload and sat on the per-rank host path.
+    flat_grad = torch.zeros(sum(p.numel() for p in params), device=dev)
+    off = 0
+    for p in params:
+        p.grad = flat_grad[off: off + p.numel()].view_as(p)
+        off += p.numel()
     host = make_batches(2, rank, pinned=True)
     resident = [tuple(t.to(dev) for t in b) for b in host]
     staging = tuple(torch.empty_like(t, device=dev) for t in host[0])
@@ -193,8 +198,10 @@ def run_ours(args):
         flush.zero_()
         out = model(rs, rd)
         loss = loss_fn(out, target)
-        opt.zero_grad(set_to_none=True)
+        flat_grad.zero_()                 # grads are views of the flat bucket: backward accumulates into it
         loss.backward()
+        if world > 1:
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)
         opt.step()
         return loss, out
 
@@ -268,10 +275,7 @@ def run_ours(args):
     # the driver (they cost the first timed pass ~50 ms on a fresh box); its samples are reset when the timed steps start
     sampler = ClockSampler(local)
     sampler.start()
-    # multi-rank runs get extra untimed settling steps: in 3 of 6 multi-GPU runs ONE step somewhere between the 8th and
-    # the 14th of the process stalled for 0.2 - 12 s on all ranks at once (never at N = 1; cause not identified in
-    # round 1 — profiles/r1b_scaling.md); the reported "warmup" is the number of untimed steps actually run
-    n_warm = max(args.warmup, 3) + (12 if world > 1 else 0)
+    n_warm = max(args.warmup, 3)
     timed(n_warm, False)
     sampler.reset()
     launches0 = L.nsvf_kernel_launches()
@@ -363,9 +367,34 @@ def run_ours(args):
             line["stages_ms"] = {"error": repr(e)[:200]}
     if world > 1:
         dist.barrier()
-    if rank == 0 and not args.no_frame:
+    # the ray-marching path alone ("MLP ... once excluded with a trivial field_fn"): the same step with a
+    # contraction-free stand-in field, so that intersect + sample + interpolate + composite (fwd + bwd) + Adam on the
+    # voxel embeddings is all that is timed
+    try:
+        hot = hot_path_step(dev, resident, args.steps, max(args.warmup, 3))
+        line["value_hot_path"] = {"value": round(world * rays_marched / (hot["ms_per_step"] / 1e3), 1), "unit": "rays/s",
+                                  "ms_per_step": hot["ms_per_step"], "field": "trivial (no contraction)",
+                                  "per_gpu": True if world > 1 else False}
+    except Exception as e:
+        hot = None
+        line["value_hot_path"] = {"error": repr(e)[:200]}
+    if rank == 0 and world == 1 and not args.no_ref_gpu:
         try:
-            line["frame"] = frame_bench(dev)
+            ours = {"step": {"ms_per_step": round(ms / args.steps, 4)},
+                    "step_hot_path": {"ms_per_step": hot["ms_per_step"] if hot else None}}
+            ref, vs = ref_gpu_leg(dev, pipe, [tuple(t.cpu() for t in b) for b in host], out["sampled"].reshape(-1),
+                                  ours, steps=min(args.steps, 6))
+            line["ref_gpu"], line["vs_ref_gpu"] = ref, vs
+            if isinstance(ref.get("ours"), dict) and "frame" in ref["ours"]:
+                line["frame"] = {"with_field_mlp": ref["ours"]["frame"],
+                                 "hot_path_only(trivial field)": ref["ours"]["frame_hot_path"]}
+        except Exception as e:
+            line["ref_gpu"] = {"error": repr(e)[:300]}
+    elif rank == 0 and not args.no_frame:
+        try:
+            fr = frame_bench(dev)
+            fr.pop("_hot_out", None)
+            line["frame"] = fr
         except Exception as e:
             line["frame"] = {"error": repr(e)[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -379,6 +408,32 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line), flush=True)
+
+
+def hot_path_step(dev, resident, steps, warmup):
+    """The C2 training step with the stand-in field (no MLP): device time per step over `steps` steps."""
+    pipe, _ = build_model(dev, field="trivial")
+    params = [p for p in pipe.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-3, betas=(0.9, 0.999))
+
+    def step(i):
+        rs, rd, target = resident[i % len(resident)]
+        out = pipe(rs, rd)
+        loss = loss_fn(out, target)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return out
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        out = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return {"ms_per_step": round(e0.elapsed_time(e1) / steps, 4), "samples_evaluated": int(out["ae"])}
 
 
 def _time(fn, n=5, warm=2):
@@ -488,29 +543,145 @@ def stage_times(dev, pipe, batch):
     return res
 
 
-def frame_bench(dev):
+def frame_bench(dev, pipe=None, rs=None, rd=None):
     """ms per 800x800 frame on the C3 scene (BASELINE.json configs[2]): eval, early termination 0.01, chunk 512."""
     from nsvf_b200 import synthetic
+    from nsvf_b200.field import TrivialField
     res = {}
-    rs, rd = synthetic.camera_rays(RES, RES, 1, radius=4.5, seed=7, device=dev)
-    rs, rd = rs[None, :, None, 0, :].contiguous(), rd[None].contiguous()
-    for name, field in (("with_field_mlp", "mlp"), ("hot_path_only(trivial field)", "trivial")):
-        pipe, scene = build_model(dev, "C3", train=False, field=field, tolerance=0.01, chunk=512, sigma_bias=2.0)
+    if rs is None:
+        rs, rd = synthetic.camera_rays(RES, RES, 1, radius=4.5, seed=7, device=dev)
+        rs, rd = rs[None, :, None, 0, :].contiguous(), rd[None].contiguous()
+    if pipe is None:
+        pipe, _ = build_model(dev, "C3", train=False, field="mlp", tolerance=0.01, chunk=512, sigma_bias=2.0)
+    mlp_field = pipe.field
+    for name, field in (("with_field_mlp", mlp_field), ("hot_path_only(trivial field)", TrivialField())):
+        pipe.field = field
         with torch.no_grad():
             pipe(rs, rd)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            n = 2
+            n = 2 if field is mlp_field else 5
             for _ in range(n):
                 out = pipe(rs, rd)
             e1.record()
             torch.cuda.synchronize()
         res[name] = {"ms_per_800x800_frame": round(e0.elapsed_time(e1) / n, 3), "field_evaluations": int(out["ae"]),
                      "rays_hit": int(out["hits"].sum())}
-        res["voxels"] = scene.n
-        del pipe
+        if field is not mlp_field:
+            res["_hot_out"] = {k: out[k].detach() for k in ("colors", "depths", "missed")}
+    pipe.field = mlp_field
+    res["voxels"] = int(pipe.encoder.num_voxels)
     return res
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference on the SAME B200: the unmodified reference (baseline/_ref) in a child process, on our tensors
+# ------------------------------------------------------------------------------------------------------
+def _ours_clib(dev, pipe, rs, rd, march, n, warm):
+    """encoder.ray_intersect -> probs/steps -> ray_sample on our kernels, timed like baseline/ref_gpu.py:leg_clib."""
+    enc = pipe.encoder
+    with torch.no_grad():
+        st = enc.precompute(id=torch.zeros(1, dtype=torch.long, device=dev))
+        t_int = _time(lambda: enc.ray_intersect(rs, rd, st), n=n, warm=warm)
+        _, _, inter, hits = enc.ray_intersect(rs, rd, st)
+        if march is None:
+            sel = hits.reshape(-1)
+        else:
+            sel = torch.zeros_like(hits.reshape(-1))
+            sel[march.to(dev)] = True
+        sub = {k: v.reshape(-1, v.size(-1))[sel] for k, v in inter.items()}
+
+        def sample():
+            o = dict(sub)
+            dists = (o["max_depth"] - o["min_depth"]).masked_fill(o["intersected_voxel_idx"].eq(-1), 0)
+            o["probs"] = dists / dists.sum(dim=-1, keepdim=True)
+            o["steps"] = dists.sum(-1) / enc.step_size
+            return enc.ray_sample(o)
+        was = enc.training
+        enc.eval()
+        t_smp = _time(sample, n=n, warm=warm)
+        enc.train(was)
+    rays = rd.numel() // 3
+    return {"rays_intersected": rays, "rays_sampled": int(sel.sum()), "intersect_ms": t_int, "sample_ms": t_smp,
+            "rays_per_s": round(rays / ((t_int + t_smp) / 1e3), 1)}
+
+
+def ref_gpu_leg(dev, pipe_c2, host_batches, march, ours, steps):
+    """Runs baseline/ref_gpu.py (unmodified reference, child process) on this GPU with OUR voxels, weights, rays and
+    targets, then our side of the same legs.  `ours` carries the numbers the main arm already measured.
+    -> (ref_gpu, vs_ref_gpu)."""
+    import subprocess
+    import tempfile
+    from nsvf_b200 import checkpoint, synthetic
+    from baseline import install_ref
+    if not install_ref.installed():
+        return {"unavailable": "baseline/_ref is not populated (python baseline/install_ref.py where /root/reference exists)"}, None
+    tmp = tempfile.mkdtemp(prefix="nsvf_refgpu_")
+    rs3, rd3 = synthetic.camera_rays(RES, RES, 1, radius=4.5, seed=7)
+    rs3, rd3 = rs3[None, :, None, 0, :].contiguous(), rd3[None].contiguous()
+    pipe_c3, scene3 = build_model(dev, "C3", train=False, field="mlp", tolerance=0.01, chunk=512, sigma_bias=2.0)
+    inp = {"steps": steps,
+           "C2": {"state": {k: v.cpu() for k, v in checkpoint.to_reference_state_dict(pipe_c2).items()},
+                  "bbox_line": "-1.2 -1.2 -1.2 1.2 1.2 1.2 0.4", "max_hits": 60, "chunk": 64, "tolerance": 0.0,
+                  "pixel_per_view": PIX_PER_VIEW, "H": RES, "W": RES, "views": VIEWS,
+                  "batches": [tuple(t.cpu() for t in b) for b in host_batches],
+                  "rs": host_batches[0][0].cpu(), "rd": host_batches[0][1].cpu(), "march": march.cpu()},
+           "C3": {"state": {k: v.cpu() for k, v in checkpoint.to_reference_state_dict(pipe_c3).items()},
+                  "bbox_line": "-2.4 -2.4 -2.4 2.4 2.4 2.4 0.4", "max_hits": scene3.max_hits, "chunk": 512,
+                  "tolerance": 0.01, "rs": rs3, "rd": rd3}}
+    torch.save(inp, os.path.join(tmp, "inputs.pt"))
+    env = {k: v for k, v in os.environ.items() if k not in ("CUBLAS_EMULATE_SINGLE_PRECISION", "RANK", "WORLD_SIZE",
+                                                             "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
+    env["CUDA_VISIBLE_DEVICES"] = os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[dev.index] \
+        if os.environ.get("CUDA_VISIBLE_DEVICES") else str(dev.index)
+    torch.cuda.empty_cache()
+    out_json = os.path.join(tmp, "ref.json")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "baseline", "ref_gpu.py"), "--inputs",
+                        os.path.join(tmp, "inputs.pt"), "--out", out_json], env=env, capture_output=True, text=True,
+                       timeout=900)
+    if r.returncode != 0 or not os.path.exists(out_json):
+        return {"error": (r.stderr or r.stdout)[-600:]}, None
+    ref = json.load(open(out_json))
+    ref["how"] = ("unmodified reference (baseline/_ref: NSVFModel._forward / SparseVoxelEncoder / VolumeRenderer / clib "
+                  "wrappers + clib kernels built by its own setup.py for sm_100a) in a child process on this GPU, same "
+                  "voxels, weights, rays and targets; CUDA events after warm-up")
+    # ---- our side of the same legs ----
+    mine = dict(ours)
+    rs2, rd2 = host_batches[0][0].to(dev), host_batches[0][1].to(dev)
+    mine["clib_C2"] = _ours_clib(dev, pipe_c2, rs2, rd2, march, 5, 2)
+    mine["clib_C3"] = _ours_clib(dev, pipe_c3, rs3.to(dev), rd3.to(dev), None, 5, 2)
+    fr = frame_bench(dev, pipe_c3, rs3.to(dev), rd3.to(dev))
+    mine["frame"], mine["frame_hot_path"] = fr["with_field_mlp"], fr["hot_path_only(trivial field)"]
+    # parity of the two arms on the tensors that were timed (deterministic eval frame, trivial field)
+    try:
+        theirs = torch.load(os.path.splitext(out_json)[0] + "_frame.pt")
+        o = fr["_hot_out"]
+        ref["frame_parity_vs_ours"] = {
+            "colors_max_abs_diff": float((o["colors"].cpu() - theirs["colors"]).abs().max()),
+            "depths_max_abs_diff": float((o["depths"].cpu() - theirs["depths"]).abs().max()),
+            "missed_max_abs_diff": float((o["missed"].cpu() - theirs["missed"]).abs().max()),
+            "field_evaluations_equal": bool(fr["hot_path_only(trivial field)"]["field_evaluations"]
+                                            == ref.get("frame_hot_path", {}).get("field_evaluations"))}
+    except Exception as e:
+        ref["frame_parity_vs_ours"] = {"error": repr(e)[:200]}
+    fr.pop("_hot_out", None)
+
+    def ratio(a, b):
+        try:
+            return round(a / b, 2)
+        except Exception:
+            return None
+    g = lambda d, *ks: (d.get(ks[0], {}) or {}).get(ks[1]) if len(ks) == 2 else d.get(ks[0])
+    vs = {"clib_C2": ratio(g(mine, "clib_C2", "rays_per_s"), g(ref, "clib_C2", "rays_per_s")),
+          "clib_C3": ratio(g(mine, "clib_C3", "rays_per_s"), g(ref, "clib_C3", "rays_per_s")),
+          "step": ratio(g(ref, "step", "ms_per_step"), g(mine, "step", "ms_per_step")),
+          "step_hot_path": ratio(g(ref, "step_hot_path", "ms_per_step"), g(mine, "step_hot_path", "ms_per_step")),
+          "frame": ratio(g(ref, "frame", "ms_per_frame"), g(mine, "frame", "ms_per_800x800_frame")),
+          "frame_hot_path": ratio(g(ref, "frame_hot_path", "ms_per_frame"),
+                                  g(mine, "frame_hot_path", "ms_per_800x800_frame"))}
+    ref["ours"] = mine
+    return ref, vs
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -134,6 +134,22 @@ NSVF_API int nsvf_inverse_cdf_sampling(nsvf_stream_t stream, int b, int num_rays
                                        const float* steps, int* sampled_idx, float* sampled_depth,
                                        float* sampled_dists, int* max_count);
 
+/* The same sampler with the post-processing of SparseVoxelEncoder.ray_sample (fairnr/modules/encoder.py:547-549:
+ * dists.clamp(min=0), depth[idx == -1] = MAX_DEPTH, dists[idx == -1] = 0) fused in and TRIMMED rows:
+ *   ray_len    : i32 [valid_rays], optional: 1 + position of the last sample with idx != -1 of each ray
+ *   holes_flag : i32 [1], optional, OR'ed with 1 when some ray's valid samples are not a prefix of its row
+ *   pad_depth  : depth written to padding slots (0 reproduces the reference kernel, 10000 = MAX_DEPTH for ray_sample)
+ *   flags      : bit 0 = write the padding beyond each ray's samples (idx -1, depth pad_depth, dists 0); without it
+ *                the rows hold exactly the produced samples and nothing else is written (consumers use ray_len);
+ *                bit 1 = apply ray_sample's clamp / masking to the produced samples. */
+NSVF_API int nsvf_inverse_cdf_sampling_ex(nsvf_stream_t stream, int b, int num_rays, long long valid_rays,
+                                          int ray_chunk, int max_hits, int max_steps, float fixed_step_size,
+                                          const int* pts_idx, const float* min_depth, const float* max_depth,
+                                          const float* uniform_noise, float noise_const, const float* probs,
+                                          const float* steps, int* sampled_idx, float* sampled_depth,
+                                          float* sampled_dists, int* max_count, int* ray_len, int* holes_flag,
+                                          float pad_depth, int flags);
+
 /* Replaces uniform_ray_sampling, fairnr/clib/src/sample.cpp:23-55 + sample_gpu.cu:15-106. */
 NSVF_API int nsvf_uniform_ray_sampling(nsvf_stream_t stream, int b, int num_rays, int max_hits, int max_steps,
                               float step_size, const int* pts_idx, const float* min_depth, const float* max_depth,
@@ -175,6 +191,74 @@ NSVF_API int nsvf_composite_bwd(nsvf_stream_t stream, long long B, int K, const 
                        const float* sampled_depth, const float* grad_probs, const float* grad_depth,
                        const float* grad_missed, const float* grad_colors, float* grad_free_energy,
                        float* grad_texture);
+
+/* The same compositing over TRIMMED rows (see "ray-marching plan" below): only eval_len[ray] leading samples of a
+ * ray carry free energy / texture (anything beyond counts as zero free energy) and only lens[ray] leading samples
+ * carry a depth; free_energy / texture / probs rows have stride K, sampled_depth rows stride ldk >= K.
+ * Also produces the two per-ray extrema of fairnr/modules/renderer.py:210-211:
+ *   max_depths f32 [B] = max depth over the ray's samples, -1 for rays flagged in early_stop (u8 [B], optional)
+ *   min_depths f32 [B] = min over the WHOLE padded row: the samples and, when lens[ray] < K, the padding value —
+ *                        pad_depth, or (depth_rows_padded != 0) the first padding slot of the row itself.
+ * probs (optional) is written densely, zeros beyond the evaluated prefix.  bwd writes gradients for the evaluated
+ * prefix only. */
+NSVF_API int nsvf_composite_trimmed_fwd(nsvf_stream_t stream, long long B, int K, long long ldk, const int* eval_len,
+                                        const int* lens, const unsigned char* early_stop, const float* free_energy,
+                                        const float* texture, const float* sampled_depth, float* probs, float* depth,
+                                        float* missed, float* colors, float* max_depths, float* min_depths,
+                                        float pad_depth, int depth_rows_padded);
+NSVF_API int nsvf_composite_trimmed_bwd(nsvf_stream_t stream, long long B, int K, long long ldk, const int* eval_len,
+                                        const float* free_energy, const float* texture, const float* sampled_depth,
+                                        const float* grad_probs, const float* grad_depth, const float* grad_missed,
+                                        const float* grad_colors, float* grad_free_energy, float* grad_texture);
+
+/* ---- ray-marching plan: the chunk loop of the renderer on the device ---------------------------------------
+ * Replaces the loop of VolumeRenderer.forward_chunk / forward_once, fairnr/modules/renderer.py:77-191: per-column
+ * `hits[:, i].sum()` host syncs (:157-158,187), boolean-mask compaction (:88-100), masked_scatter into zero-filled
+ * [B,K] tensors (:109-131), free_energy = relu(noise + sigma) * dists * 7 (:117-121) and the early-termination
+ * update after every field evaluation (:170-174).  Same schedule, same samples reach the field.
+ * Rows are TRIMMED: ray r owns slots [0, lens[r]) of row r of sampled_idx / sampled_depth / sampled_dists (row
+ * stride ldk >= K); valid samples must be a prefix of the row (nsvf_march_ray_lengths reports rows where they are
+ * not in plan word 4; callers then use nsvf_compact_* below).
+ *   plan        : device scratch of nsvf_march_plan_bytes(B, K) bytes, ZEROED once per forward_chunk call
+ *   host_info   : i32 [>= 16 (+ 3 per window)] in PINNED host memory (written by the device through the unified
+ *                 address space): [0] start, [1] end, [2] valid samples of the window, [3] done, [4] holes,
+ *                 [5] number of windows, [8] total samples; with all_windows the triplets (start, end, count) of
+ *                 every window follow from word 16.  Read it after synchronising the stream.
+ *   nsvf_march_ray_lengths : lens i32 [B] from a padded sampled_idx (idx != -1)
+ *   nsvf_march_begin       : column counts from lens; publishes the first window, or (all_windows = 1, valid when
+ *                            there is no early termination) the complete window list
+ *   nsvf_march_compact     : compacts the samples of window [start, end) of the live rays in row-major order (the
+ *                            order boolean indexing produces): out_vox i32 [M], out_xyz f32 [M,3] = ray_start +
+ *                            ray_dir * depth, out_dir f32 [M,3], out_dists f32 [M] (either optional), and
+ *                            ray_off i32 [B+1] = exclusive offsets of the rays in that order.  launch_no = number of
+ *                            earlier nsvf_march_compact launches on this plan (0, 1, 2, ...).
+ *   nsvf_march_epilogue    : sigma f32 [M] (+ noise f32 [M] or NULL, dists f32 [M]) -> free_energy_rows f32 [B,K],
+ *                            texture f32 [M,3] -> texture_rows f32 [B,K,3] at the window's slots; eval_len i32 [B] =
+ *                            evaluated prefix; with tolerance > 0: acc_free_energy f32 [B] += row sums, early_stop
+ *                            u8 [B] = acc > tolerance, column counts updated; with schedule_next the next window is
+ *                            published to plan / host_info by the last CTA.
+ *   nsvf_march_epilogue_bwd: gradients of the rows back to the compacted order of one window:
+ *                            grad_sigma = (g_fe * 7) * dists * [noise + sigma > 0], grad_texture = g_tex. */
+NSVF_API size_t nsvf_march_plan_bytes(long long B, int K);
+NSVF_API int nsvf_march_ray_lengths(nsvf_stream_t stream, long long B, int K, long long ldk, const int* sampled_idx,
+                                    int* lens, void* plan);
+NSVF_API int nsvf_march_begin(nsvf_stream_t stream, long long B, int K, int chunk_size, const int* lens,
+                              const unsigned char* early_stop, int all_windows, void* plan, int* host_info,
+                              int host_capacity_ints);
+NSVF_API int nsvf_march_compact(nsvf_stream_t stream, long long B, int K, long long ldk, int start, int end,
+                                const int* lens, const unsigned char* early_stop, const int* sampled_idx,
+                                const float* sampled_depth, const float* sampled_dists, const float* ray_start,
+                                const float* ray_dir, int* out_vox, float* out_xyz, float* out_dir, float* out_dists,
+                                int* ray_off, void* plan, int launch_no);
+NSVF_API int nsvf_march_epilogue(nsvf_stream_t stream, long long B, int K, int start, int end, const int* ray_off,
+                                 const int* lens, unsigned char* early_stop, float* acc_free_energy, int* eval_len,
+                                 const float* sigma, const float* noise, const float* dists, const float* texture,
+                                 float tolerance, float* free_energy_rows, float* texture_rows, int chunk_size,
+                                 int schedule_next, void* plan, int* host_info);
+NSVF_API int nsvf_march_epilogue_bwd(nsvf_stream_t stream, long long B, int K, int start, int end, const int* ray_off,
+                                     const float* grad_free_energy_rows, const float* grad_texture_rows,
+                                     const float* sigma, const float* noise, const float* dists, float* grad_sigma,
+                                     float* grad_texture);
 
 /* ---- sample compaction ---------------------------------------------------------------------------------
  * Replaces the boolean-mask compaction of VolumeRenderer.forward_once, fairnr/modules/renderer.py:88-100

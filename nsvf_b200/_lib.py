@@ -37,6 +37,20 @@ SIGNATURES = {
     "nsvf_inverse_cdf_sampling": (c_int, [c_void_p, c_int, c_int, c_ll, c_int, c_int, c_int, c_float,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p]),
+    "nsvf_inverse_cdf_sampling_ex": (c_int, [c_void_p, c_int, c_int, c_ll, c_int, c_int, c_int, c_float,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                             c_int]),
+    "nsvf_composite_trimmed_fwd": (c_int, [c_void_p, c_ll, c_int, c_ll] + [c_void_p] * 12 + [c_float, c_int]),
+    "nsvf_composite_trimmed_bwd": (c_int, [c_void_p, c_ll, c_int, c_ll] + [c_void_p] * 10),
+    "nsvf_march_plan_bytes": (c_size_t, [c_ll, c_int]),
+    "nsvf_march_ray_lengths": (c_int, [c_void_p, c_ll, c_int, c_ll, c_void_p, c_void_p, c_void_p]),
+    "nsvf_march_begin": (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int]),
+    "nsvf_march_compact": (c_int, [c_void_p, c_ll, c_int, c_ll, c_int, c_int] + [c_void_p] * 13 + [c_int]),
+    "nsvf_march_epilogue": (c_int, [c_void_p, c_ll, c_int, c_int, c_int] + [c_void_p] * 9 + [c_float, c_void_p,
+                                                                                             c_void_p, c_int, c_int,
+                                                                                             c_void_p, c_void_p]),
+    "nsvf_march_epilogue_bwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_int] + [c_void_p] * 8),
     "nsvf_uniform_ray_sampling": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float] + [c_void_p] * 7),
     "nsvf_octree_build": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p]),
     "nsvf_octree_flatten": (c_int, [c_void_p, c_void_p, c_ll]),

@@ -176,6 +176,50 @@ class InverseCDFRaySampling(Function):
 inverse_cdf_sampling = InverseCDFRaySampling.apply
 
 
+@torch.no_grad()
+def inverse_cdf_sampling_rows(pts_idx, min_depth, max_depth, probs, steps, fixed_step_size=-1, deterministic=False,
+                              trimmed=False, pad_depth=MAX_DEPTH):
+    """inverse_cdf_sampling + the post-processing of SparseVoxelEncoder.ray_sample (encoder.py:547-549: dists clamped at
+    0, depth = MAX_DEPTH and dists = 0 where idx == -1) in ONE kernel, for the renderer's trimmed-row path:
+
+        -> (sampled_idx i32, sampled_depth, sampled_dists [N, K], ray_len i32 [N], holes i32 [1])
+
+    ray_len[r] = number of leading slots of row r that hold samples.  trimmed=False: K = max_len like the reference
+    wrapper (one extra host sync) and the rows are padded (-1 / MAX_DEPTH / 0); trimmed=True: K = max_steps, nothing
+    beyond ray_len[r] is written (or may be read), no max_len sync.  Same tiling quirks and RNG draw as
+    InverseCDFRaySampling above."""
+    G, N, P = 200, pts_idx.size(0), pts_idx.size(1)
+    R = int(np.ceil(N / G))
+    dev = pts_idx.device
+    in_dtype = min_depth.dtype
+    pts_idx = pts_idx.int().contiguous()
+    min_depth, max_depth = min_depth.float().contiguous(), max_depth.float().contiguous()
+    probs, steps = probs.float().contiguous(), steps.float().contiguous()
+    max_steps = int(steps.ceil().long().max()) + P
+    if deterministic:
+        noise, noise_ptr = None, None
+    else:
+        noise = min_depth.new_zeros(G, R, max_steps).uniform_().clamp(min=0.001, max=0.999)
+        noise_ptr = _p(noise)
+    sampled_idx = torch.empty((N, max_steps), dtype=torch.int32, device=dev)
+    sampled_depth = torch.empty((N, max_steps), dtype=torch.float32, device=dev)
+    sampled_dists = torch.empty((N, max_steps), dtype=torch.float32, device=dev)
+    meta = torch.zeros(2, dtype=torch.int32, device=dev)          # [max_count, holes]
+    ray_len = torch.empty(N, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_L.nsvf_inverse_cdf_sampling_ex(
+            _lib.current_stream(dev), G, R, N, 4 * G, P, max_steps, float(fixed_step_size), _p(pts_idx), _p(min_depth),
+            _p(max_depth), noise_ptr, 0.5, _p(probs), _p(steps), _p(sampled_idx), _p(sampled_depth),
+            _p(sampled_dists), _p(meta[0:1]), _p(ray_len), _p(meta[1:2]), float(pad_depth), (0 if trimmed else 1) | 2))
+    if in_dtype != torch.float32:
+        sampled_depth, sampled_dists = sampled_depth.to(in_dtype), sampled_dists.to(in_dtype)
+    if not trimmed:
+        max_len = int(meta[0].item())
+        sampled_idx, sampled_depth, sampled_dists = (sampled_idx[:, :max_len], sampled_depth[:, :max_len],
+                                                     sampled_dists[:, :max_len])
+    return sampled_idx, sampled_depth, sampled_dists, ray_len, meta[1:2]
+
+
 class BallRayIntersect(Function):
     """fairnr/clib/__init__.py:38-55."""
 

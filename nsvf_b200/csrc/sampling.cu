@@ -98,7 +98,8 @@ inverse_cdf_sampling_kernel(int b, int num_rays, long long valid_rays, int ray_c
                             const float* __restrict__ noise, float noise_const, const float* __restrict__ probs,
                             const float* __restrict__ steps, int* __restrict__ sampled_idx,
                             float* __restrict__ sampled_depth, float* __restrict__ sampled_dists,
-                            int* __restrict__ max_count) {
+                            int* __restrict__ max_count, int* __restrict__ ray_len, int* __restrict__ holes_flag,
+                            float pad_depth, int flags) {
   constexpr int LD = TS + 1;
   __shared__ int t_idx[kSampWarps][32 * LD];
   __shared__ float t_depth[kSampWarps][32 * LD];
@@ -117,7 +118,7 @@ inverse_cdf_sampling_kernel(int b, int num_rays, long long valid_rays, int ray_c
     const float* noise_row = noise;
     st.phase = 3;
     st.s = 0;
-    int next_idx0 = -1, n_valid = 0;
+    int next_idx0 = -1, n_valid = 0, lastv = 0, produced = 0;
     if (active) {
       const long long batch = ray / num_rays;
       const int r = (int)(ray - batch * num_rays);
@@ -157,6 +158,12 @@ inverse_cdf_sampling_kernel(int b, int num_rays, long long valid_rays, int ray_c
         if (cdf_next(st, max_hits, max_steps, H, next_idx0, pts_idx, row0_idx, min_depth, max_depth, probs,
                      noise_row, noise_const, oi, od, oz)) {
           n_valid += (oi != -1);
+          ++produced;
+          if (oi != -1) lastv = produced;
+          if (flags & 2) {   // ray_sample's post-processing (encoder.py:547-549)
+            od = od < 0.f ? 0.f : od;
+            if (oi == -1) { od = 0.f; oz = pad_depth; }
+          }
           t_idx[warp][lane * LD + c] = oi;
           t_dist[warp][lane * LD + c] = od;
           t_depth[warp][lane * LD + c] = oz;
@@ -166,7 +173,7 @@ inverse_cdf_sampling_kernel(int b, int num_rays, long long valid_rays, int ray_c
       for (; c < tw; ++c) {
         t_idx[warp][lane * LD + c] = -1;
         t_dist[warp][lane * LD + c] = 0.0f;
-        t_depth[warp][lane * LD + c] = 0.0f;
+        t_depth[warp][lane * LD + c] = pad_depth;
       }
       __syncwarp();
       // coalesced flush: 32/TS rows per instruction
@@ -185,13 +192,13 @@ inverse_cdf_sampling_kernel(int b, int num_rays, long long valid_rays, int ray_c
       // every lane finished: the rest of all rows is padding, written directly
       if (__all_sync(NSVF_FULL_MASK, st.phase == 3)) {
         const int tnext = t0 + TS;
-        if (tnext < max_steps) {
+        if (tnext < max_steps && (flags & 1)) {
           const int rem = max_steps - tnext;
           for (int r = 0; r < rows; ++r) {
             const long long o = out_base + (long long)r * max_steps + tnext;
             for (int k = lane; k < rem; k += 32) {
               sampled_idx[o + k] = -1;
-              sampled_depth[o + k] = 0.0f;
+              sampled_depth[o + k] = pad_depth;
               sampled_dists[o + k] = 0.0f;
             }
           }
@@ -200,6 +207,8 @@ inverse_cdf_sampling_kernel(int b, int num_rays, long long valid_rays, int ray_c
       }
     }
     my_max = max(my_max, n_valid);
+    if (active && ray_len != nullptr) ray_len[ray] = lastv;
+    if (active && holes_flag != nullptr && n_valid != lastv) atomicOr(holes_flag, 1);
   }
   if (max_count != nullptr) {
 #pragma unroll
@@ -246,7 +255,8 @@ inverse_cdf_warp_kernel(int b, int num_rays, long long valid_rays, int ray_chunk
                         const float* __restrict__ max_depth, const float* __restrict__ noise, float noise_const,
                         const float* __restrict__ probs, const float* __restrict__ steps,
                         int* __restrict__ sampled_idx, float* __restrict__ sampled_depth,
-                        float* __restrict__ sampled_dists, int* __restrict__ max_count) {
+                        float* __restrict__ sampled_dists, int* __restrict__ max_count, int* __restrict__ ray_len,
+                        int* __restrict__ holes_flag, float pad_depth, int flags) {
   extern __shared__ __align__(16) float cdf_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* base = cdf_smem + (size_t)warp * 6 * P;
@@ -307,7 +317,18 @@ inverse_cdf_warp_kernel(int b, int num_rays, long long valid_rays, int ray_chunk
     if (fixed_step_size > 0.0f) step_size = fixed_step_size;
     // steps beyond max_steps could only produce samples at slots >= max_steps, which are dropped anyway
     const int total_steps = min((int)ceilf(sj), max_steps);
-    int s_end = 0, n_valid = 0;
+    int s_end = 0, n_valid = 0, lastv = 0;
+    const bool post = (flags & 2) != 0;   // ray_sample's clamp / masking (encoder.py:547-549) fused in
+    auto emit = [&](int pos, int oi, float od, float oz) {
+      if (post) {
+        od = od < 0.f ? 0.f : od;
+        if (oi == -1) { od = 0.f; oz = pad_depth; }
+      }
+      sampled_idx[K + pos] = oi;
+      sampled_dists[K + pos] = od;
+      sampled_depth[K + pos] = oz;
+      if (oi != -1) { ++n_valid; lastv = max(lastv, pos + 1); }
+    };
 
     if (!ok) {
       // serial fallback (exact reference loop) on lane 0
@@ -323,8 +344,7 @@ inverse_cdf_warp_kernel(int b, int num_rays, long long valid_rays, int ray_chunk
           int oi; float od, oz;
           if (cdf_next(st, P, max_steps, H, next_idx0, pts_idx, row0_idx, min_depth, max_depth, probs, noise_row,
                        noise_const, oi, od, oz)) {
-            sampled_idx[K + sidx] = oi; sampled_dists[K + sidx] = od; sampled_depth[K + sidx] = oz;
-            n_valid += (oi != -1);
+            emit(sidx, oi, od, oz);
             ++sidx;
           }
         }
@@ -371,13 +391,7 @@ inverse_cdf_warp_kernel(int b, int num_rays, long long valid_rays, int ray_chunk
         if (act) {
           const float zlow = (pb == bb) ? pz : s_min[bb];
           const int pos = i + bb;
-          if (pos < max_steps) {
-            const int oi = s_idx[bb];
-            sampled_idx[K + pos] = oi;
-            sampled_dists[K + pos] = __fsub_rn(z, zlow);
-            sampled_depth[K + pos] = __fmul_rn(__fadd_rn(z, zlow), 0.5f);
-            n_valid += (oi != -1);
-          }
+          if (pos < max_steps) emit(pos, s_idx[bb], __fsub_rn(z, zlow), __fmul_rn(__fadd_rn(z, zlow), 0.5f));
           atomicAdd(&s_cnt[bb], 1);
           const bool next_act = lane < 31 && ((amask >> (lane + 1)) & 1u);
           if (!next_act || nbn != bb) s_zlast[bb] = z;   // the last step sample of a bin (so far)
@@ -402,11 +416,7 @@ inverse_cdf_warp_kernel(int b, int num_rays, long long valid_rays, int ray_chunk
           const int pos = j + incl;
           if (pos < max_steps) {
             const float zlow = cnt > 0 ? s_zlast[j] : s_min[j];
-            const int oi = s_idx[j];
-            sampled_idx[K + pos] = oi;
-            sampled_dists[K + pos] = __fsub_rn(s_max[j], zlow);
-            sampled_depth[K + pos] = __fmul_rn(__fadd_rn(s_max[j], zlow), 0.5f);
-            n_valid += (oi != -1);
+            emit(pos, s_idx[j], __fsub_rn(s_max[j], zlow), __fmul_rn(__fadd_rn(s_max[j], zlow), 0.5f));
           }
         }
         cbase = __shfl_sync(NSVF_FULL_MASK, incl, 31);
@@ -425,12 +435,7 @@ inverse_cdf_warp_kernel(int b, int num_rays, long long valid_rays, int ray_chunk
       }
       while (zl < curr_max) {
         const int oi = curr_bin < P ? s_idx[curr_bin] : next_idx0;
-        if (sidx < max_steps && lane == 0) {
-          sampled_idx[K + sidx] = oi;
-          sampled_dists[K + sidx] = __fsub_rn(curr_max, zl);
-          sampled_depth[K + sidx] = __fmul_rn(__fadd_rn(curr_max, zl), 0.5f);
-          n_valid += (oi != -1);
-        }
+        if (sidx < max_steps && lane == 0) emit(sidx, oi, __fsub_rn(curr_max, zl), __fmul_rn(__fadd_rn(curr_max, zl), 0.5f));
         ++curr_bin;
         ++sidx;
         if (curr_bin >= P || row0_idx[curr_bin] == -1) break;
@@ -439,15 +444,24 @@ inverse_cdf_warp_kernel(int b, int num_rays, long long valid_rays, int ray_chunk
       }
       s_end = min(sidx, max_steps);
     }
-    // 6) padding
-    for (int t = s_end + lane; t < max_steps; t += 32) {
-      sampled_idx[K + t] = -1;
-      sampled_depth[K + t] = 0.0f;
-      sampled_dists[K + t] = 0.0f;
+    // 6) padding (skipped for trimmed rows: consumers then read ray_len samples per row and nothing beyond)
+    if (flags & 1) {
+      for (int t = s_end + lane; t < max_steps; t += 32) {
+        sampled_idx[K + t] = -1;
+        sampled_depth[K + t] = pad_depth;
+        sampled_dists[K + t] = 0.0f;
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) n_valid += __shfl_xor_sync(NSVF_FULL_MASK, n_valid, o);
+    for (int o = 16; o > 0; o >>= 1) {
+      n_valid += __shfl_xor_sync(NSVF_FULL_MASK, n_valid, o);
+      lastv = max(lastv, __shfl_xor_sync(NSVF_FULL_MASK, lastv, o));
+    }
     my_max = max(my_max, n_valid);
+    if (lane == 0) {
+      if (ray_len != nullptr) ray_len[ray] = lastv;
+      if (holes_flag != nullptr && n_valid != lastv) atomicOr(holes_flag, 1);
+    }
     __syncwarp();
   }
   if (max_count != nullptr && lane == 0 && my_max > 0) atomicMax(max_count, my_max);
@@ -525,12 +539,13 @@ __global__ void uniform_ray_sampling_kernel(long long total_rays, int max_hits, 
 
 using namespace nsvf;
 
-extern "C" int nsvf_inverse_cdf_sampling(nsvf_stream_t stream_, int b, int num_rays, long long valid_rays,
+extern "C" int nsvf_inverse_cdf_sampling_ex(nsvf_stream_t stream_, int b, int num_rays, long long valid_rays,
                                          int ray_chunk, int max_hits, int max_steps, float fixed_step_size,
                                          const int* pts_idx, const float* min_depth, const float* max_depth,
                                          const float* uniform_noise, float noise_const, const float* probs,
                                          const float* steps, int* sampled_idx, float* sampled_depth,
-                                         float* sampled_dists, int* max_count) {
+                                         float* sampled_dists, int* max_count, int* ray_len, int* holes_flag,
+                                         float pad_depth, int flags) {
   cudaStream_t stream = (cudaStream_t)stream_;
   NSVF_REQUIRE(b >= 0 && num_rays >= 0 && max_hits >= 0 && max_steps >= 0, "inverse_cdf_sampling: negative size");
   if (b == 0 || num_rays == 0 || max_steps == 0) return 0;
@@ -552,7 +567,7 @@ extern "C" int nsvf_inverse_cdf_sampling(nsvf_stream_t stream_, int b, int num_r
                         (inverse_cdf_warp_kernel<<<grid, kCdfWarps * 32, smem, stream>>>(
                             b, num_rays, valid_rays, ray_chunk, max_hits, max_steps, fixed_step_size, pts_idx, min_depth,
                             max_depth, uniform_noise, noise_const, probs, steps, sampled_idx, sampled_depth,
-                            sampled_dists, max_count)));
+                            sampled_dists, max_count, ray_len, holes_flag, pad_depth, flags)));
       return 0;
     }
   }
@@ -562,8 +577,20 @@ extern "C" int nsvf_inverse_cdf_sampling(nsvf_stream_t stream_, int b, int num_r
   int grid = (int)(want < cap ? want : cap);
   NSVF_TIMED_LAUNCH("inverse_cdf_sampling_kernel", stream, (inverse_cdf_sampling_kernel<16><<<grid, kSampWarps * 32, 0, stream>>>(
       b, num_rays, valid_rays, ray_chunk, max_hits, max_steps, fixed_step_size, pts_idx, min_depth, max_depth,
-      uniform_noise, noise_const, probs, steps, sampled_idx, sampled_depth, sampled_dists, max_count)));
+      uniform_noise, noise_const, probs, steps, sampled_idx, sampled_depth, sampled_dists, max_count, ray_len,
+      holes_flag, pad_depth, flags)));
   return 0;
+}
+
+extern "C" int nsvf_inverse_cdf_sampling(nsvf_stream_t stream, int b, int num_rays, long long valid_rays,
+                                         int ray_chunk, int max_hits, int max_steps, float fixed_step_size,
+                                         const int* pts_idx, const float* min_depth, const float* max_depth,
+                                         const float* uniform_noise, float noise_const, const float* probs,
+                                         const float* steps, int* sampled_idx, float* sampled_depth,
+                                         float* sampled_dists, int* max_count) {
+  return nsvf_inverse_cdf_sampling_ex(stream, b, num_rays, valid_rays, ray_chunk, max_hits, max_steps, fixed_step_size,
+                                      pts_idx, min_depth, max_depth, uniform_noise, noise_const, probs, steps,
+                                      sampled_idx, sampled_depth, sampled_dists, max_count, nullptr, nullptr, 0.0f, 1);
 }
 
 extern "C" int nsvf_uniform_ray_sampling(nsvf_stream_t stream_, int b, int num_rays, int max_hits, int max_steps,

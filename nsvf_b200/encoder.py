@@ -176,16 +176,19 @@ class SparseVoxelEncoder(nn.Module):
                                        self.voxel_size)
         return ray_start, ray_dir, hits
 
-    def ray_sample(self, intersection_outputs):
-        sampled_idx, sampled_depth, sampled_dists = clib.inverse_cdf_sampling(
+    def ray_sample(self, intersection_outputs, trimmed=False):
+        """encoder.py:538-556.  The clamp / masked_fill post-processing runs inside the sampler kernel.  `trimmed=True`
+        (extension, used by NSVFPipeline with our VolumeRenderer) returns rows of max_steps slots of which only the
+        first `sampled_point_count[r]` are written — no padding traffic, no max_len host sync."""
+        sampled_idx, sampled_depth, sampled_dists, ray_len, _ = clib.inverse_cdf_sampling_rows(
             intersection_outputs["intersected_voxel_idx"], intersection_outputs["min_depth"],
             intersection_outputs["max_depth"], intersection_outputs["probs"], intersection_outputs["steps"],
-            -1, self.deterministic_step or (not self.training))
-        sampled_dists = sampled_dists.clamp(min=0.0)
-        sampled_depth.masked_fill_(sampled_idx.eq(-1), MAX_DEPTH)
-        sampled_dists.masked_fill_(sampled_idx.eq(-1), 0.0)
-        return {"sampled_point_depth": sampled_depth, "sampled_point_distance": sampled_dists,
-                "sampled_point_voxel_idx": sampled_idx}
+            -1, self.deterministic_step or (not self.training), trimmed=trimmed, pad_depth=MAX_DEPTH)
+        samples = {"sampled_point_depth": sampled_depth, "sampled_point_distance": sampled_dists,
+                   "sampled_point_voxel_idx": sampled_idx}
+        if trimmed:
+            samples["sampled_point_count"] = ray_len
+        return samples
 
     @torch.enable_grad()
     def forward(self, samples, encoder_states):

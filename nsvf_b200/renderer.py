@@ -6,18 +6,23 @@ Same interface — forward(input_fn, field_fn, ray_start, ray_dir, samples, enco
 <= chunk_size, and early termination is evaluated at those chunk boundaries only), so the set of samples that
 reach the field is identical to the reference's, including under raymarching_tolerance > 0.
 
-What changes underneath:
-  * the schedule is computed from windowed device->host copies of per-column sample counts (48 columns per copy;
-    re-fetched after a chunk only when early termination changed who is alive), instead of one `.sum()` host sync
-    per sample column (K+1 syncs);
-  * boolean-mask compaction of five tensors + masked_scatter back (renderer.py:100,109-114) become the
-    compaction kernels (csrc/compact.cu) and one index_put per output;
-  * compositing (renderer.py:193-218) is the fused ops.composite kernel with its own backward.
+Two implementations of forward_chunk:
+
+  * the ray-marching PLAN (csrc/march.cu; default): the chunk schedule lives on the device.  Samples stay in trimmed
+    rows (nothing beyond a ray's last sample is read or written), per window there are three launches of ours
+    (single-pass compaction -> [input_fn, field_fn] -> epilogue: free energy, scatter into the rows, early
+    termination, next window) and — only with early termination — one 4-int readback; without it the whole window
+    list is read once.  Compositing runs on the trimmed rows, and ONE autograd node covers the whole call: its
+    backward is the compositing backward followed by one gather kernel per window;
+  * the GENERAL path (csrc/compact.cu; inputs whose valid samples are not a prefix of their row, `global_weights`,
+    fields without sigma): windowed column counts, count/scan/fill compaction, index_put, dense compositing.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
+from torch.autograd import Function
 
 from . import _lib, ops
 
@@ -80,6 +85,74 @@ def compact_samples(sampled_idx, sampled_depth, sampled_dists, ray_start, ray_di
     return vox, xyz, dirs, dists, flat
 
 
+class _MarchRecord:
+    """What one forward_chunk of the plan path leaves behind for compositing and its backward."""
+
+    def __init__(self, B, K, ldk, depth, lens, early_stop, eval_len, fe_rows, tex_rows, rows_padded):
+        self.B, self.K, self.ldk = B, K, ldk
+        self.depth, self.lens, self.early_stop, self.eval_len = depth, lens, early_stop, eval_len
+        self.fe_rows, self.tex_rows, self.rows_padded = fe_rows, tex_rows, rows_padded
+        self.windows = []      # (start, end, M, ray_off, sigma, texture, sigma_f32, noise_f32, dists_f32)
+
+
+class _MarchComposite(Function):
+    """Compositing over the trimmed rows a plan run filled (renderer.py:193-218), differentiable w.r.t. every window's
+    field outputs: backward = trimmed compositing backward + one gather kernel per window (march_epilogue_bwd)."""
+
+    @staticmethod
+    def forward(ctx, rec, want_probs, *field_outputs):
+        B, K = rec.B, rec.K
+        dev = rec.fe_rows.device
+        probs = torch.empty((B, K), dtype=torch.float32, device=dev) if want_probs else None
+        depth = torch.empty(B, dtype=torch.float32, device=dev)
+        missed = torch.empty(B, dtype=torch.float32, device=dev)
+        colors = torch.empty((B, 3), dtype=torch.float32, device=dev)
+        maxd = torch.empty(B, dtype=torch.float32, device=dev)
+        mind = torch.empty(B, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_L.nsvf_composite_trimmed_fwd(
+                _lib.current_stream(dev), B, K, rec.ldk, _p(rec.eval_len), _p(rec.lens), _p(rec.early_stop),
+                _p(rec.fe_rows), _p(rec.tex_rows), _p(rec.depth), _p(probs), _p(depth), _p(missed),
+                _p(colors if rec.tex_rows is not None else None), _p(maxd), _p(mind), 10000.0, int(rec.rows_padded)))
+        if rec.tex_rows is None:
+            colors.zero_()
+        ctx.rec = rec
+        ctx.mark_non_differentiable(maxd, mind)
+        if probs is None:
+            probs = torch.empty(0, device=dev)
+            ctx.mark_non_differentiable(probs)
+        return probs, depth, missed, colors, maxd, mind
+
+    @staticmethod
+    def backward(ctx, g_probs, g_depth, g_missed, g_colors, _g_maxd, _g_mind):
+        rec = ctx.rec
+        B, K = rec.B, rec.K
+        dev = rec.fe_rows.device
+
+        def c(t):
+            return None if t is None else t.float().contiguous()
+        g_probs = c(g_probs) if (g_probs is not None and g_probs.numel() == B * K) else None
+        g_depth, g_missed, g_colors = c(g_depth), c(g_missed), c(g_colors)
+        has_tex = rec.tex_rows is not None
+        g_fe = torch.empty(B * K, dtype=torch.float32, device=dev)
+        g_tex = torch.empty(B * K * 3, dtype=torch.float32, device=dev) if has_tex else None
+        grads = []
+        with torch.cuda.device(dev):
+            st = _lib.current_stream(dev)
+            _lib.check(_L.nsvf_composite_trimmed_bwd(
+                st, B, K, rec.ldk, _p(rec.eval_len), _p(rec.fe_rows), _p(rec.tex_rows), _p(rec.depth), _p(g_probs),
+                _p(g_depth), _p(g_missed), _p(g_colors if has_tex else None), _p(g_fe), _p(g_tex)))
+            for (start, end, M, ray_off, sigma, texture, sg, nz, dd) in rec.windows:
+                gs = torch.empty(M, dtype=torch.float32, device=dev)
+                gt = torch.empty((M, 3), dtype=torch.float32, device=dev) if texture is not None else None
+                _lib.check(_L.nsvf_march_epilogue_bwd(st, B, K, start, end, _p(ray_off), _p(g_fe), _p(g_tex), _p(sg),
+                                                      _p(nz), _p(dd), _p(gs), _p(gt)))
+                grads.append(gs.view_as(sigma).to(sigma.dtype))
+                if texture is not None:
+                    grads.append(gt.view_as(texture).to(texture.dtype))
+        return (None, None, *grads)
+
+
 class VolumeRenderer(nn.Module):
     def __init__(self, chunk_size=64, valid_chunk_size=None, discrete_regularization=False,
                  raymarching_tolerance=0.0):
@@ -88,6 +161,7 @@ class VolumeRenderer(nn.Module):
         self.valid_chunk_size = 1024 * (valid_chunk_size if valid_chunk_size is not None else chunk_size)
         self.discrete_reg = discrete_regularization
         self.raymarching_tolerance = raymarching_tolerance
+        self.return_probs = True      # 'probs' [B,K] of the reference's results; False skips the dense write
 
     # one field evaluation over the valid samples of columns [col0, col1)  (reference forward_once, :77-133)
     def forward_once(self, input_fn, field_fn, ray_start, ray_dir, samples, encoder_states, col0, col1,
@@ -115,6 +189,122 @@ class VolumeRenderer(nn.Module):
 
     def forward_chunk(self, input_fn, field_fn, ray_start, ray_dir, samples, encoder_states,
                       output_types=("sigma", "texture"), global_weights=None, noise_fn=None):
+        """renderer.py:135-232.  `noise_fn(start, end, M)` (tests) supplies the sigma noise of a window instead of
+        torch.normal_."""
+        if (global_weights is None and "sigma" in output_types and samples["sampled_point_voxel_idx"].dim() == 2
+                and not os.environ.get("NSVF_RENDER_GENERAL")):
+            results = self._forward_chunk_plan(input_fn, field_fn, ray_start, ray_dir, samples, encoder_states,
+                                               output_types, noise_fn)
+            if results is not None:
+                return results
+        return self._forward_chunk_general(input_fn, field_fn, ray_start, ray_dir, samples, encoder_states,
+                                           output_types, global_weights, noise_fn)
+
+    def _forward_chunk_plan(self, input_fn, field_fn, ray_start, ray_dir, samples, encoder_states, output_types,
+                            noise_fn):
+        sidx, depth, dists = (samples["sampled_point_voxel_idx"], samples["sampled_point_depth"],
+                              samples["sampled_point_distance"])
+        lens = samples.get("sampled_point_count", None)
+        # rows may be strided views (the sampler returns [:, :max_len] slices); anything else is made dense
+        ok = (sidx.dtype == torch.int32 and depth.dtype == torch.float32 and dists.dtype == torch.float32
+              and sidx.stride(1) == 1 and depth.stride(1) == 1 and dists.stride(1) == 1
+              and sidx.stride(0) == depth.stride(0) == dists.stride(0))
+        if not ok:
+            sidx, depth, dists = sidx.int().contiguous(), depth.float().contiguous(), dists.float().contiguous()
+        B, K = sidx.shape
+        ldk = sidx.stride(0) if B > 1 else max(K, sidx.stride(0))
+        dev = sidx.device
+        ray_start, ray_dir = ray_start.float().contiguous(), ray_dir.float().contiguous()
+        tolerance = self.raymarching_tolerance
+        chunk_size = self.chunk_size if self.training else self.valid_chunk_size
+        tol = -math.log(tolerance) if tolerance > 0 else 0.0
+        want_tex = "texture" in output_types
+        all_windows = tol <= 0
+        rows_padded = lens is None
+        with torch.cuda.device(dev):
+            st = _lib.current_stream(dev)
+            plan = torch.zeros(_L.nsvf_march_plan_bytes(B, K) // 4 + 2, dtype=torch.int32, device=dev)
+            if lens is None:
+                lens = torch.empty(B, dtype=torch.int32, device=dev)
+                _lib.check(_L.nsvf_march_ray_lengths(st, B, K, ldk, _p(sidx), _p(lens), _p(plan)))
+            else:
+                lens = lens.int().contiguous()
+            info = self._host_info(16 + 3 * (K + 1))
+            _lib.check(_L.nsvf_march_begin(st, B, K, chunk_size, _p(lens), None, int(all_windows), _p(plan),
+                                           info.data_ptr(), info.numel()))
+            torch.cuda.current_stream(dev).synchronize()
+            head = info[:16].tolist()
+            if head[4]:
+                return None                      # some row's valid samples are not a prefix: general path
+            if all_windows:
+                windows = info[16: 16 + 3 * head[5]].view(-1, 3).tolist()
+            else:
+                windows = None if head[3] else [head[0:3]]
+            early_stop = torch.zeros(B, dtype=torch.uint8, device=dev)
+            eval_len = torch.zeros(B, dtype=torch.int32, device=dev)
+            acc_fe = torch.zeros(B, dtype=torch.float32, device=dev) if tol > 0 else None
+            fe_rows = torch.empty(B * K, dtype=torch.float32, device=dev)
+            tex_rows = torch.empty(B * K * 3, dtype=torch.float32, device=dev) if want_tex else None
+            record = _MarchRecord(B, K, ldk, depth, lens, early_stop, eval_len, fe_rows, tex_rows, rows_padded)
+            evals, launch_no, w = 0, 0, 0
+            while windows is not None and w < len(windows):
+                start, end, M = windows[w]
+                w += 1
+                vox = torch.empty(M, dtype=torch.int32, device=dev)
+                xyz = torch.empty((M, 3), dtype=torch.float32, device=dev)
+                dirs = torch.empty((M, 3), dtype=torch.float32, device=dev)
+                dists_c = torch.empty(M, dtype=torch.float32, device=dev)
+                ray_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
+                _lib.check(_L.nsvf_march_compact(st, B, K, ldk, start, end, _p(lens), _p(early_stop), _p(sidx),
+                                                 _p(depth), _p(dists), _p(ray_start), _p(ray_dir), _p(vox), _p(xyz),
+                                                 _p(dirs), _p(dists_c), _p(ray_off), _p(plan), launch_no))
+                launch_no += 1
+                field_inputs = input_fn({"sampled_point_voxel_idx": vox, "sampled_point_xyz": xyz,
+                                         "sampled_point_ray_direction": dirs, "sampled_point_distance": dists_c},
+                                        encoder_states)
+                field_outputs = field_fn(field_inputs, outputs=list(output_types))
+                sigma = field_outputs["sigma"]
+                texture = field_outputs["texture"] if want_tex else None
+                if noise_fn is not None:
+                    noise = noise_fn(start, end, M)
+                elif self.discrete_reg or self.training:
+                    noise = torch.zeros_like(sigma).normal_()                       # renderer.py:118
+                else:
+                    noise = None
+                sg = sigma.detach().float().contiguous()
+                tx = texture.detach().float().contiguous() if texture is not None else None
+                nz = noise.float().contiguous() if noise is not None else None
+                dd = field_inputs["dists"].detach().float().contiguous()
+                _lib.check(_L.nsvf_march_epilogue(st, B, K, start, end, _p(ray_off), _p(lens), _p(early_stop),
+                                                  _p(acc_fe), _p(eval_len), _p(sg), _p(nz), _p(dd), _p(tx), float(tol),
+                                                  _p(fe_rows), _p(tex_rows), chunk_size, int(not all_windows),
+                                                  _p(plan), info.data_ptr()))
+                evals += M
+                record.windows.append((start, end, M, ray_off, sigma, texture, sg, nz, dd))
+                if not all_windows:
+                    torch.cuda.current_stream(dev).synchronize()
+                    head = info[:4].tolist()
+                    if not head[3]:
+                        windows.append(head[0:3])
+            outs = _MarchComposite.apply(record, self.return_probs, *[t for wnd in record.windows for t in
+                                                                       (wnd[4], wnd[5]) if t is not None])
+        probs, depth_out, missed, colors, max_depths, min_depths = outs
+        results = {"probs": probs, "depths": depth_out, "max_depths": max_depths, "min_depths": min_depths,
+                   "missed": missed, "ae": evals}
+        if want_tex:
+            results["colors"] = colors
+        return results
+
+    def _host_info(self, n):
+        """Pinned host words the plan kernels publish the schedule to (device writes through the unified address space)."""
+        buf = getattr(self, "_info_buf", None)
+        if buf is None or buf.numel() < n:
+            buf = torch.zeros(max(n, 4096), dtype=torch.int32).pin_memory()
+            self._info_buf = buf
+        return buf
+
+    def _forward_chunk_general(self, input_fn, field_fn, ray_start, ray_dir, samples, encoder_states,
+                               output_types=("sigma", "texture"), global_weights=None, noise_fn=None):
         # dense, typed copies ONCE per call (the sampler returns [:, :max_len] views)
         samples = {"sampled_point_depth": samples["sampled_point_depth"].float().contiguous(),
                    "sampled_point_distance": samples["sampled_point_distance"].float().contiguous(),
@@ -138,7 +328,7 @@ class VolumeRenderer(nn.Module):
                 total = None if early_stop is not None else size_so_far
                 out, n = self.forward_once(input_fn, field_fn, ray_start, ray_dir, samples, encoder_states, start, i,
                                            early_stop=early_stop, total=total, output_types=output_types,
-                                           noise=None if noise_fn is None else noise_fn(start, i))
+                                           noise=None if noise_fn is None else noise_fn(start, i, None))
                 if out is not None:
                     evals += n
                     flats.append(out["flat"])

@@ -114,8 +114,8 @@ def make_scene(name, seed=0):
         return Scene(bbox_voxels([-0.875] * 3, [0.875] * 3, 0.25), 0.25, max_hits=60, seed=seed)
     if name == "C2":      # nsvf_base training: bbox centres +-1.2, voxel 0.4 -> 343 voxels, step 0.05
         return Scene(bbox_voxels([-1.2] * 3, [1.2] * 3, 0.4), 0.4, max_hits=60, seed=seed)
-    if name in ("C3", "C4"):   # 13^3 grid carved to ~1.7k voxels, split 2x (C3) / 3x (C4)
-        pts = carve_shell(bbox_voxels([-2.4] * 3, [2.4] * 3, 0.4))
+    if name in ("C3", "C4"):   # 13^3 grid carved to 1752 voxels, split 2x (C3: 112 128 voxels) / 3x (C4: 897 024)
+        pts = carve_shell(bbox_voxels([-2.4] * 3, [2.4] * 3, 0.4), 0.35, 1.1)
         times = 2 if name == "C3" else 3
         pts, vs = split_points(pts, 0.4, times)
         return Scene(pts, vs, max_hits=135 if name == "C3" else 202, seed=seed)
