@@ -192,39 +192,27 @@ NSVF_API int nsvf_composite_bwd(nsvf_stream_t stream, long long B, int K, const 
                        const float* grad_missed, const float* grad_colors, float* grad_free_energy,
                        float* grad_texture);
 
-/* The same compositing over TRIMMED rows (see "ray-marching plan" below): only eval_len[ray] leading samples of a
- * ray carry free energy / texture (anything beyond counts as zero free energy) and only lens[ray] leading samples
- * carry a depth; free_energy / texture / probs rows have stride K, sampled_depth rows stride ldk >= K.
- * Also produces the two per-ray extrema of fairnr/modules/renderer.py:210-211:
- *   max_depths f32 [B] = max depth over the ray's samples, -1 for rays flagged in early_stop (u8 [B], optional)
- *   min_depths f32 [B] = min over the WHOLE padded row: the samples and, when lens[ray] < K, the padding value —
- *                        pad_depth, or (depth_rows_padded != 0) the first padding slot of the row itself.
- * probs (optional) is written densely, zeros beyond the evaluated prefix.  bwd writes gradients for the evaluated
- * prefix only. */
-NSVF_API int nsvf_composite_trimmed_fwd(nsvf_stream_t stream, long long B, int K, long long ldk, const int* eval_len,
-                                        const int* lens, const unsigned char* early_stop, const float* free_energy,
-                                        const float* texture, const float* sampled_depth, float* probs, float* depth,
-                                        float* missed, float* colors, float* max_depths, float* min_depths,
-                                        float pad_depth, int depth_rows_padded);
-NSVF_API int nsvf_composite_trimmed_bwd(nsvf_stream_t stream, long long B, int K, long long ldk, const int* eval_len,
-                                        const float* free_energy, const float* texture, const float* sampled_depth,
-                                        const float* grad_probs, const float* grad_depth, const float* grad_missed,
-                                        const float* grad_colors, float* grad_free_energy, float* grad_texture);
-
 /* ---- ray-marching plan: the chunk loop of the renderer on the device ---------------------------------------
  * Replaces the loop of VolumeRenderer.forward_chunk / forward_once, fairnr/modules/renderer.py:77-191: per-column
  * `hits[:, i].sum()` host syncs (:157-158,187), boolean-mask compaction (:88-100), masked_scatter into zero-filled
- * [B,K] tensors (:109-131), free_energy = relu(noise + sigma) * dists * 7 (:117-121) and the early-termination
- * update after every field evaluation (:170-174).  Same schedule, same samples reach the field.
- * Rows are TRIMMED: ray r owns slots [0, lens[r]) of row r of sampled_idx / sampled_depth / sampled_dists (row
+ * [B,K] tensors (:109-131), free_energy = relu(noise + sigma) * dists * 7 (:117-121), the early-termination
+ * update after every field evaluation (:170-174), and the compositing block (:193-218) with its two per-ray depth
+ * extrema (:210-211).  Same schedule, same samples reach the field.
+ * Input rows are TRIMMED: ray r owns slots [0, lens[r]) of row r of sampled_idx / sampled_depth / sampled_dists (row
  * stride ldk >= K); valid samples must be a prefix of the row (nsvf_march_ray_lengths reports rows where they are
- * not in plan word 4; callers then use nsvf_compact_* below).
+ * not in plan word 4; callers then use nsvf_compact_* below).  Inside the plan everything is SLOT-MAJOR: planes
+ * [K][ldb] with ldb = nsvf_march_plane_stride(B) >= B (entry (k, r) at k*ldb + r, defined for k < lens[r]; texture
+ * planes [K][ldb][3]), so that one thread per ray walks a column window with coalesced accesses.
  *   plan        : device scratch of nsvf_march_plan_bytes(B, K) bytes, ZEROED once per forward_chunk call
  *   host_info   : i32 [>= 16 (+ 3 per window)] in PINNED host memory (written by the device through the unified
  *                 address space): [0] start, [1] end, [2] valid samples of the window, [3] done, [4] holes,
  *                 [5] number of windows, [8] total samples; with all_windows the triplets (start, end, count) of
  *                 every window follow from word 16.  Read it after synchronising the stream.
  *   nsvf_march_ray_lengths : lens i32 [B] from a padded sampled_idx (idx != -1)
+ *   nsvf_march_transpose   : columns [k_begin, k_end) (k_begin a multiple of 32) of idxT i32 / depthT, distsT f32 from
+ *                            the rows (tiled shared-memory transpose); rays flagged in early_stop (optional) are
+ *                            skipped, so with early termination the planes are filled block by block as the window
+ *                            loop advances and stopped rays cost nothing
  *   nsvf_march_begin       : column counts from lens; publishes the first window, or (all_windows = 1, valid when
  *                            there is no early termination) the complete window list
  *   nsvf_march_compact     : compacts the samples of window [start, end) of the live rays in row-major order (the
@@ -232,33 +220,53 @@ NSVF_API int nsvf_composite_trimmed_bwd(nsvf_stream_t stream, long long B, int K
  *                            ray_dir * depth, out_dir f32 [M,3], out_dists f32 [M] (either optional), and
  *                            ray_off i32 [B+1] = exclusive offsets of the rays in that order.  launch_no = number of
  *                            earlier nsvf_march_compact launches on this plan (0, 1, 2, ...).
- *   nsvf_march_epilogue    : sigma f32 [M] (+ noise f32 [M] or NULL, dists f32 [M]) -> free_energy_rows f32 [B,K],
- *                            texture f32 [M,3] -> texture_rows f32 [B,K,3] at the window's slots; eval_len i32 [B] =
+ *   nsvf_march_epilogue    : sigma f32 [M] (+ noise f32 [M] or NULL, dists f32 [M]) -> feT f32 [K][B],
+ *                            texture f32 [M,3] -> texT f32 [K][B][3] at the window's slots; eval_len i32 [B] =
  *                            evaluated prefix; with tolerance > 0: acc_free_energy f32 [B] += row sums, early_stop
  *                            u8 [B] = acc > tolerance, column counts updated; with schedule_next the next window is
  *                            published to plan / host_info by the last CTA.
- *   nsvf_march_epilogue_bwd: gradients of the rows back to the compacted order of one window:
- *                            grad_sigma = (g_fe * 7) * dists * [noise + sigma > 0], grad_texture = g_tex. */
+ *   nsvf_march_epilogue_bwd: gradients of the planes back to the compacted order of one window:
+ *                            grad_sigma = (g_fe * 7) * dists * [noise + sigma > 0], grad_texture = g_tex.
+ *   nsvf_march_composite_fwd: probsT f32 [K][B] (optional, zeros beyond the evaluated prefix), depth / missed f32 [B],
+ *                            colors f32 [B,3]; max_depths f32 [B] = max sample depth, -1 for rays flagged in
+ *                            early_stop; min_depths f32 [B] = min over the WHOLE padded row: the samples and, when
+ *                            lens[r] < K, the padding — the first padding slot of padded_depth_rows (row stride ldk)
+ *                            when given, else pad_depth.  lazy_planes != 0: the planes of a ray flagged in early_stop
+ *                            hold its evaluated prefix only (block-wise transpose); its minimum is then taken over
+ *                            that prefix, which is exact for depth-ordered (ray-marched) samples.
+ *   nsvf_march_composite_bwd: g_feT [K][B], g_texT [K][B][3] for the evaluated prefix; scratchT f32 [K][B]. */
+NSVF_API long long nsvf_march_plane_stride(long long B);
 NSVF_API size_t nsvf_march_plan_bytes(long long B, int K);
 NSVF_API int nsvf_march_ray_lengths(nsvf_stream_t stream, long long B, int K, long long ldk, const int* sampled_idx,
                                     int* lens, void* plan);
+NSVF_API int nsvf_march_transpose(nsvf_stream_t stream, long long B, int K, long long ldk, int k_begin, int k_end,
+                                  const unsigned char* early_stop, const int* lens, const int* sampled_idx, const float* sampled_depth, const float* sampled_dists,
+                                  int* idxT, float* depthT, float* distsT);
 NSVF_API int nsvf_march_begin(nsvf_stream_t stream, long long B, int K, int chunk_size, const int* lens,
                               const unsigned char* early_stop, int all_windows, void* plan, int* host_info,
                               int host_capacity_ints);
-NSVF_API int nsvf_march_compact(nsvf_stream_t stream, long long B, int K, long long ldk, int start, int end,
-                                const int* lens, const unsigned char* early_stop, const int* sampled_idx,
-                                const float* sampled_depth, const float* sampled_dists, const float* ray_start,
-                                const float* ray_dir, int* out_vox, float* out_xyz, float* out_dir, float* out_dists,
-                                int* ray_off, void* plan, int launch_no);
+NSVF_API int nsvf_march_compact(nsvf_stream_t stream, long long B, int K, int start, int end, const int* lens,
+                                const unsigned char* early_stop, const int* idxT, const float* depthT,
+                                const float* distsT, const float* ray_start, const float* ray_dir, int* out_vox,
+                                float* out_xyz, float* out_dir, float* out_dists, int* ray_off, void* plan,
+                                int launch_no);
 NSVF_API int nsvf_march_epilogue(nsvf_stream_t stream, long long B, int K, int start, int end, const int* ray_off,
                                  const int* lens, unsigned char* early_stop, float* acc_free_energy, int* eval_len,
                                  const float* sigma, const float* noise, const float* dists, const float* texture,
-                                 float tolerance, float* free_energy_rows, float* texture_rows, int chunk_size,
-                                 int schedule_next, void* plan, int* host_info);
+                                 float tolerance, float* feT, float* texT, int chunk_size, int schedule_next,
+                                 void* plan, int* host_info);
 NSVF_API int nsvf_march_epilogue_bwd(nsvf_stream_t stream, long long B, int K, int start, int end, const int* ray_off,
-                                     const float* grad_free_energy_rows, const float* grad_texture_rows,
-                                     const float* sigma, const float* noise, const float* dists, float* grad_sigma,
-                                     float* grad_texture);
+                                     const float* g_feT, const float* g_texT, const float* sigma, const float* noise,
+                                     const float* dists, float* grad_sigma, float* grad_texture);
+NSVF_API int nsvf_march_composite_fwd(nsvf_stream_t stream, long long B, int K, const int* eval_len, const int* lens,
+                                      const unsigned char* early_stop, const float* feT, const float* texT,
+                                      const float* depthT, float* probsT, float* depth, float* missed, float* colors,
+                                      float* max_depths, float* min_depths, const float* padded_depth_rows,
+                                      long long ldk, float pad_depth, int lazy_planes);
+NSVF_API int nsvf_march_composite_bwd(nsvf_stream_t stream, long long B, int K, const int* eval_len, const float* feT,
+                                      const float* texT, const float* depthT, const float* grad_probsT,
+                                      const float* grad_depth, const float* grad_missed, const float* grad_colors,
+                                      float* g_feT, float* g_texT, float* scratchT);
 
 /* ---- sample compaction ---------------------------------------------------------------------------------
  * Replaces the boolean-mask compaction of VolumeRenderer.forward_once, fairnr/modules/renderer.py:88-100

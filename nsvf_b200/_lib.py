@@ -41,16 +41,18 @@ SIGNATURES = {
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                              c_int]),
-    "nsvf_composite_trimmed_fwd": (c_int, [c_void_p, c_ll, c_int, c_ll] + [c_void_p] * 12 + [c_float, c_int]),
-    "nsvf_composite_trimmed_bwd": (c_int, [c_void_p, c_ll, c_int, c_ll] + [c_void_p] * 10),
+    "nsvf_march_plane_stride": (c_ll, [c_ll]),
     "nsvf_march_plan_bytes": (c_size_t, [c_ll, c_int]),
     "nsvf_march_ray_lengths": (c_int, [c_void_p, c_ll, c_int, c_ll, c_void_p, c_void_p, c_void_p]),
+    "nsvf_march_transpose": (c_int, [c_void_p, c_ll, c_int, c_ll, c_int, c_int] + [c_void_p] * 8),
     "nsvf_march_begin": (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int]),
-    "nsvf_march_compact": (c_int, [c_void_p, c_ll, c_int, c_ll, c_int, c_int] + [c_void_p] * 13 + [c_int]),
+    "nsvf_march_compact": (c_int, [c_void_p, c_ll, c_int, c_int, c_int] + [c_void_p] * 13 + [c_int]),
     "nsvf_march_epilogue": (c_int, [c_void_p, c_ll, c_int, c_int, c_int] + [c_void_p] * 9 + [c_float, c_void_p,
                                                                                              c_void_p, c_int, c_int,
                                                                                              c_void_p, c_void_p]),
     "nsvf_march_epilogue_bwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_int] + [c_void_p] * 8),
+    "nsvf_march_composite_fwd": (c_int, [c_void_p, c_ll, c_int] + [c_void_p] * 13 + [c_ll, c_float, c_int]),
+    "nsvf_march_composite_bwd": (c_int, [c_void_p, c_ll, c_int] + [c_void_p] * 11),
     "nsvf_uniform_ray_sampling": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float] + [c_void_p] * 7),
     "nsvf_octree_build": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p]),
     "nsvf_octree_flatten": (c_int, [c_void_p, c_void_p, c_ll]),
@@ -119,3 +121,24 @@ def ptr(t):
 def current_stream(device):
     import torch
     return torch.cuda.current_stream(device).cuda_stream
+
+
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_guard(device):
+    """`with torch.cuda.device(device)` only when `device` is not already current (the context manager costs several
+    microseconds per call, which matters on paths that launch one small kernel per call)."""
+    import torch
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)

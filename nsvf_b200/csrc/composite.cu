@@ -257,26 +257,3 @@ extern "C" int nsvf_composite_bwd(nsvf_stream_t stream_, long long B, int K, con
                               grad_depth, grad_missed, grad_colors, grad_free_energy, grad_texture);
 }
 
-extern "C" int nsvf_composite_trimmed_fwd(nsvf_stream_t stream_, long long B, int K, long long ldk, const int* eval_len,
-                                          const int* lens, const unsigned char* early_stop, const float* free_energy,
-                                          const float* texture, const float* sampled_depth, float* probs, float* depth,
-                                          float* missed, float* colors, float* max_depths, float* min_depths,
-                                          float pad_depth, int depth_rows_padded) {
-  NSVF_REQUIRE(B >= 0 && K >= 0 && ldk >= K, "composite_trimmed_fwd: bad sizes");
-  NSVF_REQUIRE(eval_len != nullptr && lens != nullptr, "composite_trimmed_fwd: eval_len and lens are required");
-  if (B == 0) return 0;
-  return composite_fwd_launch((cudaStream_t)stream_, B, K, ldk, eval_len, lens, early_stop, free_energy, texture,
-                              sampled_depth, probs, depth, missed, colors, max_depths, min_depths, pad_depth,
-                              depth_rows_padded);
-}
-
-extern "C" int nsvf_composite_trimmed_bwd(nsvf_stream_t stream_, long long B, int K, long long ldk, const int* eval_len,
-                                          const float* free_energy, const float* texture, const float* sampled_depth,
-                                          const float* grad_probs, const float* grad_depth, const float* grad_missed,
-                                          const float* grad_colors, float* grad_free_energy, float* grad_texture) {
-  NSVF_REQUIRE(B >= 0 && K >= 0 && ldk >= K, "composite_trimmed_bwd: bad sizes");
-  NSVF_REQUIRE(eval_len != nullptr, "composite_trimmed_bwd: eval_len is required");
-  if (B == 0 || K == 0) return 0;
-  return composite_bwd_launch((cudaStream_t)stream_, B, K, ldk, eval_len, free_energy, texture, sampled_depth,
-                              grad_probs, grad_depth, grad_missed, grad_colors, grad_free_energy, grad_texture);
-}

@@ -8,8 +8,11 @@
 // rays have accumulated enough free energy to stop.  Here the same schedule — the identical windows, hence the
 // identical set of samples reaching the field — is kept on the device:
 //
-//   * samples live in TRIMMED rows: ray r owns slots [0, len_r) of its row (row stride ldk), nothing beyond len_r is
-//     ever read or written, so traffic is proportional to the samples that exist, not to B x K;
+//   * the call's samples are transposed ONCE into slot-major planes [K][B] (march_transpose_kernel, a tiled smem
+//     transpose that only touches the lens[r] valid slots of each row).  A window is a range of sample columns, so with
+//     one thread per ray every access of the window loop — compaction reads, free-energy / texture writes, the
+//     compositing scan and its backward — is coalesced across the warp, and nothing beyond a ray's last sample is
+//     ever read or written: traffic is proportional to the samples that exist, not to B x K;
 //   * per-column counts of live samples are maintained incrementally: a histogram of the row lengths at the start,
 //     and a (-1 at the window end, +1 at len_r) difference pair for every ray that stops; the LAST CTA of the
 //     epilogue kernel integrates the differences and picks the next window (same rule as renderer.py:157-158), so
@@ -36,8 +39,15 @@ constexpr int kHdr = 16;
 constexpr int H_START = 0, H_END = 1, H_COUNT = 2, H_DONE = 3, H_HOLES = 4, H_NWIN = 5, H_TICKET = 6, H_CTAS = 7,
               H_TOTAL = 8;
 constexpr int kTile = 256;        // rays per compaction tile
-constexpr int kNarrow = 12;       // windows up to this many columns: one thread per ray; wider: one warp per ray
 
+// Row stride (in elements) of the slot-major planes: B rounded up to 32 rays, and never a multiple of 1024 — with
+// B = 2^19 rays (chunk_size 512) consecutive slots of a ray would lie exactly 2 MiB apart and every access of the
+// transpose would fall into the same memory channel.
+__host__ __device__ inline long long plane_stride(long long B) {
+  long long s = (B + 31) / 32 * 32;
+  if (s % 1024 == 0) s += 32;
+  return s;
+}
 __host__ __device__ inline long long plan_tiles(long long B) { return (B + kTile - 1) / kTile; }
 __host__ __device__ inline size_t plan_words_before_tiles(int K) {
   size_t w = (size_t)kHdr + (size_t)K + (size_t)K + 1;
@@ -174,6 +184,73 @@ march_ray_lengths_kernel(long long B, int K, long long ldk, const int* __restric
   if (holes && lane == 0) atomicOr(plan + H_HOLES, 1);
 }
 
+// ---- row-major trimmed rows -> slot-major planes ------------------------------------------------------------------
+// idxT / depthT / distsT [K][B]: entry (k, r) is defined for k < lens[r] only.  A CTA takes kTR = 128 rays and walks
+// their slots in tiles of 32: each warp reads 32 consecutive slots of 8 rays (128-byte row pieces), the tile is turned
+// in shared memory, and each warp writes 2 slots for the 128 rays (512 contiguous bytes per slot and plane, so the
+// write stream keeps some DRAM page locality although consecutive slots of a plane lie 4*B bytes apart).
+constexpr int kTR = 128;
+__global__ void __launch_bounds__(512)
+march_transpose_kernel(long long B, long long ldb, int K, long long ldk, int k_begin, int k_end,
+                       const unsigned char* __restrict__ early_stop, const int* __restrict__ lens, const int* __restrict__ idx,
+                       const float* __restrict__ depth, const float* __restrict__ dists, int* __restrict__ idxT,
+                       float* __restrict__ depthT, float* __restrict__ distsT) {
+  extern __shared__ int tr_smem[];
+  int (*t_i)[33] = reinterpret_cast<int (*)[33]>(tr_smem);
+  float (*t_d)[33] = reinterpret_cast<float (*)[33]>(tr_smem + kTR * 33);
+  float (*t_s)[33] = reinterpret_cast<float (*)[33]>(tr_smem + 2 * kTR * 33);
+  int* s_len = tr_smem + 3 * kTR * 33;
+  __shared__ int s_max;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;   // 16 warps
+  for (long long r0 = (long long)blockIdx.x * kTR; r0 < B; r0 += (long long)gridDim.x * kTR) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    if (threadIdx.x < kTR) {
+      int l = (r0 + threadIdx.x < B) ? lens[r0 + threadIdx.x] : 0;
+      l = l < 0 ? 0 : (l > k_end ? k_end : l);
+      if (l > 0 && early_stop != nullptr && early_stop[r0 + threadIdx.x]) l = 0;   // stopped rays need no more columns
+      s_len[threadIdx.x] = l;
+      int m = l;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(NSVF_FULL_MASK, m, o));
+      if (lane == 0) atomicMax(&s_max, m);
+    }
+    __syncthreads();
+    const int maxlen = s_max;
+    for (int k0 = k_begin; k0 < maxlen; k0 += 32) {
+#pragma unroll
+      for (int j = 0; j < kTR / 16; ++j) {
+        const int rr = warp * (kTR / 16) + j;
+        const int k = k0 + lane;
+        if (k < s_len[rr]) {
+          const long long a = (r0 + rr) * ldk + k;
+          t_i[rr][lane] = idx[a];
+          t_d[rr][lane] = depth[a];
+          t_s[rr][lane] = dists[a];
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int kk = warp * 2 + j;
+        const int k = k0 + kk;
+#pragma unroll
+        for (int q = 0; q < kTR / 32; ++q) {
+          const int rr = q * 32 + lane;
+          if (k < s_len[rr]) {
+            const long long a = (long long)k * ldb + r0 + rr;
+            idxT[a] = t_i[rr][kk];
+            depthT[a] = t_d[rr][kk];
+            distsT[a] = t_s[rr][kk];
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // ---- begin: histogram of the row lengths -> counts, first window / all windows ---------------------------------
 __global__ void __launch_bounds__(256)
 march_begin_kernel(long long B, int K, int chunk_size, const int* __restrict__ lens,
@@ -216,16 +293,15 @@ __device__ __forceinline__ int window_samples(int len, int start, int end) {
 }
 
 __global__ void __launch_bounds__(kTile)
-march_compact_kernel(long long B, int K, long long ldk, int start, int end, const int* __restrict__ lens,
-                     const unsigned char* __restrict__ early_stop, const int* __restrict__ s_idx,
-                     const float* __restrict__ s_depth, const float* __restrict__ s_dists,
+march_compact_kernel(long long B, long long ldb, int K, int start, int end, const int* __restrict__ lens,
+                     const unsigned char* __restrict__ early_stop, const int* __restrict__ idxT,
+                     const float* __restrict__ depthT, const float* __restrict__ distsT,
                      const float* __restrict__ ray_start, const float* __restrict__ ray_dir,
                      int* __restrict__ out_vox, float* __restrict__ out_xyz, float* __restrict__ out_dir,
                      float* __restrict__ out_dists, int* __restrict__ ray_off, int* __restrict__ plan,
                      unsigned long long* __restrict__ tile_state, unsigned epoch, unsigned ticket_base) {
   __shared__ unsigned sh_tile, sh_base;
-  __shared__ int sh_warp[kTile / 32];
-  __shared__ int sh_off[kTile], sh_n[kTile];
+  __shared__ int sh_warp[kTile / 32], sh_total;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) sh_tile = atomicAdd(reinterpret_cast<unsigned*>(plan + H_TICKET), 1u) - ticket_base;
   __syncthreads();
@@ -233,86 +309,74 @@ march_compact_kernel(long long B, int K, long long ldk, int start, int end, cons
   const long long ray = (long long)tile * kTile + tid;
   int n = 0;
   if (ray < B && (early_stop == nullptr || early_stop[ray] == 0)) n = window_samples(lens[ray], start, end);
+  // the first column's loads do not depend on the offsets: issue them before the scan / look-back
+  int v0 = 0;
+  float d0 = 0.f, s0 = 0.f;
+  if (n > 0) {
+    const long long a = (long long)start * ldb + ray;
+    v0 = idxT[a]; d0 = depthT[a]; s0 = distsT[a];
+  }
   // block-wide exclusive scan of n
   const int incl = warp_incl_sum_i(n, lane);
   if (lane == 31) sh_warp[warp] = incl;
   __syncthreads();
   if (warp == 0) {
-    int w = lane < kTile / 32 ? sh_warp[lane] : 0;
+    const int w = lane < kTile / 32 ? sh_warp[lane] : 0;
     const int wi = warp_incl_sum_i(w, lane);
     if (lane < kTile / 32) sh_warp[lane] = wi - w;          // exclusive warp bases
-    if (lane == kTile / 32 - 1) sh_off[0] = wi;             // stash the tile total
+    if (lane == kTile / 32 - 1) sh_total = wi;
   }
   __syncthreads();
-  const int tile_total = sh_off[0];
+  const int tile_total = sh_total;
   const int excl = incl - n + sh_warp[warp];
-  __syncthreads();
-  // decoupled look-back: state = (epoch*4 + flag) << 32 | value, flag 1 = aggregate, 2 = inclusive prefix
-  if (tid == 0) {
+  // decoupled look-back by warp 0: state = (epoch*4 + flag) << 32 | value, flag 1 = aggregate, 2 = inclusive prefix
+  if (warp == 0) {
     const unsigned long long tag = (unsigned long long)epoch << 34;
     unsigned base = 0;
     if (tile == 0) {
-      atomicExch(tile_state + tile, tag | (2ull << 32) | (unsigned)tile_total);
+      if (lane == 0) atomicExch(tile_state + tile, tag | (2ull << 32) | (unsigned)tile_total);
     } else {
-      atomicExch(tile_state + tile, tag | (1ull << 32) | (unsigned)tile_total);
-      long long p = (long long)tile - 1;
+      if (lane == 0) atomicExch(tile_state + tile, tag | (1ull << 32) | (unsigned)tile_total);
+      long long p = (long long)tile - 1;      // lane l inspects tile p - l
       while (true) {
-        const unsigned long long s = *reinterpret_cast<volatile unsigned long long*>(tile_state + p);
-        if ((s >> 34) != epoch) continue;                   // not published in this launch yet
-        base += (unsigned)(s & 0xffffffffull);
-        if (((s >> 32) & 3ull) == 2ull) break;
-        --p;
+        const long long q = p - lane;
+        unsigned long long st = tag | (2ull << 32);         // tiles before 0: inclusive prefix 0
+        if (q >= 0) st = *reinterpret_cast<volatile unsigned long long*>(tile_state + q);
+        const bool ready = (st >> 34) == epoch;
+        if (!__all_sync(NSVF_FULL_MASK, ready)) continue;
+        const unsigned incl_mask = __ballot_sync(NSVF_FULL_MASK, ((st >> 32) & 3ull) == 2ull);
+        const int stop = incl_mask ? __ffs(incl_mask) - 1 : 31;    // nearest tile that already knows its prefix
+        unsigned v = lane <= stop ? (unsigned)(st & 0xffffffffull) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NSVF_FULL_MASK, v, o);
+        base += v;
+        if (incl_mask) break;
+        p -= 32;
       }
-      atomicExch(tile_state + tile, tag | (2ull << 32) | (unsigned)(base + tile_total));
+      if (lane == 0) atomicExch(tile_state + tile, tag | (2ull << 32) | (unsigned)(base + tile_total));
     }
-    sh_base = base;
+    if (lane == 0) sh_base = base;
   }
   __syncthreads();
   const int off = (int)sh_base + excl;
   if (ray < B) ray_off[ray] = off;
   if (ray == B - 1) ray_off[B] = off + n;
-  sh_off[tid] = off;
-  sh_n[tid] = n;
-  __syncthreads();
-
-  if (end - start <= kNarrow) {
-    if (n > 0) {
-      const float ox = ray_start[ray * 3 + 0], oy = ray_start[ray * 3 + 1], oz = ray_start[ray * 3 + 2];
-      const float dx = ray_dir[ray * 3 + 0], dy = ray_dir[ray * 3 + 1], dz = ray_dir[ray * 3 + 2];
-      const long long row = ray * ldk + start;
-      for (int t = 0; t < n; ++t) {
-        const long long o = (long long)off + t;
-        const float d = s_depth[row + t];
-        out_vox[o] = s_idx[row + t];
-        // ray(): ray_start + ray_dir * depth — a separate multiply and add in the reference (no FMA)
-        out_xyz[o * 3 + 0] = __fadd_rn(ox, __fmul_rn(dx, d));
-        out_xyz[o * 3 + 1] = __fadd_rn(oy, __fmul_rn(dy, d));
-        out_xyz[o * 3 + 2] = __fadd_rn(oz, __fmul_rn(dz, d));
-        if (out_dir != nullptr) { out_dir[o * 3 + 0] = dx; out_dir[o * 3 + 1] = dy; out_dir[o * 3 + 2] = dz; }
-        if (out_dists != nullptr) out_dists[o] = s_dists[row + t];
+  if (n > 0) {
+    const float ox = ray_start[ray * 3 + 0], oy = ray_start[ray * 3 + 1], oz = ray_start[ray * 3 + 2];
+    const float dx = ray_dir[ray * 3 + 0], dy = ray_dir[ray * 3 + 1], dz = ray_dir[ray * 3 + 2];
+    for (int t = 0; t < n; ++t) {
+      if (t > 0) {
+        const long long a = (long long)(start + t) * ldb + ray;
+        v0 = idxT[a]; d0 = depthT[a]; s0 = distsT[a];
       }
-    }
-  } else {
-    // wide window: a warp walks its 32 rays one after the other, lanes along the samples (coalesced both ways)
-    for (int j = 0; j < 32; ++j) {
-      const int lt = warp * 32 + j;
-      const int nn = sh_n[lt];
-      if (nn == 0) continue;
-      const long long r = (long long)tile * kTile + lt;
-      const long long o0 = sh_off[lt];
-      const float ox = ray_start[r * 3 + 0], oy = ray_start[r * 3 + 1], oz = ray_start[r * 3 + 2];
-      const float dx = ray_dir[r * 3 + 0], dy = ray_dir[r * 3 + 1], dz = ray_dir[r * 3 + 2];
-      const long long row = r * ldk + start;
-      for (int t = lane; t < nn; t += 32) {
-        const long long o = o0 + t;
-        const float d = s_depth[row + t];
-        out_vox[o] = s_idx[row + t];
-        out_xyz[o * 3 + 0] = __fadd_rn(ox, __fmul_rn(dx, d));
-        out_xyz[o * 3 + 1] = __fadd_rn(oy, __fmul_rn(dy, d));
-        out_xyz[o * 3 + 2] = __fadd_rn(oz, __fmul_rn(dz, d));
-        if (out_dir != nullptr) { out_dir[o * 3 + 0] = dx; out_dir[o * 3 + 1] = dy; out_dir[o * 3 + 2] = dz; }
-        if (out_dists != nullptr) out_dists[o] = s_dists[row + t];
-      }
+      const long long o = (long long)off + t;
+      out_vox[o] = v0;
+      // ray(): ray_start + ray_dir * depth — a separate multiply and add in the reference (no FMA)
+      out_xyz[o * 3 + 0] = __fadd_rn(ox, __fmul_rn(dx, d0));
+      out_xyz[o * 3 + 1] = __fadd_rn(oy, __fmul_rn(dy, d0));
+      out_xyz[o * 3 + 2] = __fadd_rn(oz, __fmul_rn(dz, d0));
+      if (out_dir != nullptr) { out_dir[o * 3 + 0] = dx; out_dir[o * 3 + 1] = dy; out_dir[o * 3 + 2] = dz; }
+      if (out_dists != nullptr) out_dists[o] = s0;
     }
   }
 }
@@ -325,78 +389,41 @@ __device__ __forceinline__ float free_energy(float sigma, float noise, float dis
 }
 
 __global__ void __launch_bounds__(kTile)
-march_epilogue_kernel(long long B, int K, int start, int end, const int* __restrict__ ray_off,
+march_epilogue_kernel(long long B, long long ldb, int K, int start, int end, const int* __restrict__ ray_off,
                       const int* __restrict__ lens, unsigned char* __restrict__ early_stop,
                       float* __restrict__ acc_fe, int* __restrict__ eval_len, const float* __restrict__ sigma,
                       const float* __restrict__ noise, const float* __restrict__ dists,
-                      const float* __restrict__ texture, float tolerance, float* __restrict__ fe_rows,
-                      float* __restrict__ tex_rows, int chunk_size, int schedule_next, int* __restrict__ plan,
+                      const float* __restrict__ texture, float tolerance, float* __restrict__ feT,
+                      float* __restrict__ texT, int chunk_size, int schedule_next, int* __restrict__ plan,
                       volatile int* host_info) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   int* diff = plan + kHdr + K;
-  if (end - start <= kNarrow) {
-    for (long long ray = (long long)blockIdx.x * kTile + tid; ray < B; ray += (long long)gridDim.x * kTile) {
-      const int o0 = ray_off[ray], n = ray_off[ray + 1] - o0;
-      if (n == 0) continue;
-      const long long row = ray * K + start;
-      float sum = 0.f;
-      for (int t = 0; t < n; ++t) {
-        const long long o = (long long)o0 + t;
-        if (sigma != nullptr) {
-          const float fe = free_energy(sigma[o], noise != nullptr ? noise[o] : 0.f, dists[o]);
-          fe_rows[row + t] = fe;
-          sum += fe;
-        }
-        if (texture != nullptr) {
-          tex_rows[(row + t) * 3 + 0] = texture[o * 3 + 0];
-          tex_rows[(row + t) * 3 + 1] = texture[o * 3 + 1];
-          tex_rows[(row + t) * 3 + 2] = texture[o * 3 + 2];
-        }
+  for (long long ray = (long long)blockIdx.x * kTile + tid; ray < B; ray += (long long)gridDim.x * kTile) {
+    const int o0 = ray_off[ray], n = ray_off[ray + 1] - o0;
+    if (n == 0) continue;
+    float sum = 0.f;
+    for (int t = 0; t < n; ++t) {
+      const long long o = (long long)o0 + t;
+      const long long a = (long long)(start + t) * ldb + ray;
+      if (sigma != nullptr) {
+        const float fe = free_energy(sigma[o], noise != nullptr ? noise[o] : 0.f, dists[o]);
+        feT[a] = fe;
+        sum += fe;
       }
-      eval_len[ray] = start + n;
-      if (tolerance > 0.f && sigma != nullptr) {
-        const float acc = acc_fe[ray] + sum;
-        acc_fe[ray] = acc;
-        if (acc > tolerance) {
-          early_stop[ray] = 1;
-          const int len = lens[ray];
-          if (len > end) { atomicSub(diff + end, 1); atomicAdd(diff + len, 1); }
-        }
+      if (texture != nullptr) {
+        texT[a * 3 + 0] = texture[o * 3 + 0];
+        texT[a * 3 + 1] = texture[o * 3 + 1];
+        texT[a * 3 + 2] = texture[o * 3 + 2];
       }
     }
-  } else {
-    for (long long ray = (long long)blockIdx.x * (kTile / 32) + warp; ray < B;
-         ray += (long long)gridDim.x * (kTile / 32)) {
-      const int o0 = ray_off[ray], n = ray_off[ray + 1] - o0;
-      if (n == 0) continue;
-      const long long row = ray * K + start;
-      float sum = 0.f;
-      for (int t = lane; t < n; t += 32) {
-        const long long o = (long long)o0 + t;
-        if (sigma != nullptr) {
-          const float fe = free_energy(sigma[o], noise != nullptr ? noise[o] : 0.f, dists[o]);
-          fe_rows[row + t] = fe;
-          sum += fe;
-        }
-        if (texture != nullptr) {
-          tex_rows[(row + t) * 3 + 0] = texture[o * 3 + 0];
-          tex_rows[(row + t) * 3 + 1] = texture[o * 3 + 1];
-          tex_rows[(row + t) * 3 + 2] = texture[o * 3 + 2];
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(NSVF_FULL_MASK, sum, o);
-      if (lane == 0) {
-        eval_len[ray] = start + n;
-        if (tolerance > 0.f && sigma != nullptr) {
-          const float acc = acc_fe[ray] + sum;
-          acc_fe[ray] = acc;
-          if (acc > tolerance) {
-            early_stop[ray] = 1;
-            const int len = lens[ray];
-            if (len > end) { atomicSub(diff + end, 1); atomicAdd(diff + len, 1); }
-          }
-        }
+    eval_len[ray] = start + n;
+    if (tolerance > 0.f && sigma != nullptr) {
+      const float acc = acc_fe[ray] + sum;
+      acc_fe[ray] = acc;
+      if (acc > tolerance) {
+        early_stop[ray] = 1;
+        const int len = lens[ray];
+        if (len > end) { atomicSub(diff + end, 1); atomicAdd(diff + len, 1); }
       }
     }
   }
@@ -404,38 +431,157 @@ march_epilogue_kernel(long long B, int K, int start, int end, const int* __restr
     publish_schedule(plan, K, chunk_size, end, true, false, host_info, 0);
 }
 
-// backward of the epilogue for one window: gradients of the trimmed rows back to the compacted field outputs
+// backward of the epilogue for one window: gradients of the planes back to the compacted field outputs
 //   d sigma = (g_fe * 7) * dists * [noise + sigma > 0];  d texture = g_tex
 __global__ void __launch_bounds__(256)
-march_epilogue_bwd_kernel(long long B, int K, int start, const int* __restrict__ ray_off,
-                          const float* __restrict__ g_fe_rows, const float* __restrict__ g_tex_rows,
+march_epilogue_bwd_kernel(long long B, long long ldb, int K, int start, const int* __restrict__ ray_off,
+                          const float* __restrict__ g_feT, const float* __restrict__ g_texT,
                           const float* __restrict__ sigma, const float* __restrict__ noise,
-                          const float* __restrict__ dists, float* __restrict__ g_sigma, float* __restrict__ g_texture,
-                          int wide) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  const long long stride = wide ? (long long)gridDim.x * 8 : (long long)gridDim.x * 256;
-  for (long long ray = wide ? (long long)blockIdx.x * 8 + (tid >> 5) : (long long)blockIdx.x * 256 + tid; ray < B;
-       ray += stride) {
+                          const float* __restrict__ dists, float* __restrict__ g_sigma, float* __restrict__ g_texture) {
+  for (long long ray = (long long)blockIdx.x * 256 + threadIdx.x; ray < B; ray += (long long)gridDim.x * 256) {
     const int o0 = ray_off[ray], n = ray_off[ray + 1] - o0;
-    const long long row = ray * K + start;
-    for (int t = wide ? lane : 0; t < n; t += wide ? 32 : 1) {
+    for (int t = 0; t < n; ++t) {
       const long long o = (long long)o0 + t;
+      const long long a = (long long)(start + t) * ldb + ray;
       if (g_sigma != nullptr) {
-        const float a = __fadd_rn(noise != nullptr ? noise[o] : 0.f, sigma[o]);
-        g_sigma[o] = a > 0.f ? __fmul_rn(__fmul_rn(g_fe_rows[row + t], 7.0f), dists[o]) : 0.f;
+        const float x = __fadd_rn(noise != nullptr ? noise[o] : 0.f, sigma[o]);
+        g_sigma[o] = x > 0.f ? __fmul_rn(__fmul_rn(g_feT[a], 7.0f), dists[o]) : 0.f;
       }
       if (g_texture != nullptr) {
-        g_texture[o * 3 + 0] = g_tex_rows[(row + t) * 3 + 0];
-        g_texture[o * 3 + 1] = g_tex_rows[(row + t) * 3 + 1];
-        g_texture[o * 3 + 2] = g_tex_rows[(row + t) * 3 + 2];
+        g_texture[o * 3 + 0] = g_texT[a * 3 + 0];
+        g_texture[o * 3 + 1] = g_texT[a * 3 + 1];
+        g_texture[o * 3 + 2] = g_texT[a * 3 + 2];
       }
     }
+  }
+}
+
+// ---- compositing over the slot-major planes (renderer.py:193-218), one thread per ray ------------------------------
+//   a = 1 - exp(-fe);  b = exp(-cumsum(shift(fe)));  probs = a * b;  depth / missed / colors = sums over the ray
+// The running free-energy sum is compensated (Kahan): it is the one long sequential sum of the scan.
+__global__ void __launch_bounds__(256)
+march_composite_fwd_kernel(long long B, long long ldb, int K, const int* __restrict__ eval_len, const int* __restrict__ lens,
+                           const unsigned char* __restrict__ early_stop, const float* __restrict__ feT,
+                           const float* __restrict__ texT, const float* __restrict__ depthT,
+                           float* __restrict__ probsT, float* __restrict__ out_depth, float* __restrict__ out_missed,
+                           float* __restrict__ out_colors, float* __restrict__ out_maxd, float* __restrict__ out_mind,
+                           const float* __restrict__ depth_rows, long long ldk, float pad_depth, int lazy_planes) {
+  const long long ray = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (ray >= B) return;
+  const int Lfull = min(max(lens[ray], 0), K);
+  const int Kr = min(eval_len[ray], Lfull);
+  // lazily transposed planes hold only the evaluated prefix of a ray that stopped early; its depth extrema do not
+  // need more: max_depths is -1 for it and the minimum of a depth-ordered ray is its first sample
+  const int Lr = (lazy_planes && early_stop != nullptr && early_stop[ray]) ? Kr : Lfull;
+  float carry = 0.f, comp = 0.f, s_p = 0.f, s_d = 0.f, s_r = 0.f, s_g = 0.f, s_b = 0.f;
+  float dmax = -1.0f, dmin = 3.0e38f;
+  int k = 0;
+  for (; k + 4 <= Kr; k += 4) {                     // 4 columns in flight per thread
+    float x[4], d[4], t[4][3];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long a = (long long)(k + j) * ldb + ray;
+      x[j] = feT[a];
+      d[j] = depthT[a];
+      if (texT != nullptr) { t[j][0] = texT[a * 3 + 0]; t[j][1] = texT[a * 3 + 1]; t[j][2] = texT[a * 3 + 2]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float p = (1.0f - expf(-x[j])) * expf(-carry);
+      const float y = x[j] - comp, tt = carry + y;
+      comp = (tt - carry) - y;
+      carry = tt;
+      if (probsT != nullptr) probsT[(long long)(k + j) * ldb + ray] = p;
+      s_p += p;
+      s_d = fmaf(d[j], p, s_d);
+      if (texT != nullptr) { s_r = fmaf(t[j][0], p, s_r); s_g = fmaf(t[j][1], p, s_g); s_b = fmaf(t[j][2], p, s_b); }
+      dmax = fmaxf(dmax, d[j]);
+      dmin = fminf(dmin, d[j]);
+    }
+  }
+  for (; k < Lr; ++k) {
+    const long long a = (long long)k * ldb + ray;
+    const float dk = depthT[a];
+    dmax = fmaxf(dmax, dk);
+    dmin = fminf(dmin, dk);
+    float p = 0.f;
+    if (k < Kr) {
+      const float xk = feT[a];
+      p = (1.0f - expf(-xk)) * expf(-carry);
+      const float y = xk - comp, tt = carry + y;
+      comp = (tt - carry) - y;
+      carry = tt;
+      s_p += p;
+      s_d = fmaf(dk, p, s_d);
+      if (texT != nullptr) {
+        s_r = fmaf(texT[a * 3 + 0], p, s_r); s_g = fmaf(texT[a * 3 + 1], p, s_g); s_b = fmaf(texT[a * 3 + 2], p, s_b);
+      }
+    }
+    if (probsT != nullptr) probsT[a] = p;
+  }
+  if (probsT != nullptr)
+    for (; k < K; ++k) probsT[(long long)k * ldb + ray] = 0.f;
+  out_depth[ray] = s_d;
+  out_missed[ray] = 1.0f - s_p;
+  if (texT != nullptr && out_colors != nullptr) {
+    out_colors[ray * 3 + 0] = s_r; out_colors[ray * 3 + 1] = s_g; out_colors[ray * 3 + 2] = s_b;
+  }
+  // renderer.py:210-211: max over the live samples (-1 for rays that stopped early / have none), min over the whole
+  // padded row (padding = pad_depth, or the first padding slot of a padded input row)
+  if (out_maxd != nullptr) out_maxd[ray] = (early_stop != nullptr && early_stop[ray]) ? -1.0f : dmax;
+  if (out_mind != nullptr) {
+    if (Lfull < K) dmin = fminf(dmin, depth_rows != nullptr ? depth_rows[ray * ldk + Lfull] : pad_depth);
+    out_mind[ray] = dmin;
+  }
+}
+
+// backward, two sweeps per ray:  G_k = dprobs_k + ddepth * t_k - dmissed + dcolors . rgb_k
+//   d fe_k = G_k e^{-fe_k} b_k - sum_{j>k} G_j probs_j ;  d rgb_k = dcolors * probs_k
+// sweep 1 (ascending) stores the first term in g_feT and q_k = G_k probs_k in scratchT; sweep 2 (descending)
+// subtracts the exclusive suffix sum — a true reverse scan, no cancellation for late samples.
+__global__ void __launch_bounds__(256)
+march_composite_bwd_kernel(long long B, long long ldb, int K, const int* __restrict__ eval_len, const float* __restrict__ feT,
+                           const float* __restrict__ texT, const float* __restrict__ depthT,
+                           const float* __restrict__ g_probsT, const float* __restrict__ g_depth,
+                           const float* __restrict__ g_missed, const float* __restrict__ g_colors,
+                           float* __restrict__ g_feT, float* __restrict__ g_texT, float* __restrict__ scratchT) {
+  const long long ray = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (ray >= B) return;
+  const int Kr = min(eval_len[ray], K);
+  if (Kr == 0) return;
+  const float gd = g_depth ? g_depth[ray] : 0.f, gm = g_missed ? g_missed[ray] : 0.f;
+  float gc0 = 0.f, gc1 = 0.f, gc2 = 0.f;
+  if (g_colors && texT) { gc0 = g_colors[ray * 3 + 0]; gc1 = g_colors[ray * 3 + 1]; gc2 = g_colors[ray * 3 + 2]; }
+  float carry = 0.f, comp = 0.f;
+  for (int k = 0; k < Kr; ++k) {
+    const long long a = (long long)k * ldb + ray;
+    const float x = feT[a];
+    const float e = expf(-x), bk = expf(-carry);
+    const float y = x - comp, tt = carry + y;
+    comp = (tt - carry) - y;
+    carry = tt;
+    const float p = (1.0f - e) * bk;
+    float G = (g_probsT ? g_probsT[a] : 0.f) + gd * depthT[a] - gm;
+    if (texT) {
+      G += gc0 * texT[a * 3 + 0] + gc1 * texT[a * 3 + 1] + gc2 * texT[a * 3 + 2];
+      if (g_texT) { g_texT[a * 3 + 0] = gc0 * p; g_texT[a * 3 + 1] = gc1 * p; g_texT[a * 3 + 2] = gc2 * p; }
+    }
+    g_feT[a] = G * e * bk;
+    scratchT[a] = G * p;
+  }
+  float tail = 0.f;
+  for (int k = Kr - 1; k >= 0; --k) {
+    const long long a = (long long)k * ldb + ray;
+    g_feT[a] -= tail;
+    tail += scratchT[a];
   }
 }
 
 }  // namespace nsvf
 
 using namespace nsvf;
+
+extern "C" long long nsvf_march_plane_stride(long long B) { return B < 0 ? 0 : plane_stride(B); }
 
 extern "C" size_t nsvf_march_plan_bytes(long long B, int K) {
   if (B < 0 || K < 0) return 0;
@@ -473,13 +619,29 @@ extern "C" int nsvf_march_begin(nsvf_stream_t stream_, long long B, int K, int c
   return 0;
 }
 
-extern "C" int nsvf_march_compact(nsvf_stream_t stream_, long long B, int K, long long ldk, int start, int end,
-                                  const int* lens, const unsigned char* early_stop, const int* sampled_idx,
-                                  const float* sampled_depth, const float* sampled_dists, const float* ray_start,
-                                  const float* ray_dir, int* out_vox, float* out_xyz, float* out_dir,
-                                  float* out_dists, int* ray_off, void* plan, int launch_no) {
+extern "C" int nsvf_march_transpose(nsvf_stream_t stream_, long long B, int K, long long ldk, int k_begin, int k_end,
+                                    const unsigned char* early_stop, const int* lens, const int* sampled_idx, const float* sampled_depth, const float* sampled_dists,
+                                    int* idxT, float* depthT, float* distsT) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  NSVF_REQUIRE(B >= 0 && K >= 0 && ldk >= K && start >= 0 && start <= end && end <= K && launch_no >= 0,
+  NSVF_REQUIRE(B >= 0 && K >= 0 && ldk >= K && k_begin >= 0 && k_begin <= k_end && k_end <= K && k_begin % 32 == 0,
+               "march_transpose: bad sizes (k_begin must be a multiple of 32)");
+  if (B == 0 || k_end == k_begin) return 0;
+  const size_t smem = (size_t)(3 * kTR * 33 + kTR) * sizeof(int);
+  NSVF_CUDA_OK(cudaFuncSetAttribute(march_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long want = (B + kTR - 1) / kTR, cap = (long long)num_sms() * 4;
+  NSVF_TIMED_LAUNCH("march_transpose_kernel", stream,
+                    (march_transpose_kernel<<<(int)(want < cap ? want : cap), 512, smem, stream>>>(
+                        B, plane_stride(B), K, ldk, k_begin, k_end, early_stop, lens, sampled_idx, sampled_depth, sampled_dists, idxT, depthT, distsT)));
+  return 0;
+}
+
+extern "C" int nsvf_march_compact(nsvf_stream_t stream_, long long B, int K, int start, int end, const int* lens,
+                                  const unsigned char* early_stop, const int* idxT, const float* depthT,
+                                  const float* distsT, const float* ray_start, const float* ray_dir, int* out_vox,
+                                  float* out_xyz, float* out_dir, float* out_dists, int* ray_off, void* plan,
+                                  int launch_no) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSVF_REQUIRE(B >= 0 && K >= 0 && start >= 0 && start <= end && end <= K && launch_no >= 0,
                "march_compact: bad sizes");
   if (B == 0) return 0;
   const long long tiles = plan_tiles(B);
@@ -488,45 +650,72 @@ extern "C" int nsvf_march_compact(nsvf_stream_t stream_, long long B, int K, lon
       reinterpret_cast<unsigned long long*>((int*)plan + plan_words_before_tiles(K));
   NSVF_TIMED_LAUNCH("march_compact_kernel", stream,
                     (march_compact_kernel<<<(unsigned)tiles, kTile, 0, stream>>>(
-                        B, K, ldk, start, end, lens, early_stop, sampled_idx, sampled_depth, sampled_dists, ray_start,
-                        ray_dir, out_vox, out_xyz, out_dir, out_dists, ray_off, (int*)plan, tile_state,
-                        (unsigned)launch_no + 1u, (unsigned)(tiles * launch_no))));
+                        B, plane_stride(B), K, start, end, lens, early_stop, idxT, depthT, distsT, ray_start, ray_dir, out_vox, out_xyz,
+                        out_dir, out_dists, ray_off, (int*)plan, tile_state, (unsigned)launch_no + 1u,
+                        (unsigned)(tiles * launch_no))));
   return 0;
 }
 
 extern "C" int nsvf_march_epilogue(nsvf_stream_t stream_, long long B, int K, int start, int end, const int* ray_off,
                                    const int* lens, unsigned char* early_stop, float* acc_free_energy, int* eval_len,
                                    const float* sigma, const float* noise, const float* dists, const float* texture,
-                                   float tolerance, float* free_energy_rows, float* texture_rows, int chunk_size,
-                                   int schedule_next, void* plan, int* host_info) {
+                                   float tolerance, float* feT, float* texT, int chunk_size, int schedule_next,
+                                   void* plan, int* host_info) {
   cudaStream_t stream = (cudaStream_t)stream_;
   NSVF_REQUIRE(B >= 0 && K >= 0 && start >= 0 && start <= end && end <= K, "march_epilogue: bad sizes");
-  NSVF_REQUIRE(sigma == nullptr || (dists != nullptr && free_energy_rows != nullptr), "march_epilogue: sigma needs dists");
-  NSVF_REQUIRE(texture == nullptr || texture_rows != nullptr, "march_epilogue: texture needs texture_rows");
+  NSVF_REQUIRE(sigma == nullptr || (dists != nullptr && feT != nullptr), "march_epilogue: sigma needs dists");
+  NSVF_REQUIRE(texture == nullptr || texT != nullptr, "march_epilogue: texture needs its plane");
   if (B == 0) return 0;
-  const bool narrow = end - start <= kNarrow;
-  long long want = narrow ? (B + kTile - 1) / kTile : (B + kTile / 32 - 1) / (kTile / 32);
-  long long cap = (long long)num_sms() * 8;
+  long long want = (B + kTile - 1) / kTile, cap = (long long)num_sms() * 8;
   NSVF_TIMED_LAUNCH("march_epilogue_kernel", stream,
                     (march_epilogue_kernel<<<(int)(want < cap ? want : cap), kTile, 0, stream>>>(
-                        B, K, start, end, ray_off, lens, early_stop, acc_free_energy, eval_len, sigma, noise, dists,
-                        texture, tolerance, free_energy_rows, texture_rows, chunk_size, schedule_next, (int*)plan,
-                        host_info)));
+                        B, plane_stride(B), K, start, end, ray_off, lens, early_stop, acc_free_energy, eval_len, sigma, noise, dists,
+                        texture, tolerance, feT, texT, chunk_size, schedule_next, (int*)plan, host_info)));
   return 0;
 }
 
 extern "C" int nsvf_march_epilogue_bwd(nsvf_stream_t stream_, long long B, int K, int start, int end,
-                                       const int* ray_off, const float* grad_free_energy_rows,
-                                       const float* grad_texture_rows, const float* sigma, const float* noise,
-                                       const float* dists, float* grad_sigma, float* grad_texture) {
+                                       const int* ray_off, const float* g_feT, const float* g_texT, const float* sigma,
+                                       const float* noise, const float* dists, float* grad_sigma,
+                                       float* grad_texture) {
   cudaStream_t stream = (cudaStream_t)stream_;
   NSVF_REQUIRE(B >= 0 && K >= 0 && start >= 0 && start <= end && end <= K, "march_epilogue_bwd: bad sizes");
   if (B == 0) return 0;
-  const int wide = end - start > kNarrow;
-  long long want = wide ? (B + 7) / 8 : (B + 255) / 256, cap = (long long)num_sms() * 8;
+  long long want = (B + 255) / 256, cap = (long long)num_sms() * 8;
   march_epilogue_bwd_kernel<<<(int)(want < cap ? want : cap), 256, 0, stream>>>(
-      B, K, start, ray_off, grad_free_energy_rows, grad_texture_rows, sigma, noise, dists, grad_sigma, grad_texture,
-      wide);
+      B, plane_stride(B), K, start, ray_off, g_feT, g_texT, sigma, noise, dists, grad_sigma, grad_texture);
   NSVF_LAUNCH_OK("march_epilogue_bwd_kernel");
+  return 0;
+}
+
+extern "C" int nsvf_march_composite_fwd(nsvf_stream_t stream_, long long B, int K, const int* eval_len,
+                                        const int* lens, const unsigned char* early_stop, const float* feT,
+                                        const float* texT, const float* depthT, float* probsT, float* depth,
+                                        float* missed, float* colors, float* max_depths, float* min_depths,
+                                        const float* padded_depth_rows, long long ldk, float pad_depth,
+                                        int lazy_planes) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSVF_REQUIRE(B >= 0 && K >= 0, "march_composite_fwd: bad sizes");
+  NSVF_REQUIRE(eval_len != nullptr && lens != nullptr, "march_composite_fwd: eval_len and lens are required");
+  if (B == 0) return 0;
+  NSVF_TIMED_LAUNCH("march_composite_fwd_kernel", stream,
+                    (march_composite_fwd_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>(
+                        B, plane_stride(B), K, eval_len, lens, early_stop, feT, texT, depthT, probsT, depth, missed, colors, max_depths,
+                        min_depths, padded_depth_rows, ldk, pad_depth, lazy_planes)));
+  return 0;
+}
+
+extern "C" int nsvf_march_composite_bwd(nsvf_stream_t stream_, long long B, int K, const int* eval_len,
+                                        const float* feT, const float* texT, const float* depthT,
+                                        const float* grad_probsT, const float* grad_depth, const float* grad_missed,
+                                        const float* grad_colors, float* g_feT, float* g_texT, float* scratchT) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSVF_REQUIRE(B >= 0 && K >= 0, "march_composite_bwd: bad sizes");
+  NSVF_REQUIRE(eval_len != nullptr && scratchT != nullptr, "march_composite_bwd: eval_len and scratch are required");
+  if (B == 0 || K == 0) return 0;
+  NSVF_TIMED_LAUNCH("march_composite_bwd_kernel", stream,
+                    (march_composite_bwd_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>(
+                        B, plane_stride(B), K, eval_len, feT, texT, depthT, grad_probsT, grad_depth, grad_missed, grad_colors, g_feT,
+                        g_texT, scratchT)));
   return 0;
 }

@@ -48,7 +48,8 @@ class SparseVoxelEncoder(nn.Module):
         # surface normals can differentiate sigma w.r.t. position; nsvf_base does not, and the flag then only
         # buys a wasted d/dxyz in every backward.  Set True for normal-based fields.
         self.track_xyz_grad = track_xyz_grad
-        self._runtime_caches = {"flatten_centers": None, "flatten_children": None, "max_voxel_probs": None}
+        self._runtime_caches = {"flatten_centers": None, "flatten_children": None, "max_voxel_probs": None,
+                                "geometry": None, "voxel_size_float": None}
         self.values = nn.Embedding(int(self.num_keys), voxel_embed_dim)
         nn.init.normal_(self.values.weight, mean=0, std=voxel_embed_dim ** -0.5)   # module_utils.py:23-26
 
@@ -101,22 +102,32 @@ class SparseVoxelEncoder(nn.Module):
         return self.keep.long().sum()
 
     # ---- hot path -------------------------------------------------------------------------------------
-    def _kept_rows(self):
-        """Row indices of the kept voxels.  The reference boolean-indexes feats / points in every forward
-        (encoder.py:380-382), which is a nonzero() + host sync per step; the keep mask only changes when the voxels are
-        pruned or split, so the index list is cached against the mask's version counter (no device work, no sync)."""
-        key = (self.keep.data_ptr(), self.keep._version, self.keep.numel())
-        cache = self._runtime_caches.get("kept_rows")
+    def _geometry_key(self):
+        bufs = (self.keep, self.points, self.feats, self.voxel_size)
+        return tuple((id(t), t.data_ptr(), t._version, t.numel()) for t in bufs)
+
+    def invalidate_geometry_cache(self):
+        """Called by every method that changes the voxel set (pruning, splitting, state loading)."""
+        self._runtime_caches["geometry"] = None
+
+    def _kept_geometry(self):
+        """(feats i64, feats i32, points with the x shift) of the kept voxels.  The reference boolean-indexes feats /
+        points in every forward (encoder.py:380-383: a nonzero() + host sync per step); the voxel set only changes when
+        voxels are pruned or split, so the gathered rows are cached — invalidated explicitly by the mutators and, as a
+        second line of defence, keyed on identity / address / version counter of the buffers involved."""
+        key = self._geometry_key()
+        cache = self._runtime_caches.get("geometry")
         if cache is None or cache[0] != key:
-            cache = (key, self.keep.bool().nonzero(as_tuple=True)[0])
-            self._runtime_caches["kept_rows"] = cache
-        return cache[1]
+            rows = self.keep.bool().nonzero(as_tuple=True)[0]
+            feats = self.feats.index_select(0, rows)
+            points = self.points.index_select(0, rows)
+            points[:, 0] += (self.voxel_size / 10)      # the reference's HACK (encoder.py:383), kept for parity
+            cache = (key, feats, feats.to(torch.int32), points)
+            self._runtime_caches["geometry"] = cache
+        return cache[1], cache[2], cache[3]
 
     def precompute(self, id=None, *args, **kwargs):
-        rows = self._kept_rows()
-        feats = self.feats.index_select(0, rows)
-        points = self.points.index_select(0, rows)
-        points[:, 0] += (self.voxel_size / 10)      # the reference's HACK (encoder.py:383), kept for parity
+        feats, _, points = self._kept_geometry()
         values = self.values.weight[: self.num_keys]
         encoder_states = {"voxel_vertex_idx": feats, "voxel_center_xyz": points, "voxel_vertex_emb": values}
         if self.use_octree:
@@ -125,6 +136,13 @@ class SparseVoxelEncoder(nn.Module):
         if id is not None:   # [1, ...] leading shape dimension, as the reference adds for id
             encoder_states = {k: v.unsqueeze(0) for k, v in encoder_states.items()}
         return encoder_states
+
+    def _feats32(self, point_feats):
+        """int32 corner keys for the gather kernels (the buffer stays int64 like the reference's)."""
+        cache = self._runtime_caches.get("geometry")
+        if cache is not None and cache[1].data_ptr() == point_feats.data_ptr() and cache[1].numel() == point_feats.numel():
+            return cache[2]
+        return ops.as_int32_feats(point_feats.reshape(-1, 8)).contiguous()
 
     def ray_intersect(self, ray_start, ray_dir, encoder_states):
         point_feats = encoder_states["voxel_vertex_idx"]
@@ -202,10 +220,19 @@ class SparseVoxelEncoder(nn.Module):
         inputs = {"pos": sampled_xyz, "ray": samples["sampled_point_ray_direction"],
                   "dists": samples["sampled_point_distance"]}
         if values is not None:
-            inputs["emb"] = ops.trilinear_embed(sampled_idx, sampled_xyz, point_feats.reshape(-1, 8),
+            inputs["emb"] = ops.trilinear_embed(sampled_idx, sampled_xyz, self._feats32(point_feats),
                                                 point_xyz.reshape(-1, 3), values.reshape(-1, values.size(-1)),
-                                                self.voxel_size)
+                                                self._voxel_size_float())
         return inputs
+
+    def _voxel_size_float(self):
+        """float(self.voxel_size) without a device sync per call (the buffer lives on the GPU)."""
+        key = (self.voxel_size.data_ptr(), self.voxel_size._version)
+        cache = self._runtime_caches.get("voxel_size_float")
+        if cache is None or cache[0] != key:
+            cache = (key, float(self.voxel_size))
+            self._runtime_caches["voxel_size_float"] = cache
+        return cache[1]
 
     @torch.no_grad()
     def track_voxel_probs(self, voxel_idxs, voxel_probs):
@@ -237,6 +264,7 @@ class SparseVoxelEncoder(nn.Module):
                 dist.all_reduce(self.max_voxel_probs, op=dist.ReduceOp.MAX)
             keep = self.max_voxel_probs > th
         self.keep.masked_scatter_(self.keep.bool(), keep.long())
+        self.invalidate_geometry_cache()
         logger.info("pruning done. # of voxels before: %d, after: %d", keep.size(0), int(keep.sum()))
 
     def _prune_scores(self, field_fn, th, bits=16, encoder_states=None, lo=0, hi=None, chunk_size=64):
@@ -293,3 +321,4 @@ class SparseVoxelEncoder(nn.Module):
         self.points = new_points
         self.feats = new_feats
         self.keep = self.keep.new_ones(new_points.size(0))
+        self.invalidate_geometry_cache()

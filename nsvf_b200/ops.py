@@ -37,32 +37,40 @@ class TrilinearEmbed(Function):
     def forward(ctx, sampled_idx, sampled_xyz, feats, centres, values, voxel_size):
         _need_cuda(sampled_idx=sampled_idx, sampled_xyz=sampled_xyz, feats=feats, centres=centres, values=values)
         voxel_size = float(voxel_size)
-        idx = sampled_idx.to(torch.int32).contiguous()
-        xyz = sampled_xyz.detach().float().contiguous()
-        feats32 = as_int32_feats(feats).contiguous()
-        centres = centres.detach().float().contiguous()
-        vals = values.detach().float().contiguous()
+        idx = sampled_idx if (sampled_idx.dtype == torch.int32 and sampled_idx.is_contiguous()) \
+            else sampled_idx.to(torch.int32).contiguous()
+        xyz = sampled_xyz.detach()
+        if xyz.dtype != torch.float32 or not xyz.is_contiguous():
+            xyz = xyz.float().contiguous()
+        feats32 = feats if (feats.dtype == torch.int32 and feats.is_contiguous()) else as_int32_feats(feats).contiguous()
+        centres = centres.detach()
+        if centres.dtype != torch.float32 or not centres.is_contiguous():
+            centres = centres.float().contiguous()
+        vals = values.detach()
+        if vals.dtype != torch.float32 or not vals.is_contiguous():
+            vals = vals.float().contiguous()
         M, D = idx.numel(), vals.shape[-1]
         out = torch.empty((M, D), dtype=torch.float32, device=vals.device)
-        with torch.cuda.device(vals.device):
+        with _lib.device_guard(vals.device):
             _lib.check(_L.nsvf_trilinear_embed_fwd(_lib.current_stream(vals.device), M, D, _p(idx), _p(xyz),
                                                    _p(feats32), _p(centres), _p(vals), voxel_size, _p(out)))
-        ctx.save_for_backward(idx, xyz, feats32, centres, vals)
+        if ctx.needs_input_grad[4] or ctx.needs_input_grad[1]:
+            ctx.save_for_backward(idx, xyz, feats32, centres, vals)
         ctx.voxel_size = voxel_size
         ctx.values_shape = values.shape
-        return out.to(values.dtype)
+        return out if values.dtype == torch.float32 else out.to(values.dtype)
 
     @staticmethod
     def backward(ctx, grad_out):
-        idx, xyz, feats32, centres, vals = ctx.saved_tensors
         need_values, need_xyz = ctx.needs_input_grad[4], ctx.needs_input_grad[1]
         if not (need_values or need_xyz):
             return None, None, None, None, None, None
+        idx, xyz, feats32, centres, vals = ctx.saved_tensors
         M, D = idx.numel(), vals.shape[-1]
         g = grad_out.float().contiguous()
         grad_values = torch.zeros(ctx.values_shape, dtype=torch.float32, device=vals.device)
         grad_xyz = torch.empty((M, 3), dtype=torch.float32, device=vals.device) if need_xyz else None
-        with torch.cuda.device(vals.device):
+        with _lib.device_guard(vals.device):
             _lib.check(_L.nsvf_trilinear_embed_bwd(_lib.current_stream(vals.device), M, D, _p(idx), _p(xyz),
                                                    _p(feats32), _p(centres), _p(vals), ctx.voxel_size, _p(g),
                                                    _p(grad_values), _p(grad_xyz)))

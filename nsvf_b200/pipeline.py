@@ -32,6 +32,7 @@ class NSVFPipeline(nn.Module):
         self.hierarchical = hierarchical_sampling
         self.fixed_fine_num_samples = fixed_fine_num_samples
         self.fine_num_sample_ratio = fine_num_sample_ratio
+        self.padded_samples = False     # True: results["samples"] are the reference's padded [N, max_len] tensors
 
     def prepare_hierarchical_sampling(self, inter, samples, results):
         """Bins of the fine pass = the coarse samples (nerf.py:64-79, nsvf.py:83-87)."""
@@ -93,17 +94,28 @@ class NSVFPipeline(nn.Module):
                 f.begin_step()
         encoder_states = self.encoder.precompute(id=torch.zeros(1, dtype=torch.long, device=ray_dir.device))
         ray_start, ray_dir, inter, hits, sampled = self.intersecting(ray_start, ray_dir, encoder_states)
-        n_rays = ray_dir.size(1)
         hits_flat = hits.reshape(-1)
-        inter = {k: v.reshape(-1, *v.shape[2:])[hits_flat] for k, v in inter.items()}
-        rs, rd = ray_start.reshape(-1, 3)[hits_flat], ray_dir.reshape(-1, 3)[hits_flat]
+        # rays that hit something: ONE nonzero (the only host sync of this stage) + row gathers, where the reference
+        # boolean-indexes five tensors (fairnr_model.py:157-159: five nonzero + sync pairs)
+        hit_rows = hits_flat.nonzero(as_tuple=True)[0]
+        if hit_rows.numel() == hits_flat.numel():       # every ray hit: the gathers would be copies
+            inter = {k: v.reshape(-1, *v.shape[2:]) for k, v in inter.items()}
+            rs, rd = ray_start.reshape(-1, 3), ray_dir.reshape(-1, 3)
+        else:
+            inter = {k: v.reshape(-1, *v.shape[2:]).index_select(0, hit_rows) for k, v in inter.items()}
+            rs, rd = (ray_start.reshape(-1, 3).index_select(0, hit_rows),
+                      ray_dir.reshape(-1, 3).index_select(0, hit_rows))
         encoder_states = {k: v.reshape(-1, v.size(-1)) for k, v in encoder_states.items()}
         dev = ray_dir.device
         results = {"ae": 0}
         bg = self.field.bg_color if hasattr(self.field, "bg_color") else torch.ones(3, device=dev)
+        # trimmed sample rows (no padding traffic, no max_len sync) whenever nothing but our renderer reads them
+        trimmed = not (self.hierarchical or getattr(self.encoder, "track_max_probs", False) or self.padded_samples)
         if rs.size(0) > 0:
-            samples = self.encoder.ray_sample(inter)
-            r = self.raymarcher(self.encoder, self.field, rs, rd, samples, encoder_states)
+            samples = self.encoder.ray_sample(inter, trimmed=trimmed)
+            # 'probs' [B,K] is read by hierarchical sampling and track_voxel_probs only
+            need_probs = self.hierarchical or getattr(self.encoder, "track_max_probs", False) or self.padded_samples
+            r = self.raymarcher(self.encoder, self.field, rs, rd, samples, encoder_states, return_probs=need_probs)
             if self.hierarchical:      # second, importance-sampled pass (fairnr_model.py:167-173)
                 results["coarse"] = {k: r[k] for k in ("colors", "missed", "depths", "probs")}
                 inter = self.prepare_hierarchical_sampling(inter, samples, r)

@@ -88,64 +88,74 @@ def compact_samples(sampled_idx, sampled_depth, sampled_dists, ray_start, ray_di
 class _MarchRecord:
     """What one forward_chunk of the plan path leaves behind for compositing and its backward."""
 
-    def __init__(self, B, K, ldk, depth, lens, early_stop, eval_len, fe_rows, tex_rows, rows_padded):
-        self.B, self.K, self.ldk = B, K, ldk
-        self.depth, self.lens, self.early_stop, self.eval_len = depth, lens, early_stop, eval_len
-        self.fe_rows, self.tex_rows, self.rows_padded = fe_rows, tex_rows, rows_padded
+    def __init__(self, B, K, ldk, padded_depth_rows, depthT, lens, early_stop, eval_len, feT, texT, lazy=False):
+        self.B, self.K, self.ldk, self.lazy = B, K, ldk, lazy
+        self.padded_depth_rows, self.depthT = padded_depth_rows, depthT
+        self.lens, self.early_stop, self.eval_len, self.feT, self.texT = lens, early_stop, eval_len, feT, texT
         self.windows = []      # (start, end, M, ray_off, sigma, texture, sigma_f32, noise_f32, dists_f32)
 
 
 class _MarchComposite(Function):
-    """Compositing over the trimmed rows a plan run filled (renderer.py:193-218), differentiable w.r.t. every window's
-    field outputs: backward = trimmed compositing backward + one gather kernel per window (march_epilogue_bwd)."""
+    """Compositing over the slot-major planes a plan run filled (renderer.py:193-218), differentiable w.r.t. every
+    window's field outputs: backward = compositing backward + one gather kernel per window (march_epilogue_bwd).
+    'probs' is returned as the [B,K] view of its [K,B] plane."""
 
     @staticmethod
     def forward(ctx, rec, want_probs, *field_outputs):
         B, K = rec.B, rec.K
-        dev = rec.fe_rows.device
-        probs = torch.empty((B, K), dtype=torch.float32, device=dev) if want_probs else None
+        dev = rec.feT.device
+        ldb = _L.nsvf_march_plane_stride(B)
+        probsT = torch.empty((K, ldb), dtype=torch.float32, device=dev) if want_probs else None
         depth = torch.empty(B, dtype=torch.float32, device=dev)
         missed = torch.empty(B, dtype=torch.float32, device=dev)
         colors = torch.empty((B, 3), dtype=torch.float32, device=dev)
         maxd = torch.empty(B, dtype=torch.float32, device=dev)
         mind = torch.empty(B, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(_L.nsvf_composite_trimmed_fwd(
-                _lib.current_stream(dev), B, K, rec.ldk, _p(rec.eval_len), _p(rec.lens), _p(rec.early_stop),
-                _p(rec.fe_rows), _p(rec.tex_rows), _p(rec.depth), _p(probs), _p(depth), _p(missed),
-                _p(colors if rec.tex_rows is not None else None), _p(maxd), _p(mind), 10000.0, int(rec.rows_padded)))
-        if rec.tex_rows is None:
+            _lib.check(_L.nsvf_march_composite_fwd(
+                _lib.current_stream(dev), B, K, _p(rec.eval_len), _p(rec.lens), _p(rec.early_stop), _p(rec.feT),
+                _p(rec.texT), _p(rec.depthT), _p(probsT), _p(depth), _p(missed),
+                _p(colors if rec.texT is not None else None), _p(maxd), _p(mind), _p(rec.padded_depth_rows), rec.ldk,
+                10000.0, int(rec.lazy)))
+        if rec.texT is None:
             colors.zero_()
         ctx.rec = rec
         ctx.mark_non_differentiable(maxd, mind)
-        if probs is None:
+        if probsT is None:
             probs = torch.empty(0, device=dev)
             ctx.mark_non_differentiable(probs)
+        else:
+            probs = probsT[:, :B].t()
         return probs, depth, missed, colors, maxd, mind
 
     @staticmethod
     def backward(ctx, g_probs, g_depth, g_missed, g_colors, _g_maxd, _g_mind):
         rec = ctx.rec
         B, K = rec.B, rec.K
-        dev = rec.fe_rows.device
+        dev = rec.feT.device
 
         def c(t):
             return None if t is None else t.float().contiguous()
-        g_probs = c(g_probs) if (g_probs is not None and g_probs.numel() == B * K) else None
+        ldb = _L.nsvf_march_plane_stride(B)
+        g_probsT = None
+        if g_probs is not None and g_probs.numel() == B * K and K > 0:
+            g_probsT = torch.empty((K, ldb), dtype=torch.float32, device=dev)
+            g_probsT[:, :B] = g_probs.t()
         g_depth, g_missed, g_colors = c(g_depth), c(g_missed), c(g_colors)
-        has_tex = rec.tex_rows is not None
-        g_fe = torch.empty(B * K, dtype=torch.float32, device=dev)
-        g_tex = torch.empty(B * K * 3, dtype=torch.float32, device=dev) if has_tex else None
+        has_tex = rec.texT is not None
+        g_feT = torch.empty(K * ldb, dtype=torch.float32, device=dev)
+        scratch = torch.empty(K * ldb, dtype=torch.float32, device=dev)
+        g_texT = torch.empty(K * ldb * 3, dtype=torch.float32, device=dev) if has_tex else None
         grads = []
         with torch.cuda.device(dev):
             st = _lib.current_stream(dev)
-            _lib.check(_L.nsvf_composite_trimmed_bwd(
-                st, B, K, rec.ldk, _p(rec.eval_len), _p(rec.fe_rows), _p(rec.tex_rows), _p(rec.depth), _p(g_probs),
-                _p(g_depth), _p(g_missed), _p(g_colors if has_tex else None), _p(g_fe), _p(g_tex)))
+            _lib.check(_L.nsvf_march_composite_bwd(
+                st, B, K, _p(rec.eval_len), _p(rec.feT), _p(rec.texT), _p(rec.depthT), _p(g_probsT), _p(g_depth),
+                _p(g_missed), _p(g_colors if has_tex else None), _p(g_feT), _p(g_texT), _p(scratch)))
             for (start, end, M, ray_off, sigma, texture, sg, nz, dd) in rec.windows:
                 gs = torch.empty(M, dtype=torch.float32, device=dev)
                 gt = torch.empty((M, 3), dtype=torch.float32, device=dev) if texture is not None else None
-                _lib.check(_L.nsvf_march_epilogue_bwd(st, B, K, start, end, _p(ray_off), _p(g_fe), _p(g_tex), _p(sg),
+                _lib.check(_L.nsvf_march_epilogue_bwd(st, B, K, start, end, _p(ray_off), _p(g_feT), _p(g_texT), _p(sg),
                                                       _p(nz), _p(dd), _p(gs), _p(gt)))
                 grads.append(gs.view_as(sigma).to(sigma.dtype))
                 if texture is not None:
@@ -188,9 +198,11 @@ class VolumeRenderer(nn.Module):
         return out, M
 
     def forward_chunk(self, input_fn, field_fn, ray_start, ray_dir, samples, encoder_states,
-                      output_types=("sigma", "texture"), global_weights=None, noise_fn=None):
+                      output_types=("sigma", "texture"), global_weights=None, noise_fn=None, return_probs=None):
         """renderer.py:135-232.  `noise_fn(start, end, M)` (tests) supplies the sigma noise of a window instead of
-        torch.normal_."""
+        torch.normal_; `return_probs=False` (extension) leaves results['probs'] empty instead of writing the dense
+        [B,K] tensor that only track_voxel_probs and hierarchical sampling read."""
+        self._want_probs = self.return_probs if return_probs is None else bool(return_probs)
         if (global_weights is None and "sigma" in output_types and samples["sampled_point_voxel_idx"].dim() == 2
                 and not os.environ.get("NSVF_RENDER_GENERAL")):
             results = self._forward_chunk_plan(input_fn, field_fn, ray_start, ray_dir, samples, encoder_states,
@@ -212,7 +224,7 @@ class VolumeRenderer(nn.Module):
         if not ok:
             sidx, depth, dists = sidx.int().contiguous(), depth.float().contiguous(), dists.float().contiguous()
         B, K = sidx.shape
-        ldk = sidx.stride(0) if B > 1 else max(K, sidx.stride(0))
+        ldk = max(K, sidx.stride(0))
         dev = sidx.device
         ray_start, ray_dir = ray_start.float().contiguous(), ray_dir.float().contiguous()
         tolerance = self.raymarching_tolerance
@@ -221,48 +233,72 @@ class VolumeRenderer(nn.Module):
         want_tex = "texture" in output_types
         all_windows = tol <= 0
         rows_padded = lens is None
+        grad = torch.is_grad_enabled()
+        E = torch.empty
+        f32, i32 = torch.float32, torch.int32
         with torch.cuda.device(dev):
-            st = _lib.current_stream(dev)
-            plan = torch.zeros(_L.nsvf_march_plan_bytes(B, K) // 4 + 2, dtype=torch.int32, device=dev)
+            stream = torch.cuda.current_stream(dev)
+            st = stream.cuda_stream
+            plan = torch.zeros(_L.nsvf_march_plan_bytes(B, K) // 4 + 2, dtype=i32, device=dev)
             if lens is None:
-                lens = torch.empty(B, dtype=torch.int32, device=dev)
+                lens = E(B, dtype=i32, device=dev)
                 _lib.check(_L.nsvf_march_ray_lengths(st, B, K, ldk, _p(sidx), _p(lens), _p(plan)))
-            else:
+            elif lens.dtype != i32 or not lens.is_contiguous():
                 lens = lens.int().contiguous()
             info = self._host_info(16 + 3 * (K + 1))
+            info_ptr = info.data_ptr()
             _lib.check(_L.nsvf_march_begin(st, B, K, chunk_size, _p(lens), None, int(all_windows), _p(plan),
-                                           info.data_ptr(), info.numel()))
-            torch.cuda.current_stream(dev).synchronize()
+                                           info_ptr, info.numel()))
+            # slot-major planes of the samples (only the lens[r] valid slots of a row are touched)
+            ldb = _L.nsvf_march_plane_stride(B)
+            idxT, depthT, distsT = E(K * ldb, dtype=i32, device=dev), E(K * ldb, dtype=f32, device=dev), E(K * ldb, dtype=f32, device=dev)
+            early_stop = torch.zeros(B, dtype=torch.uint8, device=dev)
+            # without early termination every sample is needed: one transpose.  With it, columns are transposed in
+            # blocks just ahead of the window loop, and rays that have stopped are skipped.
+            t_block = K if (all_windows or rows_padded) else 64
+            t_upto = min(K, t_block)
+            _lib.check(_L.nsvf_march_transpose(st, B, K, ldk, 0, t_upto, None, _p(lens), _p(sidx), _p(depth), _p(dists),
+                                               _p(idxT), _p(depthT), _p(distsT)))
+            eval_len = torch.zeros(B, dtype=i32, device=dev)
+            acc_fe = torch.zeros(B, dtype=f32, device=dev) if tol > 0 else None
+            feT = E(K * ldb, dtype=f32, device=dev)
+            texT = E(K * ldb * 3, dtype=f32, device=dev) if want_tex else None
+            stream.synchronize()
             head = info[:16].tolist()
             if head[4]:
                 return None                      # some row's valid samples are not a prefix: general path
             if all_windows:
                 windows = info[16: 16 + 3 * head[5]].view(-1, 3).tolist()
             else:
-                windows = None if head[3] else [head[0:3]]
-            early_stop = torch.zeros(B, dtype=torch.uint8, device=dev)
-            eval_len = torch.zeros(B, dtype=torch.int32, device=dev)
-            acc_fe = torch.zeros(B, dtype=torch.float32, device=dev) if tol > 0 else None
-            fe_rows = torch.empty(B * K, dtype=torch.float32, device=dev)
-            tex_rows = torch.empty(B * K * 3, dtype=torch.float32, device=dev) if want_tex else None
-            record = _MarchRecord(B, K, ldk, depth, lens, early_stop, eval_len, fe_rows, tex_rows, rows_padded)
+                windows = [] if head[3] else [head[0:3]]
+            record = _MarchRecord(B, K, ldk, depth if rows_padded else None, depthT, lens, early_stop, eval_len, feT,
+                                  texT, lazy=t_block < K)
+            p_lens, p_es, p_acc, p_ev, p_plan = _p(lens), _p(early_stop), _p(acc_fe), _p(eval_len), _p(plan)
+            p_idxT, p_depthT, p_distsT, p_rs, p_rd = _p(idxT), _p(depthT), _p(distsT), _p(ray_start), _p(ray_dir)
+            p_feT, p_texT = _p(feT), _p(texT)
+            out_types = list(output_types)
             evals, launch_no, w = 0, 0, 0
-            while windows is not None and w < len(windows):
+            ray_off = None
+            while w < len(windows):
                 start, end, M = windows[w]
                 w += 1
-                vox = torch.empty(M, dtype=torch.int32, device=dev)
-                xyz = torch.empty((M, 3), dtype=torch.float32, device=dev)
-                dirs = torch.empty((M, 3), dtype=torch.float32, device=dev)
-                dists_c = torch.empty(M, dtype=torch.float32, device=dev)
-                ray_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
-                _lib.check(_L.nsvf_march_compact(st, B, K, ldk, start, end, _p(lens), _p(early_stop), _p(sidx),
-                                                 _p(depth), _p(dists), _p(ray_start), _p(ray_dir), _p(vox), _p(xyz),
-                                                 _p(dirs), _p(dists_c), _p(ray_off), _p(plan), launch_no))
+                vox, xyz, dirs = E(M, dtype=i32, device=dev), E((M, 3), dtype=f32, device=dev), E((M, 3), dtype=f32, device=dev)
+                dists_c = E(M, dtype=f32, device=dev)
+                while t_upto < end:
+                    t_next = min(K, t_upto + t_block)
+                    _lib.check(_L.nsvf_march_transpose(st, B, K, ldk, t_upto, t_next, p_es, p_lens, _p(sidx),
+                                                       _p(depth), _p(dists), p_idxT, p_depthT, p_distsT))
+                    t_upto = t_next
+                if grad or ray_off is None:      # the backward needs every window's offsets
+                    ray_off = E(B + 1, dtype=i32, device=dev)
+                _lib.check(_L.nsvf_march_compact(st, B, K, start, end, p_lens, p_es, p_idxT, p_depthT, p_distsT, p_rs,
+                                                 p_rd, _p(vox), _p(xyz), _p(dirs), _p(dists_c), _p(ray_off), p_plan,
+                                                 launch_no))
                 launch_no += 1
                 field_inputs = input_fn({"sampled_point_voxel_idx": vox, "sampled_point_xyz": xyz,
                                          "sampled_point_ray_direction": dirs, "sampled_point_distance": dists_c},
                                         encoder_states)
-                field_outputs = field_fn(field_inputs, outputs=list(output_types))
+                field_outputs = field_fn(field_inputs, outputs=out_types)
                 sigma = field_outputs["sigma"]
                 texture = field_outputs["texture"] if want_tex else None
                 if noise_fn is not None:
@@ -271,23 +307,31 @@ class VolumeRenderer(nn.Module):
                     noise = torch.zeros_like(sigma).normal_()                       # renderer.py:118
                 else:
                     noise = None
-                sg = sigma.detach().float().contiguous()
-                tx = texture.detach().float().contiguous() if texture is not None else None
+                sg = sigma.detach()
+                if sg.dtype != f32 or not sg.is_contiguous():
+                    sg = sg.float().contiguous()
+                tx = None
+                if texture is not None:
+                    tx = texture.detach()
+                    if tx.dtype != f32 or not tx.is_contiguous():
+                        tx = tx.float().contiguous()
                 nz = noise.float().contiguous() if noise is not None else None
-                dd = field_inputs["dists"].detach().float().contiguous()
-                _lib.check(_L.nsvf_march_epilogue(st, B, K, start, end, _p(ray_off), _p(lens), _p(early_stop),
-                                                  _p(acc_fe), _p(eval_len), _p(sg), _p(nz), _p(dd), _p(tx), float(tol),
-                                                  _p(fe_rows), _p(tex_rows), chunk_size, int(not all_windows),
-                                                  _p(plan), info.data_ptr()))
+                dd = field_inputs["dists"]
+                if dd is not dists_c:
+                    dd = dd.detach().float().contiguous()
+                _lib.check(_L.nsvf_march_epilogue(st, B, K, start, end, _p(ray_off), p_lens, p_es, p_acc, p_ev,
+                                                  _p(sg), _p(nz), _p(dd), _p(tx), tol, p_feT, p_texT, chunk_size,
+                                                  int(not all_windows), p_plan, info_ptr))
                 evals += M
-                record.windows.append((start, end, M, ray_off, sigma, texture, sg, nz, dd))
+                if grad:
+                    record.windows.append((start, end, M, ray_off, sigma, texture, sg, nz, dd))
                 if not all_windows:
-                    torch.cuda.current_stream(dev).synchronize()
+                    stream.synchronize()
                     head = info[:4].tolist()
                     if not head[3]:
                         windows.append(head[0:3])
-            outs = _MarchComposite.apply(record, self.return_probs, *[t for wnd in record.windows for t in
-                                                                       (wnd[4], wnd[5]) if t is not None])
+            tracked = [t for wnd in record.windows for t in (wnd[4], wnd[5]) if t is not None]
+            outs = _MarchComposite.apply(record, self._want_probs, *tracked)
         probs, depth_out, missed, colors, max_depths, min_depths = outs
         results = {"probs": probs, "depths": depth_out, "max_depths": max_depths, "min_depths": min_depths,
                    "missed": missed, "ae": evals}
@@ -384,8 +428,14 @@ class VolumeRenderer(nn.Module):
             parts = [self.forward_chunk(input_fn, field_fn, ray_start[i: i + chunk_size], ray_dir[i: i + chunk_size],
                                         {name: s[i: i + chunk_size] for name, s in samples.items()}, *args, **kwargs)
                      for i in range(0, ray_start.size(0), chunk_size)]
-            results = {name: torch.cat([r[name] for r in parts], 0) if torch.is_tensor(parts[0][name])
-                       else sum(r[name] for r in parts) for name in parts[0]}
+            def merge(name):
+                vals = [r[name] for r in parts]
+                if not torch.is_tensor(vals[0]):
+                    return sum(vals)
+                if vals[0].dim() == 2 and vals[0].size(1) > 1 and vals[0].stride(0) == 1:
+                    return torch.cat([v.t() for v in vals], 1).t()      # [K,B] planes (probs of the plan path)
+                return torch.cat(vals, 0)
+            results = {name: merge(name) for name in parts[0]}
         if getattr(input_fn, "track_max_probs", False) and (not self.training):
             input_fn.track_voxel_probs(samples["sampled_point_voxel_idx"], results["probs"])
         return results

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+NSVF_PROFILE_PY=1 timeout 300 python scratch/r2_frame_prof.py trivial 5 > gpurun_out/r2c4_frame.txt 2>&1
+head -45 gpurun_out/r2c4_frame.txt
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2c4_frame_launches.csv python scratch/r2_frame_prof.py trivial 1 > gpurun_out/r2c4_ncu.log 2>&1
+tail -2 gpurun_out/r2c4_ncu.log
