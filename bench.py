@@ -46,6 +46,11 @@ import numpy as np
 import torch
 
 VIEWS, RES, PIX_PER_VIEW = 4, 800, 2048
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the frame's kernels, `ncu --set full` on the C3 hot-path frame
+# (profiles/r2_ncu_c3_frame.md; same scene, camera and chunking as frame_bench below)
+NCU_TRAFFIC = {"inverse_cdf_sampling_kernel": 7.305e9, "march_composite_fwd_kernel": 0.983e9,
+               "march_compact_kernel": 21.5e6, "trilinear_fwd_kernel": 19.7e6, "march_epilogue_kernel": 14.7e6,
+               "aabb_intersect_kernel": 0.999e9, "march_transpose_kernel": None}
 LN_BWD_DRAM_TRAFFIC = 149.0e6  # bytes per launch: dram read 135 MB + write 14 MB, ncu --set full, [65536, 256] (profiles/r1b_ncu_ln_relu.md)
 METRIC = "rays/s (intersect+sample+composite), nsvf_base training step"
 
@@ -56,6 +61,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5"],
+                    help="BASELINE.json configs[1..4]; C2 (the nsvf_base training step) is the headline the driver runs, "
+                         "the others are the multi-GPU runs of configs[2..4] (frames sharded / octree + sharded pruning / "
+                         "hierarchical training)")
     ap.add_argument("--no-frame", action="store_true", help="skip the C3 full-frame extra")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-on-this-GPU legs (child process)")
@@ -378,25 +387,41 @@ def run_ours(args):
     except Exception as e:
         hot = None
         line["value_hot_path"] = {"error": repr(e)[:200]}
-    if rank == 0 and world == 1 and not args.no_ref_gpu:
+    if rank == 0 and not args.no_frame:
+        # BASELINE.json configs[2]: one 800x800 frame of the C3 scene (eval, early termination 0.01, chunk 512), with the
+        # field MLP and with the stand-in field; the §8 kernels are timed live inside the hot-path frame
+        c3 = None
         try:
-            ours = {"step": {"ms_per_step": round(ms / args.steps, 4)},
-                    "step_hot_path": {"ms_per_step": hot["ms_per_step"] if hot else None}}
-            ref, vs = ref_gpu_leg(dev, pipe, [tuple(t.cpu() for t in b) for b in host], out["sampled"].reshape(-1),
-                                  ours, steps=min(args.steps, 6))
-            line["ref_gpu"], line["vs_ref_gpu"] = ref, vs
-            if isinstance(ref.get("ours"), dict) and "frame" in ref["ours"]:
-                line["frame"] = {"with_field_mlp": ref["ours"]["frame"],
-                                 "hot_path_only(trivial field)": ref["ours"]["frame_hot_path"]}
+            from nsvf_b200 import synthetic
+            rs3, rd3 = synthetic.camera_rays(RES, RES, 1, radius=4.5, seed=7, device=dev)
+            rs3, rd3 = rs3[None, :, None, 0, :].contiguous(), rd3[None].contiguous()
+            pipe_c3, scene3 = build_model(dev, "C3", train=False, field="mlp", tolerance=0.01, chunk=512, sigma_bias=2.0)
+            fr = frame_bench(dev, pipe_c3, rs3, rd3)
+            c3 = {"pipe": pipe_c3, "scene": scene3, "rs": rs3, "rd": rd3, "frame": fr}
+            line["frame"] = {k: v for k, v in fr.items() if not k.startswith("_")}
+            kernels = frame_rooflines(dev, pipe_c3, rs3, rd3, peak, peak_src,
+                                      fr["hot_path_only(trivial field)"]["ms_per_800x800_frame"])
+            for k in kernels:
+                k["traffic"] = NCU_TRAFFIC.get(k["kernel"])
+            hbm = [k for k in kernels if k["kernel"] != "aabb_intersect_kernel"]
+            if hbm:
+                # THE roofline of this line: the HBM-bound kernel of the ray-marching path with the largest share of the
+                # frame's device time; the field-MLP glue kernel that led round 1's line moves to roofline_mlp_glue
+                line["roofline_mlp_glue"] = line["roofline"]
+                line["roofline"] = max(hbm, key=lambda k: k["share_of_frame"])
+            line["roofline_kernels"] = kernels
         except Exception as e:
-            line["ref_gpu"] = {"error": repr(e)[:300]}
-    elif rank == 0 and not args.no_frame:
-        try:
-            fr = frame_bench(dev)
-            fr.pop("_hot_out", None)
-            line["frame"] = fr
-        except Exception as e:
-            line["frame"] = {"error": repr(e)[:200]}
+            line["frame"] = {"error": repr(e)[:300]}
+        if world == 1 and not args.no_ref_gpu and c3 is not None:
+            try:
+                ours = {"step": {"ms_per_step": round(ms / args.steps, 4)},
+                        "step_hot_path": {"ms_per_step": hot["ms_per_step"] if hot else None}}
+                ref, vs = ref_gpu_leg(dev, pipe, [tuple(t.cpu() for t in b) for b in host], out["sampled"].reshape(-1),
+                                      ours, steps=min(args.steps, 6), c3=c3)
+                line["ref_gpu"], line["vs_ref_gpu"] = ref, vs
+            except Exception as e:
+                line["ref_gpu"] = {"error": repr(e)[:300]}
+        del c3
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             # bounded sample: ~10-20 s of host-core work (8 steps of 1/4 of the rays each)
@@ -543,6 +568,75 @@ def stage_times(dev, pipe, batch):
     return res
 
 
+def live_kernel_time(fn, name, repeats=2):
+    """Device time of every launch of kernel `name` inside `fn()` (library hook: one CUDA event pair per launch, recorded
+    on the launching stream) -> (launches per call, total ms per call, min launch ms, max launch ms)."""
+    import ctypes
+    from nsvf_b200 import _lib
+    L = _lib.load()
+    n, tot, mn, mx = ctypes.c_int(0), ctypes.c_float(0), ctypes.c_float(0), ctypes.c_float(0)
+    fn()
+    torch.cuda.synchronize()
+    L.nsvf_profile_begin(name.encode())
+    for _ in range(repeats):
+        fn()
+    torch.cuda.synchronize()
+    L.nsvf_profile_end(ctypes.addressof(n), ctypes.addressof(tot), ctypes.addressof(mn), ctypes.addressof(mx))
+    return n.value / repeats, tot.value / repeats, mn.value, mx.value
+
+
+def frame_rooflines(dev, pipe, rs, rd, peak, peak_src, frame_ms):
+    """The hand-written kernels of the ray-marching path, timed LIVE inside the C3 hot-path frame (stand-in field), against
+    the HBM roofline.  Algorithmic bytes per launch are SURVEY.md §8d's compulsory traffic (DESIGN.md §4 states them per
+    unit); the units one launch processes come from the frame itself (rays, emitted samples, evaluated samples)."""
+    from nsvf_b200.field import TrivialField
+    saved, pipe.field = pipe.field, TrivialField()
+    state = {}
+
+    def frame():
+        with torch.no_grad():
+            state["out"] = pipe(rs, rd)
+    try:
+        frame()
+        out = state["out"]
+        rays = int(out["hits"].sum())
+        ae = int(out["ae"])
+        emitted = int(out["samples"]["sampled_point_count"].sum()) if "sampled_point_count" in out["samples"] else ae
+        P, n_vox = int(pipe.encoder.max_hits), int(pipe.encoder.num_voxels)
+        all_rays = rd.numel() // 3
+        table = [  # (profile name, what, bound, bytes per FRAME as a function of launches)
+            ("inverse_cdf_sampling_kernel", "inverse-CDF sampler, %d rays -> %d samples" % (rays, emitted), "hbm",
+             lambda n: rays * (16 * P + 4 + 4) + 12 * emitted),
+            ("trilinear_fwd_kernel", "trilinear interpolation fwd, %d samples in the frame's windows" % ae, "hbm",
+             lambda n: 144 * ae + 0 * n),
+            ("march_compact_kernel", "window compaction (12 B in + 32 B out per sample, 9 B per ray and window)", "hbm",
+             lambda n: 44 * ae + 9 * rays * n),
+            ("march_epilogue_kernel", "free energy + scatter + early stop (36 B per sample, 21 B per ray and window)", "hbm",
+             lambda n: 36 * ae + 21 * rays * n),
+            ("march_composite_fwd_kernel", "compositing over the planes (20 B per evaluated sample, 36 B per ray)", "hbm",
+             lambda n: 20 * ae + 36 * rays),
+            ("march_transpose_kernel", "row -> slot-major transpose (24 B per sample; lower bound: evaluated samples)", "hbm",
+             lambda n: 24 * ae),
+            ("aabb_intersect_kernel", "sorted aabb intersection, %d rays x %d voxels (ALU / L1-bound by design)" % (all_rays, n_vox),
+             "hbm", lambda n: all_rays * (24 + 12 * P + 1) + 24 * n_vox),
+        ]
+        res = []
+        for name, what, bound, nbytes in table:
+            launches, ms, mn, mx = live_kernel_time(frame, name)
+            if launches == 0 or ms <= 0:
+                continue
+            b = nbytes(launches)
+            ach = b / (ms / 1e3) / 1e9
+            res.append({"kernel": name, "what": what, "bound": bound, "achieved": round(ach, 1), "peak": peak,
+                        "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                        "launches_per_frame": launches, "ms_per_frame": round(ms, 4),
+                        "avg_launch_ms": round(ms / launches, 5), "algorithmic_bytes_per_launch": int(b / launches),
+                        "share_of_frame": round(ms / frame_ms, 4), "workload": "C3 800x800 frame, hot path only"})
+        return res
+    finally:
+        pipe.field = saved
+
+
 def frame_bench(dev, pipe=None, rs=None, rd=None):
     """ms per 800x800 frame on the C3 scene (BASELINE.json configs[2]): eval, early termination 0.01, chunk 512."""
     from nsvf_b200 import synthetic
@@ -607,7 +701,7 @@ def _ours_clib(dev, pipe, rs, rd, march, n, warm):
             "rays_per_s": round(rays / ((t_int + t_smp) / 1e3), 1)}
 
 
-def ref_gpu_leg(dev, pipe_c2, host_batches, march, ours, steps):
+def ref_gpu_leg(dev, pipe_c2, host_batches, march, ours, steps, c3):
     """Runs baseline/ref_gpu.py (unmodified reference, child process) on this GPU with OUR voxels, weights, rays and
     targets, then our side of the same legs.  `ours` carries the numbers the main arm already measured.
     -> (ref_gpu, vs_ref_gpu)."""
@@ -618,9 +712,7 @@ def ref_gpu_leg(dev, pipe_c2, host_batches, march, ours, steps):
     if not install_ref.installed():
         return {"unavailable": "baseline/_ref is not populated (python baseline/install_ref.py where /root/reference exists)"}, None
     tmp = tempfile.mkdtemp(prefix="nsvf_refgpu_")
-    rs3, rd3 = synthetic.camera_rays(RES, RES, 1, radius=4.5, seed=7)
-    rs3, rd3 = rs3[None, :, None, 0, :].contiguous(), rd3[None].contiguous()
-    pipe_c3, scene3 = build_model(dev, "C3", train=False, field="mlp", tolerance=0.01, chunk=512, sigma_bias=2.0)
+    pipe_c3, scene3, rs3, rd3, fr = c3["pipe"], c3["scene"], c3["rs"].cpu(), c3["rd"].cpu(), c3["frame"]
     inp = {"steps": steps,
            "C2": {"state": {k: v.cpu() for k, v in checkpoint.to_reference_state_dict(pipe_c2).items()},
                   "bbox_line": "-1.2 -1.2 -1.2 1.2 1.2 1.2 0.4", "max_hits": 60, "chunk": 64, "tolerance": 0.0,
@@ -651,7 +743,6 @@ def ref_gpu_leg(dev, pipe_c2, host_batches, march, ours, steps):
     rs2, rd2 = host_batches[0][0].to(dev), host_batches[0][1].to(dev)
     mine["clib_C2"] = _ours_clib(dev, pipe_c2, rs2, rd2, march, 5, 2)
     mine["clib_C3"] = _ours_clib(dev, pipe_c3, rs3.to(dev), rd3.to(dev), None, 5, 2)
-    fr = frame_bench(dev, pipe_c3, rs3.to(dev), rd3.to(dev))
     mine["frame"], mine["frame_hot_path"] = fr["with_field_mlp"], fr["hot_path_only(trivial field)"]
     # parity of the two arms on the tensors that were timed (deterministic eval frame, trivial field)
     try:
@@ -661,11 +752,15 @@ def ref_gpu_leg(dev, pipe_c2, host_batches, march, ours, steps):
             "colors_max_abs_diff": float((o["colors"].cpu() - theirs["colors"]).abs().max()),
             "depths_max_abs_diff": float((o["depths"].cpu() - theirs["depths"]).abs().max()),
             "missed_max_abs_diff": float((o["missed"].cpu() - theirs["missed"]).abs().max()),
+            "rays_with_colour_diff_above_1e-5": int(((o["colors"].cpu() - theirs["colors"]).abs().max(-1)[0] > 1e-5).sum()),
+            "rays": int(theirs["missed"].numel()),
+            "note": "early termination compares a running fp32 free-energy sum with -log(0.01) after every window; the two "
+                    "arms interpolate with different (tolerance-equal) op orders, so a ray whose sum lands within an ulp of "
+                    "the threshold can stop one window apart — those rays carry the whole difference",
             "field_evaluations_equal": bool(fr["hot_path_only(trivial field)"]["field_evaluations"]
                                             == ref.get("frame_hot_path", {}).get("field_evaluations"))}
     except Exception as e:
         ref["frame_parity_vs_ours"] = {"error": repr(e)[:200]}
-    fr.pop("_hot_out", None)
 
     def ratio(a, b):
         try:
@@ -777,9 +872,275 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------------
+# configs[2..4] on N GPUs (same launch contract; the driver's own runs use the default C2)
+# ------------------------------------------------------------------------------------------------------
+def _dist_setup():
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    return dist, world, rank, local, dev
+
+
+def _timed_steps(dist, world, dev, step, n):
+    """n calls of step(i) between barrier + synchronize on both sides; CUDA-event time, MAX over ranks (ms)."""
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    last = None
+    for i in range(n):
+        last = step(i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, last
+
+
+def _base_line(args, world, value, unit, ms, n_warm, workload, extra_cfg, clocks, launches, e2e):
+    line = {"metric": METRIC if args.config == "C5" else "rays/s (intersect+sample+composite)", "value": round(value, 1),
+            "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
+            "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": dict({"workload": workload}, **extra_cfg), "clocks": clocks,
+            "gpu_launches": int(launches), "e2e": e2e}
+    return line
+
+
+def run_c3(args):
+    """configs[2]: 800x800 full-frame rendering of the ~112k-voxel scene with early termination, frames sharded over the
+    ranks (fairnr_cli/render_multigpu.py:95-104: every rank renders its own frames), colours gathered on rank 0."""
+    from nsvf_b200 import _lib, synthetic
+    from nsvf_b200.field import TrivialField
+    L = _lib.load()
+    dist, world, rank, local, dev = _dist_setup()
+    pipe, scene = build_model(dev, "C3", train=False, field="mlp", tolerance=0.01, chunk=512, sigma_bias=2.0)
+    frames = []
+    for f in range(4):     # this rank's cameras (frame f of rank r = camera 4 r + f of the trajectory)
+        rs, rd = synthetic.camera_rays(RES, RES, 1, radius=4.5, seed=100 + 4 * rank + f)
+        frames.append((rs[None, :, None, 0, :].contiguous().pin_memory(), rd[None].contiguous().pin_memory()))
+    resident = [(a.to(dev), b.to(dev)) for a, b in frames]
+    staging = (torch.empty_like(resident[0][0]), torch.empty_like(resident[0][1]))
+    gathered = [torch.empty(RES * RES, 3, device=dev) for _ in range(world)] if rank == 0 else None
+    host_out = torch.empty(RES * RES, 3).pin_memory()
+
+    def render(i, from_host=False):
+        if from_host:
+            staging[0].copy_(frames[i % 4][0], non_blocking=True)
+            staging[1].copy_(frames[i % 4][1], non_blocking=True)
+            rs, rd = staging
+        else:
+            rs, rd = resident[i % 4]
+        with torch.no_grad():
+            out = pipe(rs, rd)
+        if world > 1:        # deliver the frame to rank 0 (NCCL gather over NVLink)
+            dist.gather(out["colors"], gathered, dst=0)
+        if from_host:
+            host_out.copy_(out["colors"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return out
+    res = {}
+    sampler = ClockSampler(local)
+    sampler.start()
+    n_warm = max(args.warmup, 3)
+    for name, field in (("with_field_mlp", pipe.field), ("hot_path_only", TrivialField())):
+        pipe.field = field
+        _timed_steps(dist, world, dev, render, n_warm)
+        sampler.reset()
+        l0 = L.nsvf_kernel_launches()
+        ms, out = _timed_steps(dist, world, dev, render, args.steps)
+        res[name] = {"ms": ms, "launches": L.nsvf_kernel_launches() - l0, "ae": int(out["ae"]), "clocks": None}
+        if name == "with_field_mlp":
+            clocks = sampler.stop()
+            ms_e2e, _ = _timed_steps(dist, world, dev, lambda i: render(i, True), args.steps)
+    rays = RES * RES
+    m = res["with_field_mlp"]
+    line = _base_line(
+        args, world, world * rays * args.steps / (m["ms"] / 1e3), "rays/s", m["ms"], n_warm,
+        "C3: 800x800 full-frame render, %d voxels (voxel 0.1, step 1/8, max_hits 135), eval, early termination 0.01, "
+        "chunk 512, one frame per GPU and step, frames sharded over the GPUs, field MLP fp32 on cuBLAS" % scene.n,
+        {"mlp_gemm": _blas.mode(), "field_evaluations_last_frame": m["ae"], "l2": "inputs and intermediates of a frame "
+         "(> 10 GB) exceed the 126 MB L2", "parallelism": "frames sharded x%d, voxel set replicated, NCCL gather of the "
+         "colours to rank 0" % world},
+        clocks, m["launches"],
+        {"value": round(world * rays * args.steps / (ms_e2e / 1e3), 1), "unit": "rays/s",
+         "h2d_bytes_per_step": sum(t.numel() * 4 for t in frames[0]), "d2h_bytes_per_step": rays * 12})
+    line["ms_per_800x800_frame"] = round(m["ms"] / args.steps, 3)
+    h = res["hot_path_only"]
+    line["value_hot_path"] = {"value": round(world * rays * args.steps / (h["ms"] / 1e3), 1), "unit": "rays/s",
+                              "ms_per_800x800_frame": round(h["ms"] / args.steps, 3), "field": "trivial (no contraction)",
+                              "field_evaluations_last_frame": h["ae"]}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def run_c4(args):
+    """configs[3]: --use-octree intersection of a frame's rays with the ~0.9 M-voxel scene (frames sharded over the ranks)
+    and one pruning pass (8^3 lattice points per voxel) with the voxels sharded over the ranks and the keep mask
+    all-gathered over NCCL (fairnr/modules/encoder.py:605-618 recomputes the full mask on every rank)."""
+    from nsvf_b200 import _lib, synthetic
+    from nsvf_b200.encoder import SparseVoxelEncoder
+    from nsvf_b200.field import RadianceField
+    L = _lib.load()
+    dist, world, rank, local, dev = _dist_setup()
+    torch.manual_seed(0)
+    scene = synthetic.make_scene("C4")
+    enc = SparseVoxelEncoder(scene.points, scene.voxel_size, max_hits=scene.max_hits, use_octree=True).to(dev).eval()
+    field = RadianceField(sigma_bias=0.0).to(dev).eval()
+    st = enc.precompute(id=torch.zeros(1, dtype=torch.long, device=dev))        # builds the octree (host, once)
+    frames = []
+    for f in range(2):
+        rs, rd = synthetic.camera_rays(RES, RES, 1, radius=4.5, seed=200 + 2 * rank + f, device=dev)
+        frames.append((rs[None, :, None, 0, :].contiguous(), rd[None].contiguous()))
+    hits_n = [0]
+
+    def intersect(i):
+        rs, rd = frames[i % 2]
+        with torch.no_grad():
+            _, _, inter, hits = enc.ray_intersect(rs, rd, st)
+        hits_n[0] = hits
+        return inter
+    sampler = ClockSampler(local)
+    sampler.start()
+    n_warm = max(args.warmup, 3)
+    _timed_steps(dist, world, dev, intersect, n_warm)
+    sampler.reset()
+    l0 = L.nsvf_kernel_launches()
+    ms, inter = _timed_steps(dist, world, dev, intersect, args.steps)
+    launches = L.nsvf_kernel_launches() - l0
+    clocks = sampler.stop()
+    rays = RES * RES
+    # pruning: voxels sharded (64-voxel chunks stay whole, so every field call sees the rows it would see on one GPU)
+    field_fn = lambda inp, outputs: field(inp, outputs=outputs)
+    keep0 = enc.keep.clone()
+    ms_prune, _ = _timed_steps(dist, world, dev, lambda i: (enc.keep.copy_(keep0),
+                                                          enc.pruning(field_fn, th=0.5, voxel_shard=(rank, world), bits=8)), 1)
+    sharded_keep = enc.keep.clone()
+    prune = {"voxels": scene.n, "lattice_points_per_voxel": 512, "ms_per_pass": round(ms_prune, 2),
+             "kept": int(sharded_keep.sum()), "keep_mask_allgather_bytes": scene.n,
+             "collective": "NCCL all_gather of the uint8 keep mask" if world > 1 else "none (1 GPU)"}
+    if world > 1 and not args.no_stages:
+        # parity of the exchange: the gathered mask must equal the mask one GPU computes alone (rank 0 recomputes it)
+        if rank == 0:
+            enc.keep.copy_(keep0)
+            enc.pruning(field_fn, th=0.5, bits=8)
+            prune["mask_equals_single_rank"] = bool(torch.equal(enc.keep, sharded_keep))
+        dist.barrier()
+    line = _base_line(
+        args, world, world * rays * args.steps / (ms / 1e3), "rays/s", ms, n_warm,
+        "C4: --use-octree svo_ray_intersect + sort of an 800x800 frame's rays per GPU against %d voxels (%d octree nodes, "
+        "max_hits 202), then one pruning pass (8^3 points per voxel) with the voxels sharded and the keep mask "
+        "all-gathered" % (scene.n, int(enc.flatten_centers.shape[0])),
+        {"l2": "hit lists of a frame (1.5 GB) exceed the 126 MB L2", "rays_hit_last_frame": int(hits_n[0].sum()),
+         "parallelism": "frames sharded x%d for the intersection; voxels sharded x%d for pruning" % (world, world)},
+        clocks, launches, {"value": None, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                           "note": "kernel-level config: rays are generated on the device, no end-to-end leg"})
+    line["metric"] = "rays/s (octree intersection + sort), pruning ms per pass"
+    line["prune"] = prune
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def run_c5(args):
+    """configs[4]: Tanks&Temples-shaped 1920x1080 scene (elongated bbox), hierarchical path (coarse pass + inverse-CDF
+    importance-sampled fine pass, fairnr/models/nerf.py:64-79), training step with the NCCL gradient all-reduce."""
+    from nsvf_b200 import _lib, synthetic
+    from nsvf_b200.encoder import SparseVoxelEncoder
+    from nsvf_b200.field import RadianceField
+    from nsvf_b200.pipeline import NSVFPipeline
+    from nsvf_b200.renderer import VolumeRenderer
+    L = _lib.load()
+    dist, world, rank, local, dev = _dist_setup()
+    H, W, V = 1080, 1920, 2
+    torch.manual_seed(0)
+    scene = synthetic.make_scene("C5")
+    enc = SparseVoxelEncoder(scene.points, scene.voxel_size, max_hits=scene.max_hits)
+    pipe = NSVFPipeline(enc, RadianceField(), VolumeRenderer(chunk_size=64, discrete_regularization=True),
+                        pixel_per_view=PIX_PER_VIEW, hierarchical_sampling=True, fixed_fine_num_samples=64).to(dev).train()
+    params = [p for p in pipe.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-3, betas=(0.9, 0.999))
+    flat_grad = torch.zeros(sum(p.numel() for p in params), device=dev)
+    off = 0
+    for p in params:
+        p.grad = flat_grad[off: off + p.numel()].view_as(p)
+        off += p.numel()
+    host = []
+    for b in range(2):
+        rs, rd = synthetic.camera_rays(H, W, V, radius=9.0, fov_focal=1111.0 * 800.0 / W * 1.6, seed=137 * b + rank)
+        g = torch.Generator().manual_seed(1000 + 137 * b + rank)
+        target = torch.rand(V * H * W, 3, generator=g) * 2 - 1
+        host.append((rs[None, :, None, 0, :].contiguous().pin_memory(), rd[None].contiguous().pin_memory(),
+                     target.pin_memory()))
+    resident = [tuple(t.to(dev) for t in b) for b in host]
+    staging = tuple(torch.empty_like(t, device=dev) for t in host[0])
+
+    def step(i, from_host=False):
+        if from_host:
+            for d, s_ in zip(staging, host[i % 2]):
+                d.copy_(s_, non_blocking=True)
+            rs, rd, target = staging
+        else:
+            rs, rd, target = resident[i % 2]
+        out = pipe(rs, rd)
+        loss = loss_fn(out, target)
+        flat_grad.zero_()
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)
+        opt.step()
+        if from_host:
+            loss.item()
+        return out
+    sampler = ClockSampler(local)
+    sampler.start()
+    n_warm = max(args.warmup, 3)
+    _timed_steps(dist, world, dev, step, n_warm)
+    sampler.reset()
+    l0 = L.nsvf_kernel_launches()
+    ms, out = _timed_steps(dist, world, dev, step, args.steps)
+    launches = L.nsvf_kernel_launches() - l0
+    clocks = sampler.stop()
+    ms_e2e, _ = _timed_steps(dist, world, dev, lambda i: step(i, True), args.steps)
+    marched = V * PIX_PER_VIEW
+    line = _base_line(
+        args, world, world * marched * args.steps / (ms / 1e3), "rays/s", ms, n_warm,
+        "C5: Tanks&Temples-shaped training step, %d voxels (bbox 12 x 8 x 6.4, voxel 0.2, step 1/8), %d views x 1920x1080 rays "
+        "intersected + %d x 2048 rays marched per GPU, hierarchical: coarse pass + 64 importance samples per ray "
+        "(inverse_cdf_sampling on the coarse samples), fwd+bwd+Adam, field MLP fp32 on cuBLAS" % (scene.n, V, V),
+        {"mlp_gemm": _blas.mode(), "samples_evaluated_per_step": int(out["ae"]), "l2": "per-step intermediates exceed the "
+         "126 MB L2 (2 x 2 M rays intersected)", "parallelism": "dp%d (rays sharded by view, voxel set replicated, one "
+         "flat-bucket NCCL grad all-reduce per step)" % world},
+        clocks, launches,
+        {"value": round(world * marched * args.steps / (ms_e2e / 1e3), 1), "unit": "rays/s",
+         "h2d_bytes_per_step": sum(t.numel() * 4 for t in host[0]), "d2h_bytes_per_step": 4})
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
     else:
-        run_ours(a)
+        {"C2": run_ours, "C3": run_c3, "C4": run_c4, "C5": run_c5}[a.config](a)

@@ -42,6 +42,12 @@ NSVF_API unsigned long long nsvf_kernel_launches(void);
  * before / after every launch of the kernel called `name` (e.g. "aabb_intersect_kernel"), so a caller can
  * time one kernel inside a longer step without a profiler.  name = NULL or "" clears the hook. */
 NSVF_API int nsvf_profile_kernel(const char* name, void* ev_start, void* ev_stop);
+/* Accumulating variant: between nsvf_profile_begin(name) and nsvf_profile_end every launch of kernel `name` is bracketed
+ * by its own event pair (pool of 8192 pairs owned by the library, recorded on the launching stream);
+ * nsvf_profile_end waits for the recorded events and returns the number of launches, their summed device time and the
+ * shortest / longest launch (ms).  This is how bench.py times a kernel "live", inside the step it belongs to. */
+NSVF_API int nsvf_profile_begin(const char* name);
+NSVF_API int nsvf_profile_end(int* n_launches, float* total_ms, float* min_ms, float* max_ms);
 
 /* y[i] = __fdividef(1.0f, x[i]) — the reciprocal the reference slab test uses
  * (fairnr/clib/src/intersect_gpu.cu:86-90). Test helper: lets a CPU oracle consume the exact values. */

@@ -18,6 +18,8 @@ SIGNATURES = {
     "nsvf_last_error": (ctypes.c_char_p, []),
     "nsvf_kernel_launches": (ctypes.c_ulonglong, []),
     "nsvf_profile_kernel": (c_int, [ctypes.c_char_p, c_void_p, c_void_p]),
+    "nsvf_profile_begin": (c_int, [ctypes.c_char_p]),
+    "nsvf_profile_end": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "nsvf_ref_rcp": (c_int, [c_void_p, c_ll, c_void_p, c_void_p]),
     "nsvf_aabb_workspace_bytes": (c_size_t, [c_int, c_int]),
     "nsvf_aabb_intersect": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p,

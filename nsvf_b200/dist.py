@@ -11,11 +11,14 @@ import torch
 import torch.distributed as dist
 
 
-def shard_range(n, rank, world):
-    """Contiguous slice [lo, hi) of n items owned by `rank` (sizes differ by at most one)."""
-    base, rem = divmod(n, world)
+def shard_range(n, rank, world, align=1):
+    """Contiguous slice [lo, hi) of n items owned by `rank`: sizes differ by at most one block of `align` items, and
+    every boundary except the last is a multiple of `align`."""
+    blocks = (n + align - 1) // align
+    base, rem = divmod(blocks, world)
     lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+    hi = lo + base + (1 if rank < rem else 0)
+    return min(lo * align, n), min(hi * align, n)
 
 
 def shard_rays(ray_start, ray_dir, rank, world, dim=1):
@@ -27,11 +30,11 @@ def shard_rays(ray_start, ray_dir, rank, world, dim=1):
     return rs, ray_dir[tuple(sl)]
 
 
-def allgather_keep_mask(local_keep, n, rank, world, group=None):
+def allgather_keep_mask(local_keep, n, rank, world, group=None, align=1):
     """All-gather of the per-shard keep masks (uint8, n bytes in total) -> bool [n] on every rank."""
     if world == 1 or not dist.is_initialized():
         return local_keep.bool()
-    sizes = [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
+    sizes = [shard_range(n, r, world, align)[1] - shard_range(n, r, world, align)[0] for r in range(world)]
     pad = max(sizes)
     buf = torch.zeros(pad, dtype=torch.uint8, device=local_keep.device)
     buf[: local_keep.numel()] = local_keep.to(torch.uint8)

@@ -160,16 +160,14 @@ class SparseVoxelEncoder(nn.Module):
                 centers, children = centers.unsqueeze(0), children.unsqueeze(0)
             pts_idx, min_depth, max_depth = clib.svo_ray_intersect(
                 self.voxel_size, self.max_hits, centers, children, ray_start, ray_dir)
-            # masked_fill + sort by entry depth + gather + any() (encoder.py:519-524) as one in-place kernel
-            if min_depth.dtype == torch.float32 and min_depth.is_contiguous() and pts_idx.is_contiguous():
-                hits = clib._ext.sort_hits_by_depth(pts_idx, min_depth, max_depth, MAX_DEPTH)
-            else:
-                min_depth.masked_fill_(pts_idx.eq(-1), MAX_DEPTH)
-                max_depth.masked_fill_(pts_idx.eq(-1), MAX_DEPTH)
-                min_depth, sorted_idx = min_depth.sort(dim=-1)
-                max_depth = max_depth.gather(-1, sorted_idx)
-                pts_idx = pts_idx.gather(-1, sorted_idx)
-                hits = pts_idx.ne(-1).any(-1)
+            # masked_fill + sort by entry depth + gather + any() (encoder.py:519-524) as one in-place kernel; fp16 models
+            # get their depths cast to fp32 for it and back afterwards (no eager-torch path)
+            in_dtype = min_depth.dtype
+            pts_idx = pts_idx.int().contiguous()
+            min_depth, max_depth = min_depth.float().contiguous(), max_depth.float().contiguous()
+            hits = clib._ext.sort_hits_by_depth(pts_idx, min_depth, max_depth, MAX_DEPTH)
+            if in_dtype != torch.float32:
+                min_depth, max_depth = min_depth.to(in_dtype), max_depth.to(in_dtype)
         else:
             # intersection + masked_fill + sort + gather + any() of encoder.py:511-524 in ONE kernel
             pts_idx, min_depth, max_depth, hits = clib._ext.aabb_intersect_sorted(
@@ -244,20 +242,22 @@ class SparseVoxelEncoder(nn.Module):
         self.max_voxel_probs = ops.track_voxel_probs(mvp, voxel_idxs, voxel_probs)
 
     @torch.no_grad()
-    def pruning(self, field_fn, th=0.5, encoder_states=None, train_stats=False, voxel_shard=None):
+    def pruning(self, field_fn, th=0.5, encoder_states=None, train_stats=False, voxel_shard=None, bits=16):
         """keep-mask update (encoder.py:605-618).  `voxel_shard=(rank, world)` scores only this rank's contiguous
         slice of the voxels and all-gathers the uint8 keep mask (nsvf_b200.dist.allgather_keep_mask): the
         multi-GPU pruning of BASELINE.json; the reference recomputes the full mask on every rank."""
         if not train_stats:
             if voxel_shard is None:
-                keep, _ = self._prune_scores(field_fn, th, bits=16, encoder_states=encoder_states)
+                keep, _ = self._prune_scores(field_fn, th, bits=bits, encoder_states=encoder_states)
             else:
                 from . import dist as nsvf_dist
                 rank, world = voxel_shard
                 n = int(self.keep.bool().sum())
-                lo, hi = nsvf_dist.shard_range(n, rank, world)
-                part, _ = self._prune_scores(field_fn, th, bits=16, encoder_states=encoder_states, lo=lo, hi=hi)
-                keep = nsvf_dist.allgather_keep_mask(part, n, rank, world)
+                # shard boundaries on multiples of the 64-voxel field-call granularity: every field call then sees
+                # exactly the rows it would see on one GPU, so the gathered mask is bit-identical to the single-rank one
+                lo, hi = nsvf_dist.shard_range(n, rank, world, align=64)
+                part, _ = self._prune_scores(field_fn, th, bits=bits, encoder_states=encoder_states, lo=lo, hi=hi)
+                keep = nsvf_dist.allgather_keep_mask(part, n, rank, world, align=64)
         else:
             import torch.distributed as dist
             if dist.is_initialized() and dist.get_world_size() > 1:

@@ -12,6 +12,7 @@ csrc/field_norm.cu and csrc/field_misc.cu, and GraphedField replays a whole chun
 CUDA only, no fallback: the plain-torch composition of the same network is oracle/field_ref.py (test infrastructure).
 """
 import math
+import weakref
 
 import torch
 import torch.nn as nn
@@ -101,6 +102,26 @@ class _FieldCore(nn.Module):
         return out["sigma"], out["texture"]
 
 
+class _SlotToken:
+    """Lives in the autograd node of one graphed chunk; its finalizer frees the slot if the graph dies without backward."""
+
+
+class _SlotGuard(torch.autograd.Function):
+    """Identity on a replayed chunk's outputs that tells the GraphedField when the chunk's backward has run."""
+
+    @staticmethod
+    def forward(ctx, owner_ref, key, token, sigma, texture):
+        ctx.owner_ref, ctx.key, ctx.token = owner_ref, key, token
+        return sigma.view_as(sigma), texture.view_as(texture)
+
+    @staticmethod
+    def backward(ctx, g_sigma, g_texture):
+        owner = ctx.owner_ref()
+        if owner is not None:
+            owner._pending.discard(ctx.key)
+        return None, None, None, g_sigma, g_texture
+
+
 class GraphedField(nn.Module):
     """CUDA-graph replay of the field's forward and backward for the full-size chunks of a training step.
 
@@ -121,6 +142,9 @@ class GraphedField(nn.Module):
         self._calls = 0                     # launched from the host, where the library's event hook can time them
         self._graphed = None
         self._next = 0
+        self._pending = set()               # ids of slot replays whose backward has not run yet
+        self._blocked = False
+        self._uses = 0
         self.graph_replays = 0
         self.launches_per_replay = 0
 
@@ -129,8 +153,13 @@ class GraphedField(nn.Module):
         return self.field.bg_color
 
     def begin_step(self):
-        self._next = 0
+        """Start of a pipeline forward.  Slots are replayed in capture order from 0 — but only when no slot of an
+        earlier forward still waits for its backward: replaying it again would overwrite the static inputs and saved
+        activations that backward will read.  Until those backwards have run, chunks evaluate eagerly."""
         self._calls = 0
+        self._blocked = len(self._pending) > 0
+        if not self._blocked:
+            self._next = 0
 
     def capture(self, dev, embed_dim=32):
         """Capture the chunk graphs.  Must run before any eager forward of the field whose autograd graph is still alive:
@@ -160,7 +189,7 @@ class GraphedField(nn.Module):
                      and inputs.get("feat", None) is None and "sigma" in outputs and "texture" in outputs
                      and emb.requires_grad and emb.dim() == 2
                      and self.rows * self.min_fill <= M <= self.rows and self._next < self.slots
-                     and self._calls >= self.eager_first)
+                     and self._calls >= self.eager_first and not self._blocked)
         eager_padded = (self.training and torch.is_grad_enabled() and emb is not None and emb.is_cuda and emb.dim() == 2
                         and inputs.get("feat", None) is None and "sigma" in outputs and "texture" in outputs
                         and self.rows * self.min_fill <= M <= self.rows and self._calls < self.eager_first)
@@ -184,6 +213,12 @@ class GraphedField(nn.Module):
         sigma, texture = self._graphed[self._next](emb.contiguous(), ray.contiguous())
         self._next += 1
         self.graph_replays += 1
+        if sigma.requires_grad:       # this slot must not be replayed again before its backward has consumed it
+            self._uses += 1
+            key, token = self._uses, _SlotToken()
+            self._pending.add(key)
+            weakref.finalize(token, self._pending.discard, key)      # graph dropped without a backward
+            sigma, texture = _SlotGuard.apply(weakref.ref(self), key, token, sigma, texture)
         inputs["sigma"], inputs["texture"] = sigma[:M], texture[:M]
         return inputs
 

@@ -119,8 +119,8 @@ def make_scene(name, seed=0):
         times = 2 if name == "C3" else 3
         pts, vs = split_points(pts, 0.4, times)
         return Scene(pts, vs, max_hits=135 if name == "C3" else 202, seed=seed)
-    if name == "C5":      # Tanks&Temples-shaped elongated bbox, 2 splits
-        pts = carve_shell(bbox_voxels([-6.0, -4.0, -3.2], [6.0, 4.0, 3.2], 0.4), 0.3, 1.0)
-        pts, vs = split_points(pts, 0.4, 2)
-        return Scene(pts, vs, max_hits=135, seed=seed)
+    if name == "C5":      # Tanks&Temples-shaped elongated bbox (12 x 8 x 6.4), thin shell, 1 split -> 28 464 voxels of 0.2
+        pts = carve_shell(bbox_voxels([-6.0, -4.0, -3.2], [6.0, 4.0, 3.2], 0.4), 0.75, 1.0)
+        pts, vs = split_points(pts, 0.4, 1)
+        return Scene(pts, vs, max_hits=90, seed=seed)
     raise ValueError(name)

@@ -196,3 +196,34 @@ def test_graphed_field_replays_match_eager(cuda):
         for (k, p), (_, q) in zip(graphed.field.named_parameters(), eager.named_parameters()):
             if q.grad is not None:
                 helpers.assert_close_scaled(p.grad, q.grad, rtol=1e-5, what=k)
+
+
+def test_graphed_field_two_forwards_before_backward(cuda):
+    """Two pipeline forwards whose losses are summed before one backward: the second forward must not replay
+    the chunk slots the first one still needs for its backward; gradients equal the eager field's."""
+    from nsvf_b200.field import GraphedField
+    torch.manual_seed(2)
+    eager = RadianceField(sigma_bias=0.1).to(cuda).train()
+    graphed = GraphedField(RadianceField().to(cuda), rows=2048, slots=2).train()
+    graphed.field.load_state_dict(eager.state_dict())
+    gen = torch.Generator(device=cuda).manual_seed(3)
+    data = [((torch.randn(2048, 32, device=cuda, generator=gen) * 0.2), F.normalize(torch.randn(2048, 3, device=cuda, generator=gen), dim=-1),
+             torch.randn(2048, 4, device=cuda, generator=gen)) for _ in range(2)]
+    grads = []
+    for f in (eager, graphed):
+        f.zero_grad(set_to_none=True)
+        total = 0
+        for emb, ray, w in data:               # forward A, forward B, then ONE backward
+            if hasattr(f, "begin_step"):
+                f.begin_step()
+            o = f({"emb": emb.clone().requires_grad_(True), "ray": ray})
+            total = total + (o["sigma"] * w[:, 0]).sum() + (o["texture"] * w[:, 1:]).sum()
+        total.backward()
+        inner = getattr(f, "field", f)
+        grads.append({k: p.grad.clone() for k, p in inner.named_parameters() if p.grad is not None})
+    assert graphed.graph_replays == 1, "the second forward must have run eagerly (slot 0 was still pending)"
+    for k in grads[0]:
+        helpers.assert_close_scaled(grads[1][k], grads[0][k], rtol=1e-5, what=k)
+    graphed.begin_step()                       # after the backward the slots are free again
+    o = graphed({"emb": data[0][0].clone().requires_grad_(True), "ray": data[0][1]})
+    assert graphed.graph_replays == 2
