@@ -126,6 +126,23 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------------
+# allocator pre-sizing
+# ------------------------------------------------------------------------------------------------------
+def presize_allocator(dev, large_gib=12, small_mib=1024):
+    """Fill torch's caching allocator BEFORE the NCCL communicator exists, so that no step ever calls cudaMalloc.
+
+    Measured on 2-GPU boxes (profiles/r2_multirank_stall.md): once several processes share the box with peer access
+    enabled, ONE cudaMalloc takes 40 - 100 ms (1 ms in a single process), and it is device-synchronising — a step that
+    needs a new 2 MiB small-pool segment stalls, and through the gradient all-reduce every rank stalls with it.  That
+    is the multi-rank "stall" of round 1 (0.2 - 12 s at 8 ranks).  The large pool is served by one big block that the
+    allocator splits on demand; the small pool (tensors < 1 MiB: ray offsets, per-ray state, scalars) cannot use that
+    block, so it gets its own segments."""
+    big = torch.empty(large_gib << 30, dtype=torch.uint8, device=dev)
+    small = [torch.empty(512 << 10, dtype=torch.uint8, device=dev) for _ in range(small_mib * 2)]
+    del big, small
+
+
+# ------------------------------------------------------------------------------------------------------
 # synthetic inputs
 # ------------------------------------------------------------------------------------------------------
 def make_batches(n_batches, rank, pinned):
@@ -181,12 +198,19 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device: there is no CPU fallback"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
     pipe, scene = build_model(dev, graphs=not args.no_graphs)
     if hasattr(pipe.field, "capture"):
         pipe.field.capture(dev)          # CUDA graphs of the field's chunk forward / backward, before any eager pass
+    # order matters: graph capture empties the allocator's cache (torch.cuda.graph.__enter__ calls empty_cache), and a
+    # cudaMalloc costs 40 - 100 ms once the NCCL communicator has mapped the peers — so: capture, pre-size, then NCCL
+    t_pre = time.perf_counter()
+    presize_allocator(dev)
+    torch.cuda.synchronize()
+    t_pre = time.perf_counter() - t_pre
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if os.environ.get("NSVF_BENCH_TRACE"):
+        print("rank %d: allocator pre-sized in %.2f s" % (rank, t_pre), file=sys.stderr, flush=True)
     model = pipe
     params = [p for p in pipe.parameters() if p.requires_grad]
     opt = torch.optim.Adam(params, lr=1e-3, betas=(0.9, 0.999))
@@ -229,7 +253,15 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t_host0 = time.perf_counter()
+        trace = os.environ.get("NSVF_BENCH_TRACE")
+        if trace:
+            import faulthandler
+            tb = open(os.path.join(ROOT, "gpurun_out", "bench_stall_rank%d.txt" % rank), "a")
+        t_prev = t_host0
         for i in range(n):
+            if trace:      # stall hunt: dump the Python stack of a step that takes > 90 ms, and count cudaMallocs
+                faulthandler.dump_traceback_later(0.09, exit=False, file=tb)
+                m0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); b.record()                                    # materialise the cudaEvent_t handles
             _lib.check(L.nsvf_profile_kernel(kname, a.cuda_event, b.cuda_event))
@@ -242,9 +274,17 @@ def run_ours(args):
             else:
                 loss, out = step(*resident[i % len(resident)])
             k_evs.append((a, b))
-            if os.environ.get("NSVF_BENCH_TRACE"):
-                print("rank %d step %d from_host=%s: host %.2f ms since loop start" %
-                      (rank, i, from_host, (time.perf_counter() - t_host0) * 1e3), file=sys.stderr, flush=True)
+            if trace:
+                faulthandler.cancel_dump_traceback_later()
+                now = time.perf_counter()
+                ms_ = torch.cuda.memory_stats(dev)
+                print("rank %d step %d from_host=%s: host %.2f ms (+%d cudaMalloc) segs small %d large %d reserved %d MiB "
+                      "peak-allocated %d MiB" %
+                      (rank, i, from_host, (now - t_prev) * 1e3, ms_.get("num_device_alloc", 0) - m0,
+                       ms_.get("segment.small_pool.current", 0), ms_.get("segment.large_pool.current", 0),
+                       ms_.get("reserved_bytes.all.current", 0) >> 20, ms_.get("allocated_bytes.all.peak", 0) >> 20),
+                      file=sys.stderr, flush=True)
+                t_prev = now
         e1.record()
         host_ms[0] = (time.perf_counter() - t_host0) * 1e3 / n      # host time to ENQUEUE a step (no sync)
         barrier()
@@ -272,11 +312,6 @@ def run_ours(args):
         torch.cuda.synchronize()
     except Exception as e:      # warm-up only: never fatal
         print("shape warm-up skipped: %r" % (e,), file=sys.stderr)
-    # pre-size the caching allocator: one 12 GiB block, freed back to torch's cache, is split to serve the step's
-    # variable-size requests, so no step after warm-up has to call cudaMalloc (slow and device-synchronising, and much
-    # slower once NCCL has enabled peer access between the GPUs of the box — the suspected cause of the multi-rank stall described below)
-    _reserve = torch.empty(12 << 30, dtype=torch.uint8, device=dev)
-    del _reserve
     import gc
     gc.collect()
     gc.freeze()          # everything built so far is permanent: keeps full collections out of the timed steps
@@ -883,6 +918,7 @@ def _dist_setup():
     assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device: there is no CPU fallback"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    presize_allocator(dev, large_gib=48)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     return dist, world, rank, local, dev

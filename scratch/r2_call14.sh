@@ -1,4 +1,5 @@
 #!/bin/bash
+timeout 600 python -m pytest tests/test_intersect_gpu.py -m gpu -x -q 2>&1 | tail -3
 for rep in 1 2 3; do
   for env in LAZY EAGER; do
     echo "== CUDA_MODULE_LOADING=$env rep $rep"

@@ -34,6 +34,8 @@ for i in range(8):
 torch.cuda.synchronize()
 if world > 1: dist.barrier()
 slow = []
+import faulthandler
+tb_file = open(os.path.join(ROOT, "gpurun_out", "r2_stall_tb_rank%d.txt" % rank), "a")
 def cgstat():
     for f in ("/sys/fs/cgroup/cpu.stat", "/sys/fs/cgroup/cpu/cpu.stat"):
         try:
@@ -50,6 +52,8 @@ if rank == 0:
 evs = []
 t_all0 = time.perf_counter()
 for i in range(80):
+    faulthandler.dump_traceback_later(0.08, exit=False, file=tb_file)
+    m0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     t0 = time.perf_counter(); c0 = time.process_time()
     ea, eb, ec = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     ea.record()
@@ -69,7 +73,9 @@ for i in range(80):
     else:
         loss.item()
     t3 = time.perf_counter()
+    faulthandler.cancel_dump_traceback_later()
     if (t3 - t0) > 0.06:
+        slow.append("mallocs +%d" % (torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - m0))
         torch.cuda.synchronize()
         slow.append("step %d: total %.0f ms = copies %.1f + enqueue %.1f + wait %.1f | cpu time of main thread+children %.0f ms | GPU: copies %.1f ms, step %.1f ms" % (
             i, (t3 - t0) * 1e3, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (time.process_time() - c0) * 1e3, ea.elapsed_time(eb), eb.elapsed_time(ec)))
