@@ -509,45 +509,84 @@ def _time(fn, n=5, warm=2):
     return round(e0.elapsed_time(e1) / n, 4)
 
 
-def roofline_at_scale(dev, peak):
-    """The HBM-bound kernels at full-frame sizes (C3 scene, 40 M samples / 262144 x 256 rays x samples), timed with
-    CUDA events around the C-ABI calls.  Algorithmic bytes per unit are SURVEY.md §8d's figures."""
+def real_sample_stream(dev, scene_name="C3", columns=64):
+    """Ray-marched samples of an 800x800 view of the scene in ray-major order (what a training step's wide windows hand
+    to the interpolation): intersect -> inverse-CDF sampling -> compaction of the first `columns` sample columns."""
     from nsvf_b200 import synthetic, _lib
+    from nsvf_b200.encoder import SparseVoxelEncoder
     L, p = _lib.load(), _lib.ptr
-    scene = synthetic.make_scene("C3")
-    pts = torch.from_numpy(scene.points).to(dev)
-    feats = torch.from_numpy(scene.feats).int().to(dev)
-    values = torch.from_numpy(scene.values).to(dev)
-    M = 40_000_000
-    g = torch.Generator(device=dev).manual_seed(0)
-    vox = torch.randint(0, scene.n, (M // 6 + 1,), device=dev, generator=g).repeat_interleave(6)[:M].int().contiguous()
-    xyz = (pts[vox.long()] + (torch.rand(M, 3, device=dev, generator=g) - 0.5) * scene.voxel_size).contiguous()
+    scene = synthetic.make_scene(scene_name)
+    enc = SparseVoxelEncoder(scene.points, scene.voxel_size, max_hits=scene.max_hits).to(dev).eval()
+    rs, rd = synthetic.camera_rays(RES, RES, 1, radius=4.5, seed=7, device=dev)
+    rs, rd = rs[None, :, None, 0, :].contiguous(), rd[None].contiguous()
+    with torch.no_grad():
+        st = enc.precompute(id=torch.zeros(1, dtype=torch.long, device=dev))
+        rs_f, rd_f, inter, hits = enc.ray_intersect(rs, rd, st)
+        sel = hits.reshape(-1).nonzero(as_tuple=True)[0]
+        inter = {k: v.reshape(-1, v.size(-1)).index_select(0, sel) for k, v in inter.items()}
+        dists = (inter["max_depth"] - inter["min_depth"]).masked_fill(inter["intersected_voxel_idx"].eq(-1), 0)
+        inter["probs"] = dists / dists.sum(-1, keepdim=True)
+        inter["steps"] = dists.sum(-1) / enc.step_size
+        smp = enc.ray_sample(inter, trimmed=True)
+        sidx, sdep, lens = smp["sampled_point_voxel_idx"], smp["sampled_point_depth"], smp["sampled_point_count"]
+        K = min(columns, sidx.shape[1])
+        mask = torch.arange(K, device=dev)[None] < lens[:, None]
+        o = rs_f.reshape(-1, 3).index_select(0, sel)
+        d = rd_f.reshape(-1, 3).index_select(0, sel)
+        vox = sidx[:, :K][mask].contiguous()
+        xyz = (o[:, None] + d[:, None] * sdep[:, :K, None])[mask].contiguous()
+    feats = enc._kept_geometry()[1]
+    pts = st["voxel_center_xyz"].reshape(-1, 3).contiguous()
+    values = st["voxel_vertex_emb"].reshape(-1, 32).detach().contiguous()
+    runs = int((vox[1:] != vox[:-1]).sum()) + 1
+    return scene, vox, xyz, feats, pts, values, runs
+
+
+def roofline_at_scale(dev, peak):
+    """The HBM-bound kernels at full-frame sizes, timed with CUDA events around the C-ABI calls on the REAL sample stream
+    of the C3 scene (ray-marched, ray-major: ~8 consecutive samples per voxel, face-adjacent voxel transitions) and,
+    for comparison, on round 1's synthetic stream (an independent random voxel every 6 samples).  Algorithmic bytes per
+    unit are SURVEY.md §8d's figures."""
+    from nsvf_b200 import _lib
+    L, p = _lib.load(), _lib.ptr
+    scene, vox, xyz, feats, pts, values, runs = real_sample_stream(dev)
+    M = vox.numel()
     out = torch.empty(M, 32, device=dev)
     gv = torch.zeros_like(values)
     st = torch.cuda.current_stream().cuda_stream
-    res = {}
+    res = {"stream": "C3 scene, 800x800 view, first 64 sample columns in ray-major order: %d samples, %.1f samples per "
+                     "voxel run" % (M, M / runs)}
 
     def rec(name, fn, nbytes):
         ms = _time(fn, n=5, warm=2)
         res[name] = {"ms": ms, "achieved_GBs": round(nbytes / ms / 1e6, 1), "frac": round(nbytes / ms / 1e6 / peak, 4),
                      "algorithmic_bytes": nbytes}
-    rec("trilinear_fwd (40M samples, 144 B/sample)",
+    rec("trilinear_fwd (real stream, 144 B/sample)",
         lambda: L.nsvf_trilinear_embed_fwd(st, M, 32, p(vox), p(xyz), p(feats), p(pts), p(values), scene.voxel_size, p(out)),
         M * 144)
-    rec("trilinear_bwd (40M samples, 144 B/sample)",
+    rec("trilinear_bwd (real stream, 144 B/sample)",
         lambda: L.nsvf_trilinear_embed_bwd(st, M, 32, p(vox), p(xyz), p(feats), p(pts), p(values), scene.voxel_size,
                                            p(out), p(gv), None), M * 144)
-    del out, xyz, vox
+    g = torch.Generator(device=dev).manual_seed(0)
+    vox2 = torch.randint(0, scene.n, (M // 6 + 1,), device=dev, generator=g).repeat_interleave(6)[:M].int().contiguous()
+    xyz2 = (pts[vox2.long()] + (torch.rand(M, 3, device=dev, generator=g) - 0.5) * scene.voxel_size).contiguous()
+    rec("trilinear_fwd (synthetic stream of round 1)",
+        lambda: L.nsvf_trilinear_embed_fwd(st, M, 32, p(vox2), p(xyz2), p(feats), p(pts), p(values), scene.voxel_size, p(out)),
+        M * 144)
+    rec("trilinear_bwd (synthetic stream of round 1)",
+        lambda: L.nsvf_trilinear_embed_bwd(st, M, 32, p(vox2), p(xyz2), p(feats), p(pts), p(values), scene.voxel_size,
+                                           p(out), p(gv), None), M * 144)
+    del out, xyz, vox, xyz2, vox2
     B, K = 262144, 256
     fe = torch.rand(B, K, device=dev) * 0.1
     tex = torch.rand(B, K, 3, device=dev)
     dep = torch.rand(B, K, device=dev)
     probs, od, om, oc = (torch.empty(B, K, device=dev), torch.empty(B, device=dev), torch.empty(B, device=dev),
                          torch.empty(B, 3, device=dev))
-    rec("composite_fwd (262144 x 256, 28 B/sample)",
+    rec("composite_fwd (dense rows, 262144 x 256, 28 B/sample)",
         lambda: L.nsvf_composite_fwd(st, B, K, p(fe), p(tex), p(dep), p(probs), p(od), p(om), p(oc)), B * K * 28 + B * 20)
     gfe, gtex = torch.empty(B, K, device=dev), torch.empty(B, K, 3, device=dev)
-    rec("composite_bwd (262144 x 256, 36 B/sample)",
+    rec("composite_bwd (dense rows, 262144 x 256, 36 B/sample)",
         lambda: L.nsvf_composite_bwd(st, B, K, p(fe), p(tex), p(dep), None, p(od), p(om), p(oc), p(gfe), p(gtex)),
         B * K * 36 + B * 20)
     return res

@@ -156,11 +156,15 @@ NSVF_API int nsvf_inverse_cdf_sampling_ex(nsvf_stream_t stream, int b, int num_r
                                           float* sampled_dists, int* max_count, int* ray_len, int* holes_flag,
                                           float pad_depth, int flags);
 
-/* Replaces uniform_ray_sampling, fairnr/clib/src/sample.cpp:23-55 + sample_gpu.cu:15-106. */
+/* Replaces uniform_ray_sampling, fairnr/clib/src/sample.cpp:23-55 + sample_gpu.cu:15-106, and the trimming glue of
+ * UniformRaySampling.forward, fairnr/clib/__init__.py:178-228.  Same layouts as above ([b, num_rays, max_hits] bins,
+ * noise / outputs [b, num_rays, max_steps]); outputs fully written: beyond a ray's samples idx -1, depth 0, dists 0
+ * (the reference leaves stale values of its in-place merge there).  max_count i32 [1] (optional, zero it first) is
+ * atomicMax'ed with the largest number of samples of any ray — the wrapper's max_len (:214). */
 NSVF_API int nsvf_uniform_ray_sampling(nsvf_stream_t stream, int b, int num_rays, int max_hits, int max_steps,
                               float step_size, const int* pts_idx, const float* min_depth, const float* max_depth,
                               const float* uniform_noise, int* sampled_idx, float* sampled_depth,
-                              float* sampled_dists);
+                              float* sampled_dists, int* max_count);
 
 /* ---- octree construction (HOST pointers, CPU) ---------------------------------------------------------
  * Replaces build_octree, fairnr/clib/src/octree.cpp:125-135.  Two calls on the same thread:

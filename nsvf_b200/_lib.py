@@ -55,7 +55,7 @@ SIGNATURES = {
     "nsvf_march_epilogue_bwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_int] + [c_void_p] * 8),
     "nsvf_march_composite_fwd": (c_int, [c_void_p, c_ll, c_int] + [c_void_p] * 13 + [c_ll, c_float, c_int]),
     "nsvf_march_composite_bwd": (c_int, [c_void_p, c_ll, c_int] + [c_void_p] * 11),
-    "nsvf_uniform_ray_sampling": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float] + [c_void_p] * 7),
+    "nsvf_uniform_ray_sampling": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float] + [c_void_p] * 8),
     "nsvf_octree_build": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p]),
     "nsvf_octree_flatten": (c_int, [c_void_p, c_void_p, c_ll]),
     "nsvf_trilinear_embed_fwd": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

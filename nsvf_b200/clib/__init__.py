@@ -73,42 +73,36 @@ svo_ray_intersect = SparseVoxelOctreeRayIntersect.apply
 
 
 class UniformRaySampling(Function):
+    """fairnr/clib/__init__.py:178-228.  The reference pads the rays to a multiple of 256 (wrapping), tiles them
+    [256, R, P], runs its kernel and trims to the longest ray with a full-tensor reduction; our kernel takes the [N, P]
+    rays as they are and reports the longest ray itself.  RNG contract kept: the noise is drawn with the numel and flat
+    order of the reference's padded [256, R, max_steps] tensor, the first N rows are used."""
+
     @staticmethod
     def forward(ctx, pts_idx, min_depth, max_depth, step_size, max_ray_length, deterministic=False):
-        # same tiling as the reference (the kernel's umin == 0 quirk reads the previous ray's row)
-        G, N, P = 256, pts_idx.size(0), pts_idx.size(1)
-        H = int(np.ceil(N / G)) * G
-        if H > N:
-            pts_idx = torch.cat([pts_idx, pts_idx[:H - N]], 0)
-            min_depth = torch.cat([min_depth, min_depth[:H - N]], 0)
-            max_depth = torch.cat([max_depth, max_depth[:H - N]], 0)
-        pts_idx = pts_idx.reshape(G, -1, P)
-        min_depth = min_depth.reshape(G, -1, P)
-        max_depth = max_depth.reshape(G, -1, P)
-
-        max_steps = int(max_ray_length / step_size)
-        max_steps = max_steps + min_depth.size(-1) * 2
-        noise = min_depth.new_zeros(*min_depth.size()[:-1], max_steps)
+        N, P = pts_idx.size(0), pts_idx.size(1)
+        dev = pts_idx.device
+        step_size = float(step_size)
+        max_steps = int(max_ray_length / step_size) + P * 2
         if deterministic:
-            noise += 0.5
+            noise = min_depth.new_full((N, max_steps), 0.5, dtype=torch.float32)
         else:
-            noise = noise.uniform_()
-
-        sampled_idx, sampled_depth, sampled_dists = _ext.uniform_ray_sampling(
-            pts_idx.int().contiguous(), min_depth.float().contiguous(), max_depth.float().contiguous(),
-            noise.float(), step_size, max_steps)
-        sampled_depth = sampled_depth.type_as(min_depth)
-        sampled_dists = sampled_dists.type_as(min_depth)
-
-        sampled_idx = sampled_idx.reshape(H, -1)[:N]
-        sampled_depth = sampled_depth.reshape(H, -1)[:N]
-        sampled_dists = sampled_dists.reshape(H, -1)[:N]
-
-        max_len = sampled_idx.ne(-1).sum(-1).max()
+            H = int(np.ceil(N / 256)) * 256
+            noise = min_depth.new_zeros(H, max_steps, dtype=torch.float32).uniform_()[:N]
+        idx32 = pts_idx.int().contiguous()
+        dmin, dmax = min_depth.float().contiguous(), max_depth.float().contiguous()
+        sampled_idx = torch.empty((N, max_steps), dtype=torch.int32, device=dev)
+        sampled_depth = torch.empty((N, max_steps), dtype=torch.float32, device=dev)
+        sampled_dists = torch.empty((N, max_steps), dtype=torch.float32, device=dev)
+        max_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_L.nsvf_uniform_ray_sampling(
+                _lib.current_stream(dev), 1, N, P, max_steps, step_size, _p(idx32), _p(dmin), _p(dmax), _p(noise),
+                _p(sampled_idx), _p(sampled_depth), _p(sampled_dists), _p(max_count)))
+        max_len = int(max_count.item())
         sampled_idx = sampled_idx[:, :max_len]
-        sampled_depth = sampled_depth[:, :max_len]
-        sampled_dists = sampled_dists[:, :max_len]
-
+        sampled_depth = sampled_depth[:, :max_len].type_as(min_depth)
+        sampled_dists = sampled_dists[:, :max_len].type_as(min_depth)
         ctx.mark_non_differentiable(sampled_idx)
         ctx.mark_non_differentiable(sampled_depth)
         ctx.mark_non_differentiable(sampled_dists)

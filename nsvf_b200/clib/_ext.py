@@ -192,7 +192,7 @@ def uniform_ray_sampling(pts_idx, min_depth, max_depth, uniform_noise, step_size
     with torch.cuda.device(dev):
         _lib.check(_L.nsvf_uniform_ray_sampling(
             _lib.current_stream(dev), g, r, p, max_steps, step_size, _p(pts_idx), _p(min_depth), _p(max_depth),
-            _p(uniform_noise), _p(sidx), _p(sdepth), _p(sdists)))
+            _p(uniform_noise), _p(sidx), _p(sdepth), _p(sdists), None))
     return sidx, sdepth, sdists
 
 

@@ -467,71 +467,149 @@ inverse_cdf_warp_kernel(int b, int num_rays, long long valid_rays, int ray_chunk
   if (max_count != nullptr && lane == 0 && my_max > 0) atomicMax(max_count, my_max);
 }
 
-// Faithful restatement of the two-phase uniform sampler (dead code in the live model path: no caller
-// in fairnr/modules/encoder.py). One thread per ray, in-place in global memory like the reference;
-// the kernel pre-fills its own row (idx -1, depth 0, dists 0) instead of relying on host fills.
-__global__ void uniform_ray_sampling_kernel(long long total_rays, int max_hits, int max_steps, float step_size,
-                                            const int* __restrict__ pts_idx, const float* __restrict__ min_depth,
-                                            const float* __restrict__ max_depth, const float* __restrict__ noise,
-                                            int* sampled_idx, float* sampled_depth, float* sampled_dists) {
-  const long long total_hits = total_rays * max_hits;
-  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < total_rays;
-       j += (long long)gridDim.x * blockDim.x) {
-    const long long H = j * max_hits, K = j * max_steps;
-    for (int t = 0; t < max_steps; ++t) {
-      sampled_idx[K + t] = -1;
-      sampled_depth[K + t] = 0.0f;
-      sampled_dists[K + t] = 0.0f;
+// ---- uniform ray sampling -----------------------------------------------------------------------------------------
+// Replaces uniform_ray_sampling_kernel, fairnr/clib/src/sample_gpu.cu:15-106.  The reference runs two passes per ray
+// IN PLACE in global memory: (1) a three-way merge of voxel entries, voxel exits and march points into the output row,
+// (2) a sweep over adjacent pairs of that row that turns them into mid-points / lengths, keeps the pairs lying inside
+// a voxel and compacts them to the front — every row is written, re-read and re-written with a stride of
+// 4 * max_steps bytes between the threads of a warp.
+// Here the two passes are ONE streaming state machine: pass 2 only ever looks at the previous merge point, so each new
+// merge point is paired with its predecessor on the spot and the kept sample is emitted directly; the un-compacted
+// row never exists.  A lane owns a ray, the warp stages its 32 x TS samples in shared memory and flushes them with
+// coalesced stores (TS consecutive slots of 32/TS rays per instruction), and the kernel writes the padding itself.
+// What is defined differently from the reference: slots beyond a ray's samples hold
+// (idx -1, depth 0, dists 0) instead of stale merge values; reads before the first / past the last element of
+// pts_idx yield -1.
+struct UniState {
+  int s, ucur, umin, umax;        // merge: points produced, march index, next entry, next exit
+  int umin2, umax2;               // pair sweep: entries / exits passed (reference phase 2 counters)
+  int prev_idx;                   // voxel id attached to the previous merge point
+  float prev_depth, base;         // previous merge point, min_depth of the first bin
+  bool done;
+};
+
+// Produces at most one kept sample per call; false = the ray is finished.
+__device__ __forceinline__ bool uni_next(UniState& st, int P, int max_steps, float step_size, long long H,
+                                         long long total_hits, const int* __restrict__ pts_idx,
+                                         const float* __restrict__ min_depth, const float* __restrict__ max_depth,
+                                         const float* __restrict__ noise_row, int& o_idx, float& o_depth,
+                                         float& o_dist) {
+  while (!st.done) {
+    // ---- next merge point (reference :47-81) ----
+    if (st.umax == P || st.ucur == max_steps || st.s >= max_steps || __ldg(pts_idx + H + st.umax) == -1) break;
+    const float last_min = st.umin < P ? __ldg(min_depth + H + st.umin) : 10000.0f;
+    const float last_max = __ldg(max_depth + H + st.umax);
+    const float curr = __fmaf_rn(__fadd_rn((float)st.ucur, __ldg(noise_row + st.ucur)), step_size, st.base);
+    float d;
+    int id;
+    if (last_max <= curr && last_max <= last_min) {
+      d = last_max; id = __ldg(pts_idx + H + st.umax); st.umax++;
+    } else if (curr <= last_min && curr <= last_max) {
+      const long long f = H + st.umin - 1;     // umin == 0: the previous ray's last slot (reference quirk)
+      d = curr; id = (f >= 0 && f < total_hits) ? __ldg(pts_idx + f) : -1; st.ucur++;
+    } else if (last_min <= curr && last_min <= last_max) {
+      d = last_min; id = st.umin < P ? __ldg(pts_idx + H + st.umin) : -1; st.umin++;
+    } else {
+      break;                                    // NaN inputs: the reference would spin forever
     }
-    int s = 0, ucur = 0, umin = 0, umax = 0;
-    float last_min_depth = 0.f, last_max_depth = 0.f, curr_depth = 0.f;
-    // merge voxel entries, voxel exits and march points (reference :47-81)
-    for (;;) {
-      if (umax == max_hits || ucur == max_steps || pts_idx[H + umax] == -1) break;
-      last_min_depth = umin < max_hits ? min_depth[H + umin] : 10000.0f;
-      last_max_depth = umax < max_hits ? max_depth[H + umax] : 10000.0f;
-      if (ucur < max_steps)
-        curr_depth = __fmaf_rn(__fadd_rn((float)ucur, noise[K + ucur]), step_size, min_depth[H]);
-      if (s >= max_steps) break;  // reference would write past the row
-      if (last_max_depth <= curr_depth && last_max_depth <= last_min_depth) {
-        sampled_depth[K + s] = last_max_depth;
-        sampled_idx[K + s] = pts_idx[H + umax];
-        umax++; s++; continue;
-      }
-      if (curr_depth <= last_min_depth && curr_depth <= last_max_depth) {
-        sampled_depth[K + s] = curr_depth;
-        // reference reads pts_idx[H + umin - 1]; with umin == 0 that is the previous ray's last slot
-        const long long f = H + umin - 1;
-        sampled_idx[K + s] = (f >= 0 && f < total_hits) ? pts_idx[f] : -1;
-        ucur++; s++; continue;
-      }
-      if (last_min_depth <= curr_depth && last_min_depth <= last_max_depth) {
-        sampled_depth[K + s] = last_min_depth;
-        sampled_idx[K + s] = umin < max_hits ? pts_idx[H + umin] : -1;
-        umin++; s++; continue;
-      }
-      break;  // NaN inputs: the reference would spin forever
+    const int pos = st.s++;
+    if (pos == 0) { st.prev_depth = d; st.prev_idx = id; continue; }
+    // ---- pair (pos - 1, pos): reference phase 2 (:83-100), iteration ucur = pos - 1 ----
+    if (id == -1) break;                        // sampled_idx[ucur + 1] == -1
+    const float l = st.prev_depth, mid = __fmul_rn(__fadd_rn(l, d), 0.5f), len = __fsub_rn(d, l);
+    const int left_idx = st.prev_idx;
+    st.prev_depth = d;
+    st.prev_idx = id;
+    if (st.umin2 < P && mid >= __ldg(min_depth + H + st.umin2) && __ldg(pts_idx + H + st.umin2) > -1) st.umin2++;
+    if (st.umax2 < P && mid >= __ldg(max_depth + H + st.umax2) && __ldg(pts_idx + H + st.umax2) > -1) st.umax2++;
+    if (st.umax2 == P || __ldg(pts_idx + H + st.umax2) == -1) break;
+    if (st.umin2 - 1 == st.umax2 && len > 0.f) {
+      o_idx = left_idx; o_depth = mid; o_dist = len;
+      return true;
     }
-    // mid-points, distances, in-voxel filter, compaction (reference :83-100)
-    int step = 0;
-    umin = 0; umax = 0;
-    for (ucur = 0; ucur < max_steps - 1; ucur++) {
-      if (sampled_idx[K + ucur + 1] == -1) break;
-      const float l_depth = sampled_depth[K + ucur];
-      const float r_depth = sampled_depth[K + ucur + 1];
-      sampled_depth[K + ucur] = __fmul_rn(__fadd_rn(l_depth, r_depth), 0.5f);
-      sampled_dists[K + ucur] = __fsub_rn(r_depth, l_depth);
-      if (umin < max_hits && sampled_depth[K + ucur] >= min_depth[H + umin] && pts_idx[H + umin] > -1) umin++;
-      if (umax < max_hits && sampled_depth[K + ucur] >= max_depth[H + umax] && pts_idx[H + umax] > -1) umax++;
-      if (umax == max_hits || pts_idx[H + umax] == -1) break;
-      if (umin - 1 == umax && sampled_dists[K + ucur] > 0) {
-        sampled_depth[K + step] = sampled_depth[K + ucur];
-        sampled_dists[K + step] = sampled_dists[K + ucur];
-        sampled_idx[K + step] = sampled_idx[K + ucur];
-        step++;
+  }
+  st.done = true;
+  return false;
+}
+
+template <int TS>
+__global__ void __launch_bounds__(kSampWarps * 32)
+uniform_sampling_kernel(long long total_rays, int P, int max_steps, float step_size, const int* __restrict__ pts_idx,
+                        const float* __restrict__ min_depth, const float* __restrict__ max_depth,
+                        const float* __restrict__ noise, int* __restrict__ sampled_idx,
+                        float* __restrict__ sampled_depth, float* __restrict__ sampled_dists,
+                        int* __restrict__ max_count) {
+  constexpr int LD = TS + 1;
+  __shared__ int t_idx[kSampWarps][32 * LD];
+  __shared__ float t_depth[kSampWarps][32 * LD];
+  __shared__ float t_dist[kSampWarps][32 * LD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long total_hits = total_rays * P;
+  const long long n_groups = (total_rays + 31) / 32;
+  int my_max = 0;
+  for (long long g = (long long)blockIdx.x * kSampWarps + warp; g < n_groups; g += (long long)gridDim.x * kSampWarps) {
+    const long long ray = g * 32 + lane;
+    const long long H = ray * P;
+    UniState st;
+    st.s = st.ucur = st.umin = st.umax = st.umin2 = st.umax2 = 0;
+    st.prev_idx = -1;
+    st.prev_depth = 0.f;
+    st.done = ray >= total_rays;
+    st.base = st.done ? 0.f : __ldg(min_depth + H);
+    const float* noise_row = noise + ray * max_steps;
+    const long long out_base = g * 32 * (long long)max_steps;
+    const int rows = (int)min((long long)32, total_rays - g * 32);
+    int n_valid = 0;
+    for (int t0 = 0; t0 < max_steps; t0 += TS) {
+      const int tw = min(TS, max_steps - t0);
+      int c = 0;
+      while (c < tw) {
+        int oi; float oz, od;
+        if (!uni_next(st, P, max_steps, step_size, H, total_hits, pts_idx, min_depth, max_depth, noise_row, oi, oz, od))
+          break;
+        t_idx[warp][lane * LD + c] = oi;
+        t_depth[warp][lane * LD + c] = oz;
+        t_dist[warp][lane * LD + c] = od;
+        n_valid += (oi != -1);
+        ++c;
+      }
+      for (; c < tw; ++c) {
+        t_idx[warp][lane * LD + c] = -1;
+        t_depth[warp][lane * LD + c] = 0.0f;
+        t_dist[warp][lane * LD + c] = 0.0f;
+      }
+      __syncwarp();
+      constexpr int RPI = 32 / TS;       // rows per store instruction
+      const int cc = lane % TS, rsub = lane / TS;
+      for (int r = 0; r < rows; r += RPI) {
+        const int rr = r + rsub;
+        if (rr < rows && cc < tw) {
+          const long long o = out_base + (long long)rr * max_steps + t0 + cc;
+          sampled_idx[o] = t_idx[warp][rr * LD + cc];
+          sampled_depth[o] = t_depth[warp][rr * LD + cc];
+          sampled_dists[o] = t_dist[warp][rr * LD + cc];
+        }
+      }
+      __syncwarp();
+      if (__all_sync(NSVF_FULL_MASK, st.done)) {   // every ray of the warp finished: the rest is padding
+        const int tnext = t0 + TS;
+        for (int r = 0; r < rows && tnext < max_steps; ++r) {
+          const long long o = out_base + (long long)r * max_steps + tnext;
+          for (int k = lane; k < max_steps - tnext; k += 32) {
+            sampled_idx[o + k] = -1;
+            sampled_depth[o + k] = 0.0f;
+            sampled_dists[o + k] = 0.0f;
+          }
+        }
+        break;
       }
     }
-    for (int t = step; t < max_steps; t++) sampled_idx[K + t] = -1;
+    my_max = max(my_max, n_valid);
+  }
+  if (max_count != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_max = max(my_max, __shfl_xor_sync(NSVF_FULL_MASK, my_max, o));
+    if (lane == 0 && my_max > 0) atomicMax(max_count, my_max);
   }
 }
 
@@ -596,18 +674,18 @@ extern "C" int nsvf_inverse_cdf_sampling(nsvf_stream_t stream, int b, int num_ra
 extern "C" int nsvf_uniform_ray_sampling(nsvf_stream_t stream_, int b, int num_rays, int max_hits, int max_steps,
                                          float step_size, const int* pts_idx, const float* min_depth,
                                          const float* max_depth, const float* uniform_noise, int* sampled_idx,
-                                         float* sampled_depth, float* sampled_dists) {
+                                         float* sampled_depth, float* sampled_dists, int* max_count) {
   cudaStream_t stream = (cudaStream_t)stream_;
   NSVF_REQUIRE(b >= 0 && num_rays >= 0 && max_hits >= 0 && max_steps >= 0, "uniform_ray_sampling: negative size");
   if (b == 0 || num_rays == 0 || max_steps == 0) return 0;
   NSVF_REQUIRE(max_hits > 0, "uniform_ray_sampling: max_hits must be > 0");
   const long long total_rays = (long long)b * num_rays;
-  long long want = (total_rays + 127) / 128;
-  long long cap = (long long)num_sms() * 16;
+  const long long groups = (total_rays + 31) / 32;
+  long long want = (groups + kSampWarps - 1) / kSampWarps, cap = (long long)num_sms() * 8;
   int grid = (int)(want < cap ? want : cap);
-  uniform_ray_sampling_kernel<<<grid, 128, 0, stream>>>(total_rays, max_hits, max_steps, step_size, pts_idx,
-                                                        min_depth, max_depth, uniform_noise, sampled_idx,
-                                                        sampled_depth, sampled_dists);
-  NSVF_LAUNCH_OK("uniform_ray_sampling_kernel");
+  NSVF_TIMED_LAUNCH("uniform_sampling_kernel", stream,
+                    (uniform_sampling_kernel<16><<<grid, kSampWarps * 32, 0, stream>>>(
+                        total_rays, max_hits, max_steps, step_size, pts_idx, min_depth, max_depth, uniform_noise,
+                        sampled_idx, sampled_depth, sampled_dists, max_count)));
   return 0;
 }
