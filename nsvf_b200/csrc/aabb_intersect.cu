@@ -485,14 +485,27 @@ aabb_small_kernel(const __grid_constant__ AabbTree tree, long long tree_stride_b
                   int n_max, const float* __restrict__ ray_start, const float* __restrict__ ray_dir,
                   int* __restrict__ out_idx, float* __restrict__ out_min, float* __restrict__ out_max,
                   unsigned char* __restrict__ out_hit) {
-  // stage the exact voxel boxes as 32-byte records {lo.xyz, hi.x | hi.yz, -, -}: one test = two LDS.128 broadcasts
+  // stage the exact voxel boxes as 32-byte records {lo.xyz, hi.x | hi.yz, -, -}: one test = two LDS.128 broadcasts;
+  // behind them the level-1 boxes (union of 8 consecutive voxels, widened by an ulp like every internal node): a ray
+  // first tests the group and scans its 8 voxels only when the group is hit — ~2.4x fewer box tests at 343 voxels
+  // (any-hit over 2.56 M rays: 0.41 -> 0.14 ms), hits still emitted in ascending voxel index.
+  // Measured and rejected for the index-order mode: recording hits as a bit mask and expanding it warp-cooperatively into
+  // coalesced rows (no pre-fill, no scattered stores) — 1.45 ms against 1.30 ms for the scattered stores below; the
+  // expansion's ~170 warp instructions per ray cost more than the partial-sector stores they remove.
   const float* gbox = tree.box + (long long)blockIdx.y * tree_stride_box;
   float4* sbox = reinterpret_cast<float4*>(aabb_smem);
+  const long long st = tree.total;
   for (int k = threadIdx.x; k < n; k += kSmallThreads) {
     const float* g = gbox + k;
-    const long long st = tree.total;
     sbox[2 * k] = make_float4(g[0], g[st], g[2 * st], g[3 * st]);
     sbox[2 * k + 1] = make_float4(g[4 * st], g[5 * st], 0.f, 0.f);
+  }
+  const int n1 = tree.nlevels > 1 ? tree.cnt[1] : 0;
+  float4* sgrp = sbox + 2 * n;
+  for (int k = threadIdx.x; k < n1; k += kSmallThreads) {
+    const float* g = gbox + tree.off[1] + k;
+    sgrp[2 * k] = make_float4(g[0], g[st], g[2 * st], g[3 * st]);
+    sgrp[2 * k + 1] = make_float4(g[4 * st], g[5 * st], 0.f, 0.f);
   }
   __syncthreads();
   const long long ray_base = (long long)blockIdx.y * rays_per_tree;
@@ -519,6 +532,10 @@ aabb_small_kernel(const __grid_constant__ AabbTree tree, long long tree_stride_b
       int cnt = 0;
       const int limit = MODE == kModeAnyHit ? 1 : n_max;
       for (int k = 0; k < n && cnt < limit; ++k) {
+        if (n1 > 0 && (k & 7) == 0) {     // entering a new group of 8: skip it when the ray misses its enclosing box
+          const float4 g0 = sgrp[2 * (k >> 3)], g1 = sgrp[2 * (k >> 3) + 1];
+          if (!slab_enclosing(ox, oy, oz, ix, iy, iz, g0.x, g0.y, g0.z, g0.w, g1.x, g1.y)) { k += 7; continue; }
+        }
         float tn, tf;
         bool hit;
         const float4 q0 = sbox[2 * k], q1 = sbox[2 * k + 1];
@@ -694,7 +711,7 @@ static int aabb_run(cudaStream_t stream, int mode, int b, int n, int m, float vo
   if (gx < 1) gx = 1;
   dim3 grid(gx, n_trees);
   if (n <= kSmallMaxVoxels && mode != kModeDepthSorted && getenv("NSVF_AABB_NO_SMALL") == nullptr) {
-    const size_t sm = (size_t)8 * n * sizeof(float);
+    const size_t sm = (size_t)8 * (n + (n + 7) / 8 + 1) * sizeof(float);
     long long want_s = (rays_per_tree + kSmallThreads - 1) / kSmallThreads, cap_s = (long long)num_sms() * 8;
     if (n_trees > 1) cap_s = (cap_s + n_trees - 1) / n_trees;
     dim3 gs((unsigned)(want_s < cap_s ? want_s : cap_s), n_trees);
