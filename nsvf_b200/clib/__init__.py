@@ -214,6 +214,35 @@ def inverse_cdf_sampling_rows(pts_idx, min_depth, max_depth, probs, steps, fixed
     return sampled_idx, sampled_depth, sampled_dists, ray_len, meta[1:2]
 
 
+@torch.no_grad()
+def inverse_cdf_sampling_lazy(pts_idx, min_depth, max_depth, probs, steps, fixed_step_size=-1, deterministic=False,
+                              pad_depth=MAX_DEPTH):
+    """On-demand sampling for the ray-marching plan: computes only how many samples each ray has (one kernel, no sample
+    tensors) and returns what nsvf_inverse_cdf_block needs to materialise column blocks later, for the rays that are still
+    alive.  Same tiling quirks / RNG draw as InverseCDFRaySampling.  -> dict of row-sliceable tensors + scalars."""
+    G, N, P = 200, pts_idx.size(0), pts_idx.size(1)
+    R = int(np.ceil(N / G))
+    dev = pts_idx.device
+    pts_idx = pts_idx.int().contiguous()
+    min_depth, max_depth = min_depth.float().contiguous(), max_depth.float().contiguous()
+    probs, steps = probs.float().contiguous(), steps.float().contiguous()
+    max_steps = int(steps.ceil().long().max()) + P
+    noise = None if deterministic else min_depth.new_zeros(G, R, max_steps).uniform_().clamp(min=0.001, max=0.999)
+    ray_len = torch.empty(N, dtype=torch.int32, device=dev)
+    quirk = torch.empty((N, 2), dtype=torch.int32, device=dev)
+    meta = torch.zeros(3, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_L.nsvf_inverse_cdf_plan(
+            _lib.current_stream(dev), G, R, N, 4 * G, P, max_steps, float(fixed_step_size), _p(pts_idx), _p(min_depth),
+            _p(max_depth), _p(noise), 0.5, _p(probs), _p(steps), _p(ray_len), _p(quirk), _p(meta)))
+    out = {"sampled_point_count": ray_len, "lazy_quirk": quirk, "lazy_pts_idx": pts_idx, "lazy_min_depth": min_depth,
+           "lazy_max_depth": max_depth, "lazy_probs": probs, "lazy_steps": steps, "lazy_meta": meta,
+           "lazy_max_steps": max_steps, "lazy_fixed_step_size": float(fixed_step_size), "lazy_pad_depth": float(pad_depth)}
+    if noise is not None:
+        out["lazy_noise"] = noise.view(G * R, max_steps)[:N]
+    return out
+
+
 class BallRayIntersect(Function):
     """fairnr/clib/__init__.py:38-55."""
 

@@ -467,6 +467,389 @@ inverse_cdf_warp_kernel(int b, int num_rays, long long valid_rays, int ray_chunk
   if (max_count != nullptr && lane == 0 && my_max > 0) atomicMax(max_count, my_max);
 }
 
+// ---- on-demand inverse-CDF sampling for the ray-marching plan ----------------------------------------------------
+// With early termination most samples the reference emits are never evaluated (C3 frame: 305.9 M emitted, 41.3 M
+// reach the field).  The sampler is a pure function of (bins, noise): in the merge formulation above, step sample i
+// lives at position f(i) = i + b_i with b_i = lower_bound(cum, cdf_i) (cdf_i is non-decreasing in i), and the bin-end
+// sample of bin j at j + c_j with c_j = #{i : b_i <= j} = lower_bound over i of (cdf_i > cum[j]).  So
+//   * inverse_cdf_plan_kernel computes, per ray and in O(bins + log steps), ONLY the number of samples the reference
+//     would emit (ray_len: what the window schedule needs), and
+//   * inverse_cdf_block_kernel materialises the samples of a column block [k0, k1) for the rays that are still alive,
+//     straight into the slot-major planes of the plan (a CTA takes 32 consecutive rays, stages the block in shared
+//     memory and writes 128-byte plane rows) — no row-major sample tensors, no transpose, work ~ evaluated samples.
+// Both are bit-identical to the eager kernels on the samples they produce (tests/test_march_gpu.py).  The two
+// neighbour-ray quirks of the reference's trailing loop are captured per ray by the plan kernel (next_idx0, and the
+// number of valid bins of the block row's ray 0), so the block kernel can work on row slices of the rays.
+struct CdfRay {
+  int nb, total_steps, n_in, b_last, ok, done;
+  float step_size;
+};
+
+__device__ __forceinline__ float cdf_at(int i, const float* __restrict__ noise_row, float noise_const, int max_steps,
+                                        float step_size) {
+  const int ns = i < max_steps ? i : max_steps - 1;
+  const float nz = noise_row != nullptr ? noise_row[ns] : noise_const;
+  return __fmul_rn(__fadd_rn((float)i, nz), step_size);
+}
+__device__ __forceinline__ int bin_of(float cdf, const float* __restrict__ s_cum, int nb) {   // first j with !(cdf > cum[j])
+  int lo = 0, hi = nb;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cdf > s_cum[mid]) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ float z_at(float cdf, int bb, const float* __restrict__ s_cum, const float* __restrict__ s_min,
+                                      const float* __restrict__ s_max) {
+  const float cmin = bb > 0 ? s_cum[bb - 1] : 0.0f, cmax = s_cum[bb];
+  const float u = __fdiv_rn(__fsub_rn(cdf, cmin), __fsub_rn(cmax, cmin));
+  return __fmaf_rn(u, __fsub_rn(s_max[bb], s_min[bb]), s_min[bb]);
+}
+
+// Warp-cooperative: bins of one ray -> shared memory, cumulative sums, step range.  Returns the ray descriptor in all
+// lanes.  s_* are the warp's tables of P entries each.
+__device__ __forceinline__ CdfRay cdf_ray_setup(long long H, int P, int max_steps, float fixed_step_size, float sj,
+                                                const int* __restrict__ pts_idx, const float* __restrict__ min_depth,
+                                                const float* __restrict__ max_depth, const float* __restrict__ probs,
+                                                const float* __restrict__ noise_row, float noise_const, int* s_idx,
+                                                float* s_min, float* s_max, float* s_cum) {
+  const int lane = threadIdx.x & 31;
+  CdfRay r;
+  int nb = P;
+  for (int j0 = 0; j0 < P; j0 += 32) {      // valid bins are loaded only up to the first -1 (bin 0 is always used)
+    const int j = j0 + lane;
+    int v = -1;
+    if (j < P) { v = pts_idx[H + j]; s_idx[j] = v; }
+    const unsigned m = __ballot_sync(NSVF_FULL_MASK, j >= 1 && j < P && v == -1);
+    if (m) { nb = j0 + __ffs(m) - 1; break; }
+  }
+  for (int j = lane; j < min(P, nb + 1); j += 32) {
+    s_min[j] = min_depth[H + j];
+    s_max[j] = max_depth[H + j];
+    s_cum[j] = probs[H + j];
+  }
+  for (int j = nb + 1 + lane; j < P; j += 32) s_idx[j] = -1;     // the trailing loop may look at bins beyond nb
+  __syncwarp();
+  int ok = 1;
+  if (lane == 0) {
+    float c = s_cum[0];
+    ok = (c == c) && (fabsf(c) <= 3.0e38f);
+    for (int j = 1; j < nb; ++j) {
+      const float n = __fadd_rn(c, s_cum[j]);
+      ok &= (n >= c) && (fabsf(n) <= 3.0e38f);
+      s_cum[j] = n;
+      c = n;
+    }
+  }
+  r.ok = __shfl_sync(NSVF_FULL_MASK, ok, 0);
+  __syncwarp();
+  r.nb = nb;
+  r.step_size = fixed_step_size > 0.0f ? fixed_step_size : __fdiv_rn(1.0f, sj);
+  r.total_steps = min((int)ceilf(sj), max_steps);
+  // the main loop stops at the first step whose bin is >= nb (cdf beyond the last cumulative sum)
+  int n_in = r.total_steps, done = 0, b_last = 0;
+  if (r.ok && lane == 0) {
+    if (r.total_steps > 0 && cdf_at(r.total_steps - 1, noise_row, noise_const, max_steps, r.step_size) > s_cum[nb - 1]) {
+      int lo = 0, hi = r.total_steps - 1;          // first i with cdf_i > cum[nb-1]
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cdf_at(mid, noise_row, noise_const, max_steps, r.step_size) > s_cum[nb - 1]) hi = mid; else lo = mid + 1;
+      }
+      n_in = lo;
+      done = 1;
+    }
+    b_last = done ? nb : (n_in > 0 ? bin_of(cdf_at(n_in - 1, noise_row, noise_const, max_steps, r.step_size), s_cum, nb) : 0);
+  }
+  r.n_in = __shfl_sync(NSVF_FULL_MASK, n_in, 0);
+  r.done = __shfl_sync(NSVF_FULL_MASK, done, 0);
+  r.b_last = __shfl_sync(NSVF_FULL_MASK, b_last, 0);
+  return r;
+}
+
+// The reference's trailing loop (sample_gpu.cu:187-200) replayed from the state the main loop leaves; calls
+// emit(position, idx, dist, depth) for every sample it produces (lane-uniform code).  row0_nb = number of leading
+// valid bins of ray 0 of the block row (its stop test reads THAT ray's idx), next_idx0 = slot 0 of the next ray.
+template <typename Emit>
+__device__ __forceinline__ void cdf_trailing(const CdfRay& r, int P, const float* __restrict__ noise_row,
+                                             float noise_const, int max_steps, int row0_nb, int next_idx0,
+                                             const int* s_idx, const float* s_min, const float* s_max,
+                                             const float* s_cum, const float* __restrict__ g_min,
+                                             const float* __restrict__ g_max, Emit emit) {
+  // bins beyond nb are not staged (cdf_ray_setup loads nb + 1 of them): the loop reads them from global memory
+  auto bmin = [&](int j) { return j <= r.nb ? s_min[j] : g_min[j]; };
+  auto bmax = [&](int j) { return j <= r.nb ? s_max[j] : g_max[j]; };
+  int curr_bin, sidx = r.n_in + r.b_last;
+  float curr_max, zl;
+  // z of the last step sample, and whether it fell into the bin the trailing loop starts from
+  float z_prev = 0.f;
+  int b_prev = -1;
+  if (r.n_in > 0) {
+    const float c = cdf_at(r.n_in - 1, noise_row, noise_const, max_steps, r.step_size);
+    b_prev = bin_of(c, s_cum, r.nb);
+    z_prev = z_at(c, b_prev, s_cum, s_min, s_max);
+  }
+  if (r.done) {
+    curr_bin = r.nb;
+    curr_max = s_max[r.nb - 1];
+    zl = b_prev == r.nb - 1 ? z_prev : s_min[r.nb - 1];
+  } else {
+    curr_bin = r.b_last;
+    curr_max = bmax(curr_bin);
+    zl = r.n_in > 0 ? z_prev : s_min[0];
+  }
+  while (zl < curr_max) {
+    const int oi = curr_bin < P ? s_idx[curr_bin] : next_idx0;
+    emit(sidx, oi, __fsub_rn(curr_max, zl), __fmul_rn(__fadd_rn(curr_max, zl), 0.5f));
+    ++curr_bin;
+    ++sidx;
+    if (curr_bin >= P || curr_bin >= row0_nb) break;
+    curr_max = bmax(curr_bin);
+    zl = bmin(curr_bin);
+  }
+}
+
+constexpr int kLazyWarps = 8;       // block kernel: 32 rays per CTA, 4 per warp
+constexpr int kLazyBlock = 64;      // positions per block (multiple of 32)
+
+__global__ void __launch_bounds__(kCdfWarps * 32)
+inverse_cdf_plan_kernel(int b, int num_rays, long long valid_rays, int ray_chunk, int P, int max_steps,
+                        float fixed_step_size, const int* __restrict__ pts_idx, const float* __restrict__ min_depth,
+                        const float* __restrict__ max_depth, const float* __restrict__ noise, float noise_const,
+                        const float* __restrict__ probs, const float* __restrict__ steps, int* __restrict__ ray_len,
+                        int2* __restrict__ quirk, int* __restrict__ meta /* [max_len, holes, fallback rays] */) {
+  extern __shared__ __align__(16) float cdf_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* base = cdf_smem + (size_t)warp * 4 * P;
+  int* s_idx = reinterpret_cast<int*>(base);
+  float *s_min = base + P, *s_max = base + 2 * P, *s_cum = base + 3 * P;
+  int my_max = 0;
+  for (long long ray = (long long)blockIdx.x * kCdfWarps + warp; ray < valid_rays;
+       ray += (long long)gridDim.x * kCdfWarps) {
+    const long long H = ray * P;
+    const long long batch = ray / num_rays;
+    const int rr = (int)(ray - batch * num_rays);
+    const int c0 = (rr / ray_chunk) * ray_chunk;
+    const long long row0 = batch * num_rays + c0;
+    const int* row0_idx = pts_idx + (row0 < valid_rays ? row0 : 0) * P;
+    long long nxt = -1;
+    if (rr + 1 < min(c0 + ray_chunk, num_rays)) nxt = ray + 1;
+    else if (batch + 1 < b) nxt = (batch + 1) * num_rays + c0;
+    const int next_idx0 = nxt >= 0 ? pts_idx[(nxt < valid_rays ? nxt : 0) * P] : -1;
+    // leading valid bins of the block row's ray 0 (hit lists are -1-terminated: sorted by the intersection)
+    int row0_nb = P;
+    for (int j0 = 0; j0 < P; j0 += 32) {
+      const int j = j0 + lane;
+      const unsigned m = __ballot_sync(NSVF_FULL_MASK, j < P && row0_idx[j] == -1);
+      if (m) { row0_nb = j0 + __ffs(m) - 1; break; }
+    }
+    const float* noise_row = noise != nullptr ? noise + ray * max_steps : nullptr;
+    const CdfRay r = cdf_ray_setup(H, P, max_steps, fixed_step_size, steps[ray], pts_idx, min_depth, max_depth, probs,
+                                   noise_row, noise_const, s_idx, s_min, s_max, s_cum);
+    int lastv = 0, n_valid = 0;
+    if (lane == 0) {
+      if (r.ok) {
+        // step samples and bin ends of the main loop: positions [0, n_in + b_last), all with a valid voxel id
+        lastv = n_valid = min(r.n_in + r.b_last, max_steps);
+        cdf_trailing(r, P, noise_row, noise_const, max_steps, row0_nb, next_idx0, s_idx, s_min, s_max, s_cum,
+                     min_depth + H, max_depth + H, [&](int pos, int oi, float, float) {
+                       if (pos < max_steps && oi != -1) { ++n_valid; lastv = pos + 1; }
+                     });
+      } else {
+        // irregular cumulative sums: count with the reference's serial machine
+        CdfState st;
+        st.curr_bin = 0; st.s = 0; st.curr_step = 0;
+        st.curr_min_depth = s_min[0]; st.curr_max_depth = s_max[0];
+        st.curr_min_cdf = 0.0f; st.curr_max_cdf = probs[H];
+        st.step_size = r.step_size; st.z_low = st.curr_min_depth; st.total_steps = r.total_steps;
+        st.curr_cdf = 0.0f; st.phase = 0;
+        int pos = 0;
+        while (pos < max_steps && st.phase != 3) {
+          int oi; float od, oz;
+          if (cdf_next(st, P, max_steps, H, next_idx0, pts_idx, row0_idx, min_depth, max_depth, probs, noise_row,
+                       noise_const, oi, od, oz)) {
+            if (oi != -1) { ++n_valid; lastv = pos + 1; }
+            ++pos;
+          }
+        }
+        atomicAdd(meta + 2, 1);
+      }
+      ray_len[ray] = lastv;
+      quirk[ray] = make_int2(next_idx0, r.ok ? row0_nb : -1);     // row0_nb = -1 marks a fallback ray
+      if (n_valid != lastv) atomicOr(meta + 1, 1);
+    }
+    lastv = __shfl_sync(NSVF_FULL_MASK, lastv, 0);
+    my_max = max(my_max, lastv);
+    __syncwarp();
+  }
+  if (lane == 0 && my_max > 0) atomicMax(meta, my_max);
+}
+
+// Samples of positions [k0, k1) of the live rays -> planes idxT / depthT / distsT [K][ldb].
+__global__ void __launch_bounds__(kLazyWarps * 32)
+inverse_cdf_block_kernel(long long B, long long ldb, int P, int max_steps, float fixed_step_size, int k0, int k1,
+                         const unsigned char* __restrict__ early_stop, const int* __restrict__ ray_len,
+                         const int2* __restrict__ quirk, const int* __restrict__ pts_idx,
+                         const float* __restrict__ min_depth, const float* __restrict__ max_depth,
+                         const float* __restrict__ noise, long long noise_stride, float noise_const,
+                         const float* __restrict__ probs, const float* __restrict__ steps, float pad_depth,
+                         int* __restrict__ idxT, float* __restrict__ depthT, float* __restrict__ distsT) {
+  extern __shared__ __align__(16) float cdf_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // tile [kLazyBlock][33] x {idx, depth, dist}, then the warps' bin tables
+  int* t_idx = reinterpret_cast<int*>(cdf_smem);
+  float* t_dep = cdf_smem + kLazyBlock * 33;
+  float* t_dst = cdf_smem + 2 * kLazyBlock * 33;
+  __shared__ int s_len[32];
+  float* base = cdf_smem + 3 * kLazyBlock * 33 + (size_t)warp * 4 * P;
+  int* s_idx = reinterpret_cast<int*>(base);
+  float *s_min = base + P, *s_max = base + 2 * P, *s_cum = base + 3 * P;
+  const int kb = k1 - k0;
+  for (long long r0 = (long long)blockIdx.x * 32; r0 < B; r0 += (long long)gridDim.x * 32) {
+    __syncthreads();
+    if (warp == 0) {
+      int l = 0;
+      if (r0 + lane < B && (early_stop == nullptr || early_stop[r0 + lane] == 0)) l = min(ray_len[r0 + lane], k1);
+      s_len[lane] = l > k0 ? l : 0;          // number of leading positions of this ray that exist, 0 = nothing in the block
+    }
+    __syncthreads();
+    for (int q = 0; q < 32 / kLazyWarps; ++q) {
+      const int rl = warp * (32 / kLazyWarps) + q;
+      if (s_len[rl] == 0) continue;
+      const long long ray = r0 + rl;
+      const long long H = ray * P;
+      const int2 qk = quirk[ray];
+      const float* noise_row = noise != nullptr ? noise + ray * noise_stride : nullptr;
+      auto put = [&](int pos, int oi, float od, float oz) {     // ray_sample's clamp / masking, as in the eager path
+        if (pos < k0 || pos >= k1) return;
+        od = od < 0.f ? 0.f : od;
+        if (oi == -1) { od = 0.f; oz = pad_depth; }
+        const int a = (pos - k0) * 33 + rl;
+        t_idx[a] = oi; t_dep[a] = oz; t_dst[a] = od;
+      };
+      if (qk.y < 0) {
+        // fallback ray: the serial machine from the start, keeping the block's positions (lane 0)
+        if (lane == 0) {
+          const int* row0_idx = pts_idx;   // unreachable in practice for sliced rays: fallback rays are reported to the host
+          CdfState st;
+          st.curr_bin = 0; st.s = 0; st.curr_step = 0;
+          st.curr_min_depth = min_depth[H]; st.curr_max_depth = max_depth[H];
+          st.curr_min_cdf = 0.0f; st.curr_max_cdf = probs[H];
+          const float sj = steps[ray];
+          st.step_size = fixed_step_size > 0.0f ? fixed_step_size : __fdiv_rn(1.0f, sj);
+          st.z_low = st.curr_min_depth; st.total_steps = min((int)ceilf(sj), max_steps);
+          st.curr_cdf = 0.0f; st.phase = 0;
+          int pos = 0;
+          while (pos < min(max_steps, k1) && st.phase != 3) {
+            int oi; float od, oz;
+            if (cdf_next(st, P, max_steps, H, qk.x, pts_idx, row0_idx, min_depth, max_depth, probs, noise_row,
+                         noise_const, oi, od, oz)) {
+              put(pos, oi, od, oz);
+              ++pos;
+            }
+          }
+        }
+        __syncwarp();
+        continue;
+      }
+      const CdfRay r = cdf_ray_setup(H, P, max_steps, fixed_step_size, steps[ray], pts_idx, min_depth, max_depth, probs,
+                                     noise_row, noise_const, s_idx, s_min, s_max, s_cum);
+      // first step whose position f(i) = i + b_i is >= k0 (f is strictly increasing)
+      int i_lo = 0;
+      if (lane == 0) {
+        int lo = 0, hi = r.n_in;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          const int bm = bin_of(cdf_at(mid, noise_row, noise_const, max_steps, r.step_size), s_cum, r.nb);
+          if (mid + bm >= k0) hi = mid; else lo = mid + 1;
+        }
+        i_lo = lo;
+      }
+      i_lo = __shfl_sync(NSVF_FULL_MASK, i_lo, 0);
+      // state of step i_lo - 1 (bin and depth), needed for z_low of the first step of the block and for the bin ends
+      int pb0 = -1;
+      float pz0 = 0.f;
+      if (i_lo > 0) {
+        const float c = cdf_at(i_lo - 1, noise_row, noise_const, max_steps, r.step_size);
+        pb0 = bin_of(c, s_cum, r.nb);
+        pz0 = z_at(c, pb0, s_cum, s_min, s_max);
+      }
+      // (a) step samples of the block, 32 per iteration
+      {
+        int prev_b = pb0;
+        float prev_z = pz0;
+        bool past = false;
+        for (int i0 = i_lo; i0 < r.n_in && !past; i0 += 32) {
+          const int i = i0 + lane;
+          const bool act = i < r.n_in;
+          float cdf = 0.f, z = 0.f;
+          int bb = 0;
+          if (act) {
+            cdf = cdf_at(i, noise_row, noise_const, max_steps, r.step_size);
+            bb = bin_of(cdf, s_cum, r.nb);
+            z = z_at(cdf, bb, s_cum, s_min, s_max);
+          }
+          float pz = __shfl_up_sync(NSVF_FULL_MASK, z, 1);
+          int pb = __shfl_up_sync(NSVF_FULL_MASK, bb, 1);
+          if (lane == 0) { pz = prev_z; pb = prev_b; }
+          if (act) {
+            const float zlow = (pb == bb) ? pz : s_min[bb];
+            const int pos = i + bb;
+            if (pos < max_steps) put(pos, s_idx[bb], __fsub_rn(z, zlow), __fmul_rn(__fadd_rn(z, zlow), 0.5f));
+          }
+          const unsigned amask = __ballot_sync(NSVF_FULL_MASK, act);
+          const int la = 31 - __clz(amask);
+          prev_b = __shfl_sync(NSVF_FULL_MASK, bb, la);
+          prev_z = __shfl_sync(NSVF_FULL_MASK, z, la);
+          past = (i0 + la + prev_b) >= k1;
+        }
+      }
+      // (b) bin-end samples of the block: bin j sits at j + c_j, c_j = first step whose cdf exceeds cum[j]
+      {
+        bool past = false;
+        for (int j0 = (pb0 < 0 ? 0 : pb0); j0 < r.b_last && !past; j0 += 32) {
+          const int j = j0 + lane;
+          int pos = 0x7fffffff;
+          if (j < r.b_last) {
+            int lo = 0, hi = r.n_in;              // c_j
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (cdf_at(mid, noise_row, noise_const, max_steps, r.step_size) > s_cum[j]) hi = mid; else lo = mid + 1;
+            }
+            pos = j + lo;
+            if (pos >= k0 && pos < k1 && pos < max_steps) {
+              float zlow = s_min[j];
+              if (lo > 0) {
+                const float c = cdf_at(lo - 1, noise_row, noise_const, max_steps, r.step_size);
+                if (bin_of(c, s_cum, r.nb) == j) zlow = z_at(c, j, s_cum, s_min, s_max);
+              }
+              put(pos, s_idx[j], __fsub_rn(s_max[j], zlow), __fmul_rn(__fadd_rn(s_max[j], zlow), 0.5f));
+            }
+          }
+          past = __any_sync(NSVF_FULL_MASK, j < r.b_last && pos >= k1);
+        }
+      }
+      // (c) trailing samples (lane-uniform replay; every lane computes, lane 0 stores)
+      if (r.n_in + r.b_last < k1) {
+        cdf_trailing(r, P, noise_row, noise_const, max_steps, qk.y, qk.x, s_idx, s_min, s_max, s_cum, min_depth + H,
+                     max_depth + H,
+                     [&](int pos, int oi, float od, float oz) { if (lane == 0 && pos < max_steps) put(pos, oi, od, oz); });
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    // flush: plane row k of the 32 rays = 128 contiguous bytes
+    for (int kk = warp; kk < kb; kk += kLazyWarps) {
+      const int k = k0 + kk;
+      if (k < s_len[lane]) {
+        const long long a = (long long)k * ldb + r0 + lane;
+        idxT[a] = t_idx[kk * 33 + lane];
+        depthT[a] = t_dep[kk * 33 + lane];
+        distsT[a] = t_dst[kk * 33 + lane];
+      }
+    }
+  }
+}
+
 // ---- uniform ray sampling -----------------------------------------------------------------------------------------
 // Replaces uniform_ray_sampling_kernel, fairnr/clib/src/sample_gpu.cu:15-106.  The reference runs two passes per ray
 // IN PLACE in global memory: (1) a three-way merge of voxel entries, voxel exits and march points into the output row,
@@ -687,5 +1070,57 @@ extern "C" int nsvf_uniform_ray_sampling(nsvf_stream_t stream_, int b, int num_r
                     (uniform_sampling_kernel<16><<<grid, kSampWarps * 32, 0, stream>>>(
                         total_rays, max_hits, max_steps, step_size, pts_idx, min_depth, max_depth, uniform_noise,
                         sampled_idx, sampled_depth, sampled_dists, max_count)));
+  return 0;
+}
+
+extern "C" int nsvf_inverse_cdf_plan(nsvf_stream_t stream_, int b, int num_rays, long long valid_rays, int ray_chunk,
+                                     int max_hits, int max_steps, float fixed_step_size, const int* pts_idx,
+                                     const float* min_depth, const float* max_depth, const float* uniform_noise,
+                                     float noise_const, const float* probs, const float* steps, int* ray_len,
+                                     int* quirk, int* meta) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSVF_REQUIRE(b >= 0 && num_rays >= 0 && max_hits > 0 && max_steps >= 0, "inverse_cdf_plan: bad sizes");
+  const long long total_rays = (long long)b * num_rays;
+  if (valid_rays < 0 || valid_rays > total_rays) valid_rays = total_rays;
+  if (ray_chunk <= 0 || ray_chunk > num_rays) ray_chunk = num_rays;
+  if (valid_rays == 0) return 0;
+  const size_t smem = (size_t)kCdfWarps * 4 * max_hits * sizeof(float);
+  NSVF_REQUIRE(smem <= 160 * 1024, "inverse_cdf_plan: max_hits=%d too large", max_hits);
+  NSVF_CUDA_OK(cudaFuncSetAttribute(inverse_cdf_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  long long want = (valid_rays + kCdfWarps - 1) / kCdfWarps, cap = (long long)num_sms() * 12;
+  NSVF_TIMED_LAUNCH("inverse_cdf_plan_kernel", stream,
+                    (inverse_cdf_plan_kernel<<<(int)(want < cap ? want : cap), kCdfWarps * 32, smem, stream>>>(
+                        b, num_rays, valid_rays, ray_chunk, max_hits, max_steps, fixed_step_size, pts_idx, min_depth,
+                        max_depth, uniform_noise, noise_const, probs, steps, ray_len, reinterpret_cast<int2*>(quirk),
+                        meta)));
+  return 0;
+}
+
+extern "C" long long nsvf_march_plane_stride(long long B);
+
+extern "C" int nsvf_inverse_cdf_block(nsvf_stream_t stream_, long long B, int max_hits, int max_steps,
+                                      float fixed_step_size, int k_begin, int k_end, const unsigned char* early_stop,
+                                      const int* ray_len, const int* quirk, const int* pts_idx, const float* min_depth,
+                                      const float* max_depth, const float* uniform_noise, long long noise_row_stride,
+                                      float noise_const, const float* probs, const float* steps, float pad_depth,
+                                      int* idxT, float* depthT, float* distsT) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSVF_REQUIRE(B >= 0 && max_hits > 0 && max_steps >= 0 && k_begin >= 0 && k_begin <= k_end, "inverse_cdf_block: bad sizes");
+  if (B == 0 || k_end == k_begin) return 0;
+  const size_t smem = ((size_t)3 * kLazyBlock * 33 + (size_t)kLazyWarps * 4 * max_hits) * sizeof(float);
+  NSVF_REQUIRE(smem <= 200 * 1024, "inverse_cdf_block: max_hits=%d too large", max_hits);
+  NSVF_CUDA_OK(cudaFuncSetAttribute(inverse_cdf_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  int per_sm = (int)((200 * 1024) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
+  const long long ldb = nsvf_march_plane_stride(B);
+  for (int k0 = k_begin; k0 < k_end; k0 += kLazyBlock) {
+    const int k1 = k0 + kLazyBlock < k_end ? k0 + kLazyBlock : k_end;
+    long long want = (B + 31) / 32, cap = (long long)num_sms() * per_sm;
+    NSVF_TIMED_LAUNCH("inverse_cdf_block_kernel", stream,
+                      (inverse_cdf_block_kernel<<<(int)(want < cap ? want : cap), kLazyWarps * 32, smem, stream>>>(
+                          B, ldb, max_hits, max_steps, fixed_step_size, k0, k1, early_stop, ray_len,
+                          reinterpret_cast<const int2*>(quirk), pts_idx, min_depth, max_depth, uniform_noise,
+                          noise_row_stride, noise_const, probs, steps, pad_depth, idxT, depthT, distsT)));
+  }
   return 0;
 }

@@ -192,10 +192,17 @@ class SparseVoxelEncoder(nn.Module):
                                        self.voxel_size)
         return ray_start, ray_dir, hits
 
-    def ray_sample(self, intersection_outputs, trimmed=False):
+    def ray_sample(self, intersection_outputs, trimmed=False, lazy=False):
         """encoder.py:538-556.  The clamp / masked_fill post-processing runs inside the sampler kernel.  `trimmed=True`
         (extension, used by NSVFPipeline with our VolumeRenderer) returns rows of max_steps slots of which only the
-        first `sampled_point_count[r]` are written — no padding traffic, no max_len host sync."""
+        first `sampled_point_count[r]` are written — no padding traffic, no max_len host sync.  `lazy=True` (extension,
+        for rendering with early termination) computes only the per-ray sample counts; our VolumeRenderer then
+        materialises the samples block by block for the rays that have not stopped."""
+        if lazy:
+            return clib.inverse_cdf_sampling_lazy(
+                intersection_outputs["intersected_voxel_idx"], intersection_outputs["min_depth"],
+                intersection_outputs["max_depth"], intersection_outputs["probs"], intersection_outputs["steps"],
+                -1, self.deterministic_step or (not self.training), pad_depth=MAX_DEPTH)
         sampled_idx, sampled_depth, sampled_dists, ray_len, _ = clib.inverse_cdf_sampling_rows(
             intersection_outputs["intersected_voxel_idx"], intersection_outputs["min_depth"],
             intersection_outputs["max_depth"], intersection_outputs["probs"], intersection_outputs["steps"],

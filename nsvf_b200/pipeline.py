@@ -33,6 +33,10 @@ class NSVFPipeline(nn.Module):
         self.fixed_fine_num_samples = fixed_fine_num_samples
         self.fine_num_sample_ratio = fine_num_sample_ratio
         self.padded_samples = False     # True: results["samples"] are the reference's padded [N, max_len] tensors
+        # rendering with early termination can sample on demand (encoder.ray_sample(lazy=True)): work proportional to
+        # the evaluated samples instead of the emitted ones.  Bit-identical results; measured 23.2 ms against 22.5 ms for
+        # the eager sampler + block transpose on the C3 frame (per-ray set-up of the block kernel eats the saving), so off
+        self.lazy_sampling = False
 
     def prepare_hierarchical_sampling(self, inter, samples, results):
         """Bins of the fine pass = the coarse samples (nerf.py:64-79, nsvf.py:83-87)."""
@@ -112,7 +116,11 @@ class NSVFPipeline(nn.Module):
         # trimmed sample rows (no padding traffic, no max_len sync) whenever nothing but our renderer reads them
         trimmed = not (self.hierarchical or getattr(self.encoder, "track_max_probs", False) or self.padded_samples)
         if rs.size(0) > 0:
-            samples = self.encoder.ray_sample(inter, trimmed=trimmed)
+            # with early termination (rendering) the samples are materialised on demand, block by block, for the rays
+            # that are still alive; otherwise every sample is needed and the sampler emits them all at once
+            lazy = (trimmed and not self.training and getattr(self.raymarcher, "raymarching_tolerance", 0) > 0
+                    and self.lazy_sampling)
+            samples = self.encoder.ray_sample(inter, trimmed=trimmed, lazy=lazy)
             # 'probs' [B,K] is read by hierarchical sampling and track_voxel_probs only
             need_probs = self.hierarchical or getattr(self.encoder, "track_max_probs", False) or self.padded_samples
             r = self.raymarcher(self.encoder, self.field, rs, rd, samples, encoder_states, return_probs=need_probs)

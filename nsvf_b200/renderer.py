@@ -203,8 +203,9 @@ class VolumeRenderer(nn.Module):
         torch.normal_; `return_probs=False` (extension) leaves results['probs'] empty instead of writing the dense
         [B,K] tensor that only track_voxel_probs and hierarchical sampling read."""
         self._want_probs = self.return_probs if return_probs is None else bool(return_probs)
-        if (global_weights is None and "sigma" in output_types and samples["sampled_point_voxel_idx"].dim() == 2
-                and not os.environ.get("NSVF_RENDER_GENERAL")):
+        lazy = "lazy_pts_idx" in samples
+        if lazy or (global_weights is None and "sigma" in output_types
+                    and samples["sampled_point_voxel_idx"].dim() == 2 and not os.environ.get("NSVF_RENDER_GENERAL")):
             results = self._forward_chunk_plan(input_fn, field_fn, ray_start, ray_dir, samples, encoder_states,
                                                output_types, noise_fn)
             if results is not None:
@@ -214,18 +215,25 @@ class VolumeRenderer(nn.Module):
 
     def _forward_chunk_plan(self, input_fn, field_fn, ray_start, ray_dir, samples, encoder_states, output_types,
                             noise_fn):
-        sidx, depth, dists = (samples["sampled_point_voxel_idx"], samples["sampled_point_depth"],
-                              samples["sampled_point_distance"])
+        lazy = samples if "lazy_pts_idx" in samples else None
         lens = samples.get("sampled_point_count", None)
-        # rows may be strided views (the sampler returns [:, :max_len] slices); anything else is made dense
-        ok = (sidx.dtype == torch.int32 and depth.dtype == torch.float32 and dists.dtype == torch.float32
-              and sidx.stride(1) == 1 and depth.stride(1) == 1 and dists.stride(1) == 1
-              and sidx.stride(0) == depth.stride(0) == dists.stride(0))
-        if not ok:
-            sidx, depth, dists = sidx.int().contiguous(), depth.float().contiguous(), dists.float().contiguous()
-        B, K = sidx.shape
-        ldk = max(K, sidx.stride(0))
-        dev = sidx.device
+        if lazy is not None:
+            # on-demand samples: only the per-ray counts exist; blocks of columns are sampled ahead of the window loop
+            sidx = depth = dists = None
+            B, K, ldk = lens.numel(), int(lazy["lazy_max_steps"]), 0
+            dev = lens.device
+        else:
+            sidx, depth, dists = (samples["sampled_point_voxel_idx"], samples["sampled_point_depth"],
+                                  samples["sampled_point_distance"])
+            # rows may be strided views (the sampler returns [:, :max_len] slices); anything else is made dense
+            ok = (sidx.dtype == torch.int32 and depth.dtype == torch.float32 and dists.dtype == torch.float32
+                  and sidx.stride(1) == 1 and depth.stride(1) == 1 and dists.stride(1) == 1
+                  and sidx.stride(0) == depth.stride(0) == dists.stride(0))
+            if not ok:
+                sidx, depth, dists = sidx.int().contiguous(), depth.float().contiguous(), dists.float().contiguous()
+            B, K = sidx.shape
+            ldk = max(K, sidx.stride(0))
+            dev = sidx.device
         ray_start, ray_dir = ray_start.float().contiguous(), ray_dir.float().contiguous()
         tolerance = self.raymarching_tolerance
         chunk_size = self.chunk_size if self.training else self.valid_chunk_size
@@ -255,10 +263,24 @@ class VolumeRenderer(nn.Module):
             early_stop = torch.zeros(B, dtype=torch.uint8, device=dev)
             # without early termination every sample is needed: one transpose.  With it, columns are transposed in
             # blocks just ahead of the window loop, and rays that have stopped are skipped.
-            t_block = K if (all_windows or rows_padded) else 64
+            t_block = K if (all_windows or rows_padded) else int(os.environ.get("NSVF_PLANE_BLOCK", 64))
             t_upto = min(K, t_block)
-            _lib.check(_L.nsvf_march_transpose(st, B, K, ldk, 0, t_upto, None, _p(lens), _p(sidx), _p(depth), _p(dists),
-                                               _p(idxT), _p(depthT), _p(distsT)))
+            if lazy is not None:
+                lz = (int(lazy["lazy_pts_idx"].size(1)), K, float(lazy["lazy_fixed_step_size"]))
+                lz_noise = lazy.get("lazy_noise", None)
+                lz_ptrs = (_p(lens), _p(lazy["lazy_quirk"]), _p(lazy["lazy_pts_idx"]), _p(lazy["lazy_min_depth"]),
+                           _p(lazy["lazy_max_depth"]), _p(lz_noise), K, 0.5, _p(lazy["lazy_probs"]),
+                           _p(lazy["lazy_steps"]), float(lazy["lazy_pad_depth"]))
+
+                def fill_planes(k_begin, k_end, stop_ptr):
+                    _lib.check(_L.nsvf_inverse_cdf_block(st, B, lz[0], lz[1], lz[2], k_begin, k_end, stop_ptr, *lz_ptrs,
+                                                         p_idxT, p_depthT, p_distsT))
+            else:
+                def fill_planes(k_begin, k_end, stop_ptr):
+                    _lib.check(_L.nsvf_march_transpose(st, B, K, ldk, k_begin, k_end, stop_ptr, _p(lens), _p(sidx),
+                                                       _p(depth), _p(dists), p_idxT, p_depthT, p_distsT))
+            p_idxT, p_depthT, p_distsT = _p(idxT), _p(depthT), _p(distsT)
+            fill_planes(0, t_upto, None)
             eval_len = torch.zeros(B, dtype=i32, device=dev)
             acc_fe = torch.zeros(B, dtype=f32, device=dev) if tol > 0 else None
             feT = E(K * ldb, dtype=f32, device=dev)
@@ -266,6 +288,8 @@ class VolumeRenderer(nn.Module):
             stream.synchronize()
             head = info[:16].tolist()
             if head[4]:
+                if lazy is not None:
+                    raise RuntimeError("nsvf_b200: lazily sampled rays must have prefix-valid rows")
                 return None                      # some row's valid samples are not a prefix: general path
             if all_windows:
                 windows = info[16: 16 + 3 * head[5]].view(-1, 3).tolist()
@@ -274,7 +298,7 @@ class VolumeRenderer(nn.Module):
             record = _MarchRecord(B, K, ldk, depth if rows_padded else None, depthT, lens, early_stop, eval_len, feT,
                                   texT, lazy=t_block < K)
             p_lens, p_es, p_acc, p_ev, p_plan = _p(lens), _p(early_stop), _p(acc_fe), _p(eval_len), _p(plan)
-            p_idxT, p_depthT, p_distsT, p_rs, p_rd = _p(idxT), _p(depthT), _p(distsT), _p(ray_start), _p(ray_dir)
+            p_rs, p_rd = _p(ray_start), _p(ray_dir)
             p_feT, p_texT = _p(feT), _p(texT)
             out_types = list(output_types)
             evals, launch_no, w = 0, 0, 0
@@ -286,8 +310,7 @@ class VolumeRenderer(nn.Module):
                 dists_c = E(M, dtype=f32, device=dev)
                 while t_upto < end:
                     t_next = min(K, t_upto + t_block)
-                    _lib.check(_L.nsvf_march_transpose(st, B, K, ldk, t_upto, t_next, p_es, p_lens, _p(sidx),
-                                                       _p(depth), _p(dists), p_idxT, p_depthT, p_distsT))
+                    fill_planes(t_upto, t_next, p_es)
                     t_upto = t_next
                 if grad or ray_off is None:      # the backward needs every window's offsets
                     ray_off = E(B + 1, dtype=i32, device=dev)
@@ -426,7 +449,9 @@ class VolumeRenderer(nn.Module):
             results = self.forward_chunk(input_fn, field_fn, ray_start, ray_dir, samples, *args, **kwargs)
         else:
             parts = [self.forward_chunk(input_fn, field_fn, ray_start[i: i + chunk_size], ray_dir[i: i + chunk_size],
-                                        {name: s[i: i + chunk_size] for name, s in samples.items()}, *args, **kwargs)
+                                        {name: (s[i: i + chunk_size] if torch.is_tensor(s) and s.dim() > 0 and
+                                                s.size(0) == ray_start.size(0) else s) for name, s in samples.items()},
+                                        *args, **kwargs)
                      for i in range(0, ray_start.size(0), chunk_size)]
             def merge(name):
                 vals = [r[name] for r in parts]

@@ -189,3 +189,50 @@ def test_plan_matches_torch_statement_of_reference_loop(cuda):
     helpers.assert_close_scaled(res["depths"], dep, what="depths")
     helpers.assert_close_scaled(res["max_depths"], depth.masked_fill(hits.eq(0), -1).max(1).values, what="max_depths")
     helpers.assert_close_scaled(res["min_depths"], depth.min(1).values, what="min_depths")
+
+
+@pytest.mark.parametrize("deterministic", [True, False])
+def test_lazy_sampling_blocks_equal_eager_samples(cuda, deterministic):
+    """nsvf_inverse_cdf_plan / _block (on-demand sampling) reproduce the eager sampler bit for bit: same per-ray counts,
+    and every block of the slot-major planes holds exactly the eager samples (all rays alive, all columns)."""
+    L, p = _lib.load(), _lib.ptr
+    enc, st, rs, rd, _, inter = _scene_samples(cuda, n_rays=4000, seed=13, train=not deterministic)
+    args = (inter["intersected_voxel_idx"], inter["min_depth"], inter["max_depth"], inter["probs"], inter["steps"])
+    torch.manual_seed(21)
+    eidx, edep, edst, elen, _ = clib.inverse_cdf_sampling_rows(*args, -1, deterministic, trimmed=True)
+    torch.manual_seed(21)
+    lz = clib.inverse_cdf_sampling_lazy(*args, -1, deterministic)
+    assert torch.equal(lz["sampled_point_count"], elen)
+    meta = lz["lazy_meta"].tolist()
+    assert meta[0] == int(elen.max()) and meta[2] == 0
+    B, K = elen.numel(), lz["lazy_max_steps"]
+    assert K == eidx.shape[1]
+    ldb = L.nsvf_march_plane_stride(B)
+    idxT = torch.full((K, ldb), -7, dtype=torch.int32, device=cuda)
+    depT = torch.full((K, ldb), -7.0, device=cuda)
+    dstT = torch.full((K, ldb), -7.0, device=cuda)
+    noise = lz.get("lazy_noise", None)
+    for k0 in range(0, K, 96):          # blocks that do not line up with the kernel's internal 64-column blocks
+        _lib.check(L.nsvf_inverse_cdf_block(
+            _lib.current_stream(cuda), B, inter["min_depth"].shape[1], K, -1.0, k0, min(K, k0 + 96), None,
+            p(lz["sampled_point_count"]), p(lz["lazy_quirk"]), p(lz["lazy_pts_idx"]), p(lz["lazy_min_depth"]),
+            p(lz["lazy_max_depth"]), p(noise), K, 0.5, p(lz["lazy_probs"]), p(lz["lazy_steps"]), 10000.0, p(idxT), p(depT),
+            p(dstT)))
+    mask = torch.arange(K, device=cuda)[None] < elen[:, None]
+    assert torch.equal(idxT[:, :B].t()[mask], eidx[mask])
+    assert torch.equal(depT[:, :B].t()[mask], edep[mask]) and torch.equal(dstT[:, :B].t()[mask], edst[mask])
+    assert bool((idxT[:, :B].t()[~mask] == -7).all()), "nothing beyond a ray's samples may be written"
+
+
+def test_lazy_rendering_equals_eager_rendering(cuda):
+    """Rendering with early termination on lazily sampled rays == on eagerly sampled (trimmed) rays, exactly."""
+    enc, st, rs, rd, _, inter = _scene_samples(cuda, n_rays=5000, seed=17)
+    eager = enc.ray_sample(inter, trimmed=True)
+    lazy = enc.ray_sample(inter, lazy=True)
+    for tol, chunk in ((0.05, 2), (0.3, 1), (0.0, 4)):
+        ren = VolumeRenderer(chunk_size=chunk, valid_chunk_size=chunk, raymarching_tolerance=tol).eval()
+        a, _ = _render(ren, enc, st, rs, rd, eager, general=False)
+        b, _ = _render(ren, enc, st, rs, rd, lazy, general=False)
+        assert a["ae"] == b["ae"]
+        for name in ("depths", "colors", "max_depths", "min_depths", "missed", "probs"):
+            assert torch.equal(a[name], b[name]), (name, tol)
