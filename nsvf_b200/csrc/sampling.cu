@@ -282,22 +282,31 @@ inverse_cdf_warp_kernel(int b, int num_rays, long long valid_rays, int ray_chunk
     const int next_idx0 = nxt >= 0 ? pts_idx[(nxt < valid_rays ? nxt : 0) * P] : -1;
     const float* noise_row = noise != nullptr ? noise + ray * max_steps : nullptr;
 
-    // 1) bins -> shared memory (coalesced)
-    for (int j = lane; j < P; j += 32) {
-      s_idx[j] = pts_idx[H + j];
+    // 1) bins -> shared memory (coalesced).  The voxel ids are loaded up to the first -1 (bin 0 is always used): that is
+    //    the number of usable bins nb; depths / probabilities are then loaded for bins 0..nb only (a hit list of
+    //    max_hits = 135 slots holds ~20 hits: 3 of the 4 row reads shrink to one 128-byte line).  The trailing loop can
+    //    look at bins beyond nb when the block row's ray 0 has more hits; it then reads them from global memory.
+    int nb = P;
+    for (int j0 = 0; j0 < P; j0 += 32) {
+      const int j = j0 + lane;
+      int v = -1;
+      if (j < P) { v = pts_idx[H + j]; s_idx[j] = v; }
+      const unsigned m = __ballot_sync(NSVF_FULL_MASK, j >= 1 && j < P && v == -1);
+      if (m) {
+        nb = j0 + __ffs(m) - 1;
+        for (int t = j0 + 32 + lane; t < P; t += 32) s_idx[t] = pts_idx[H + t];   // rare: ids beyond the first -1
+        break;
+      }
+    }
+    const int n_ld = min(P, nb + 1);
+    for (int j = lane; j < n_ld; j += 32) {
       s_min[j] = min_depth[H + j];
       s_max[j] = max_depth[H + j];
       s_cum[j] = probs[H + j];
       s_cnt[j] = 0;
     }
     __syncwarp();
-    // 2) number of usable bins (bin 0 is always used) and the reference's sequential cumulative sums
-    int nb = P;
-    for (int j0 = 0; j0 < P; j0 += 32) {
-      const int j = j0 + lane;
-      const unsigned m = __ballot_sync(NSVF_FULL_MASK, j >= 1 && j < P && s_idx[j] == -1);
-      if (m) { nb = j0 + __ffs(m) - 1; break; }
-    }
+    // 2) the reference's sequential cumulative sums
     int ok = 1;
     if (lane == 0) {
       float c = s_cum[0];
@@ -439,8 +448,8 @@ inverse_cdf_warp_kernel(int b, int num_rays, long long valid_rays, int ray_chunk
         ++curr_bin;
         ++sidx;
         if (curr_bin >= P || row0_idx[curr_bin] == -1) break;
-        curr_max = s_max[curr_bin];
-        zl = s_min[curr_bin];
+        curr_max = curr_bin < n_ld ? s_max[curr_bin] : max_depth[H + curr_bin];
+        zl = curr_bin < n_ld ? s_min[curr_bin] : min_depth[H + curr_bin];
       }
       s_end = min(sidx, max_steps);
     }
