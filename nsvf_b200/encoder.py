@@ -213,8 +213,16 @@ class SparseVoxelEncoder(nn.Module):
             samples["sampled_point_count"] = ray_len
         return samples
 
-    @torch.enable_grad()
     def forward(self, samples, encoder_states):
+        """encoder.py:558-592.  The reference decorates this with torch.enable_grad() so that fields which differentiate
+        sigma w.r.t. the sample position (normals) work under no_grad; here that is only done when track_xyz_grad asks
+        for position gradients (the context switch costs host time once per renderer window)."""
+        if self.track_xyz_grad and not torch.is_grad_enabled():
+            with torch.enable_grad():
+                return self._forward(samples, encoder_states)
+        return self._forward(samples, encoder_states)
+
+    def _forward(self, samples, encoder_states):
         point_feats = encoder_states["voxel_vertex_idx"]
         point_xyz = encoder_states["voxel_center_xyz"]
         values = encoder_states["voxel_vertex_emb"]

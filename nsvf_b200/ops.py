@@ -79,6 +79,20 @@ class TrilinearEmbed(Function):
 
 def trilinear_embed(sampled_idx, sampled_xyz, feats, centres, values, voxel_size):
     """emb[M, D] = sum_j w_j(xyz) * values[feats[idx][j]]  (see include/nsvf_b200.h)."""
+    if not torch.is_grad_enabled() or not (values.requires_grad or sampled_xyz.requires_grad):
+        # inference: straight to the kernel (an autograd.Function.apply costs ~15 us of host time per call, and the
+        # renderer calls this once per window)
+        if (sampled_idx.dtype == torch.int32 and sampled_idx.is_contiguous() and sampled_xyz.dtype == torch.float32
+                and sampled_xyz.is_contiguous() and feats.dtype == torch.int32 and feats.is_contiguous()
+                and centres.dtype == torch.float32 and centres.is_contiguous() and values.dtype == torch.float32
+                and values.is_contiguous() and values.is_cuda and sampled_idx.is_cuda):
+            M, D = sampled_idx.numel(), values.shape[-1]
+            out = torch.empty((M, D), dtype=torch.float32, device=values.device)
+            with _lib.device_guard(values.device):
+                _lib.check(_L.nsvf_trilinear_embed_fwd(_lib.current_stream(values.device), M, D, _p(sampled_idx),
+                                                       _p(sampled_xyz), _p(feats), _p(centres), _p(values),
+                                                       float(voxel_size), _p(out)))
+            return out
     return TrilinearEmbed.apply(sampled_idx, sampled_xyz, feats, centres, values, voxel_size)
 
 
