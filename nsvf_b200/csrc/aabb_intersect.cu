@@ -637,6 +637,13 @@ extern "C" size_t nsvf_aabb_workspace_bytes(int n, int n_trees) {
 }
 
 // mode: 0 = reference order (ascending voxel index), 1 = sorted by entry depth, 2 = any-hit mask only
+__global__ void fill_f32_kernel(float* __restrict__ a, float* __restrict__ b, long long n, float v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    a[i] = v;
+    b[i] = v;
+  }
+}
+
 static int aabb_run(cudaStream_t stream, int mode, int b, int n, int m, float voxelsize, int n_max, float empty_depth,
                     const float* ray_start, const float* ray_dir, const float* points,
                     long long points_batch_stride, int* idx, float* min_depth, float* max_depth,
@@ -651,8 +658,11 @@ static int aabb_run(cudaStream_t stream, int mode, int b, int n, int m, float vo
       if (empty_depth == 0.0f) {
         NSVF_CUDA_OK(cudaMemsetAsync(min_depth, 0, sizeof(float) * rays * n_max, stream));
         NSVF_CUDA_OK(cudaMemsetAsync(max_depth, 0, sizeof(float) * rays * n_max, stream));
-      } else {
-        NSVF_REQUIRE(false, "aabb_intersect: empty voxel set with a non-zero fill depth is not supported");
+      } else {   // sorted mode of an empty voxel set (everything pruned): every slot holds the fill depth
+        const long long cells = rays * n_max;
+        fill_f32_kernel<<<(unsigned)((cells + 255) / 256 < 65535 ? (cells + 255) / 256 : 65535), 256, 0, stream>>>(
+            min_depth, max_depth, cells, empty_depth);
+        NSVF_LAUNCH_OK("fill_f32_kernel");
       }
     }
     if (hit != nullptr) NSVF_CUDA_OK(cudaMemsetAsync(hit, 0, rays, stream));

@@ -38,8 +38,9 @@ class _PosEnc(nn.Module):
 
 
 class _FCLayer(nn.Sequential):
-    """FCLayer of the reference (module_utils.py:97-111): Linear -> LayerNorm([o]) -> ReLU, same parameter names
-    ("0.weight", "0.bias", "1.weight", "1.bias").  The contraction runs on cuBLAS, everything else in the hand-written
+    """FCLayer of the reference (module_utils.py:97-111): Linear -> LayerNorm([o]) -> ReLU.  Parameter names here are the
+    flat Sequential's ("0.weight", "0.bias", "1.weight", "1.bias"); the reference nests them under `.net` — reference
+    checkpoints load through nsvf_b200.checkpoint, which maps the names both ways.  The contraction runs on cuBLAS, everything else in the hand-written
     kernels of csrc/field_norm.cu: torch's own LayerNorm backward (GammaBetaBackwardCUDAKernel) plus the bias-gradient
     column reductions cost 0.5 ms per call on tall [65536, 256] activations, 40 % of the whole training step.  CUDA
     only, no fallback; the plain-torch composition lives in oracle/field_ref.py (test yardstick, CPU reference arm)."""

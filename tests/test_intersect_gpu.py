@@ -299,3 +299,14 @@ def test_ball_and_triangle_intersect_vs_reference(cuda, ref_ext):
                                                   torch.arange(480 * 3, device=cuda).view(-1, 3) * 0 +
                                                   torch.tensor([0, 1, 2], device=cuda), rs[:1], rd[:1])
     assert inds.shape == (1, rs.shape[1], 12) and depth.shape == (1, rs.shape[1], 12, 3)
+
+
+def test_aabb_sorted_on_an_empty_voxel_set(cuda):
+    """Everything pruned (n == 0): the sorted intersection returns all -1 / MAX_DEPTH and hits False, like the reference's
+    masked_fill + sort of an all-miss result (this used to raise in the middle of a training step)."""
+    rs = torch.randn(1, 100, 3, device=cuda)
+    rd = torch.nn.functional.normalize(torch.randn(1, 100, 3, device=cuda), dim=-1)
+    idx, dmin, dmax, hits = ours.aabb_intersect_sorted(rs, rd, torch.zeros(0, 3, device=cuda), 0.25, 7, 10000.0,
+                                                       shared_points=True)
+    assert idx.shape == (1, 100, 7) and bool((idx == -1).all()) and not bool(hits.any())
+    assert bool((dmin == 10000.0).all()) and bool((dmax == 10000.0).all())
