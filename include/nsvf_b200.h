@@ -61,7 +61,12 @@ NSVF_API int nsvf_ref_rcp(nsvf_stream_t stream, long long n, const float* x, flo
  *                        [b, n, 3] layout is points_batch_stride = 3 * n
  *   idx                : i32 [b, m, n_max]  first n_max hit voxels in ascending voxel index, then -1
  *   min_depth/max_depth: f32 [b, m, n_max]  entry / exit depth of each hit, 0 in unused slots
- * The outputs are fully written by the call (no pre-fill needed). */
+ * The outputs are fully written by the call (no pre-fill needed).
+ * How: voxel centres that lie on a regular lattice (every NSVF voxel set does) are scattered into a dense cell array
+ * and each ray walks the cells it passes through, running the reference's slab test on the occupied ones
+ * (csrc/voxel_grid.cu); any other point set goes through an 8-ary hierarchy of enclosing boxes
+ * (csrc/aabb_intersect.cu).  The choice is made on the device, per voxel set, and does not change results.
+ * Workspace: hierarchy + 16 cells (4 B each) per voxel. */
 NSVF_API size_t nsvf_aabb_workspace_bytes(int n, int n_trees /* 1 if points_batch_stride == 0 else b */);
 NSVF_API int nsvf_aabb_intersect(nsvf_stream_t stream, int b, int n, int m, float voxelsize, int n_max,
                         const float* ray_start, const float* ray_dir, const float* points,
@@ -90,6 +95,20 @@ NSVF_API int nsvf_sort_hits_by_depth(nsvf_stream_t stream, long long rays, int n
 NSVF_API int nsvf_aabb_hit_mask(nsvf_stream_t stream, int b, int n, int m, float voxelsize, const float* ray_start,
                                 const float* ray_dir, const float* points, long long points_batch_stride,
                                 unsigned char* hits, void* workspace, size_t workspace_bytes);
+
+/* The voxel set only changes when voxels are pruned or split (fairnr/modules/encoder.py:440-505), the rays change every
+ * call: nsvf_aabb_prepare fills a workspace of nsvf_aabb_workspace_bytes(n, n_sets) once (n_sets = 1 with
+ * points_batch_stride 0, else one set per batch row) and nsvf_aabb_intersect_prepared runs any of the three queries
+ * above on it without rebuilding — mode 0: nsvf_aabb_intersect (empty_depth ignored, hits may be NULL),
+ * 1: nsvf_aabb_intersect_sorted, 2: nsvf_aabb_hit_mask (idx / depths may be NULL).  `points` must be the centres the
+ * workspace was prepared from (the exact test reads them).  The one-shot entry points are prepare + this. */
+NSVF_API int nsvf_aabb_prepare(nsvf_stream_t stream, int n_sets, int n, float voxelsize, const float* points,
+                               long long points_batch_stride, void* workspace, size_t workspace_bytes);
+NSVF_API int nsvf_aabb_intersect_prepared(nsvf_stream_t stream, int mode, int b, int n, int m, float voxelsize,
+                                          int n_max, float empty_depth, const float* ray_start, const float* ray_dir,
+                                          const float* points, long long points_batch_stride, int* idx,
+                                          float* min_depth, float* max_depth, unsigned char* hits,
+                                          const void* workspace, size_t workspace_bytes);
 
 /* Replaces svo_intersect, fairnr/clib/src/intersect.cpp:84-112 + intersect_gpu.cu:170-237.
  *   points   : f32 [T, 3] node centres, children : i32 [T, 9] (slot 8 = node size in voxels, 1 = leaf),

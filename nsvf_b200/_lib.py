@@ -29,6 +29,10 @@ SIGNATURES = {
     "nsvf_sort_hits_by_depth": (c_int, [c_void_p, c_ll, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nsvf_aabb_hit_mask": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_ll,
                                    c_void_p, c_void_p, c_size_t]),
+    "nsvf_aabb_prepare": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_ll, c_void_p, c_size_t]),
+    "nsvf_aabb_intersect_prepared": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_float, c_void_p,
+                                             c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_size_t]),
     "nsvf_ball_intersect": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_ll,
                                     c_void_p, c_void_p, c_void_p]),
     "nsvf_triangle_intersect": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p,

@@ -83,10 +83,50 @@ def _aabb_args(ray_start, ray_dir, points, shared_points):
     return b, m, points.shape[1], points.shape[1] * 3, b
 
 
-def aabb_intersect_sorted(ray_start, ray_dir, points, voxelsize, n_max, empty_depth=10000.0, shared_points=False):
+class AabbIndex:
+    """A voxel set prepared for intersection (nsvf_aabb_prepare): the lattice / hierarchy workspace plus the centres it
+    was built from.  Build it once per voxel-set change and pass it as `index=` to the queries below."""
+
+    def __init__(self, points, voxelsize, shared_points=False):
+        _check_float_cuda(points=points)
+        self.points, self.voxelsize = points, float(voxelsize)
+        if shared_points:
+            self.n, self.stride, self.sets = points.shape[-2], 0, 1
+        else:
+            _chk(points.dim() == 3, "points must be [B, n, 3]")
+            self.n, self.stride, self.sets = points.shape[1], points.shape[1] * 3, points.shape[0]
+        with torch.cuda.device(points.device):
+            self.ws = _workspace(_L.nsvf_aabb_workspace_bytes(self.n, self.sets), points.device)
+            _lib.check(_L.nsvf_aabb_prepare(_lib.current_stream(points.device), self.sets, self.n, self.voxelsize,
+                                            _p(points), self.stride, _p(self.ws), self.ws.numel()))
+
+    def query(self, mode, ray_start, ray_dir, n_max, empty_depth):
+        _check_float_cuda(ray_start=ray_start, ray_dir=ray_dir)
+        b, m = ray_start.shape[0], ray_start.shape[1]
+        _chk(self.stride == 0 or b == self.sets, "one voxel set per batch row was prepared")
+        dev = ray_start.device
+        idx = dmin = dmax = None
+        if mode != 2:
+            idx, dmin, dmax = _hit_outputs(ray_start, int(n_max))
+        hits = torch.empty((b, m), dtype=torch.uint8, device=dev) if mode != 0 else None
+        with torch.cuda.device(dev):
+            _lib.check(_L.nsvf_aabb_intersect_prepared(
+                _lib.current_stream(dev), mode, b, self.n, m, self.voxelsize, int(n_max), float(empty_depth),
+                _p(ray_start), _p(ray_dir), _p(self.points), self.stride, _p(idx) if idx is not None else None,
+                _p(dmin) if dmin is not None else None, _p(dmax) if dmax is not None else None,
+                _p(hits) if hits is not None else None, _p(self.ws), self.ws.numel()))
+        return idx, dmin, dmax, hits
+
+
+def aabb_intersect_sorted(ray_start, ray_dir, points, voxelsize, n_max, empty_depth=10000.0, shared_points=False,
+                          index=None):
     """Extension (not in the reference _ext): aabb_intersect + the sort / fill / any() of
     SparseVoxelEncoder.ray_intersect (encoder.py:519-524) in one kernel.
-    -> idx i32, min_depth f32, max_depth f32 [B,M,n_max] sorted by entry depth, hits bool [B,M]."""
+    -> idx i32, min_depth f32, max_depth f32 [B,M,n_max] sorted by entry depth, hits bool [B,M].
+    `index` (AabbIndex of the same points) skips rebuilding the lattice / hierarchy."""
+    if index is not None:
+        idx, dmin, dmax, hits = index.query(1, ray_start, ray_dir, n_max, empty_depth)
+        return idx, dmin, dmax, hits.bool()
     b, m, n, stride, trees = _aabb_args(ray_start, ray_dir, points, shared_points)
     voxelsize, n_max = float(voxelsize), int(n_max)
     idx, dmin, dmax = _hit_outputs(ray_start, n_max)
@@ -112,8 +152,10 @@ def sort_hits_by_depth(idx, min_depth, max_depth, empty_depth=10000.0):
     return hits.bool()
 
 
-def aabb_hit_mask(ray_start, ray_dir, points, voxelsize, shared_points=False):
+def aabb_hit_mask(ray_start, ray_dir, points, voxelsize, shared_points=False, index=None):
     """Extension: hits bool [B,M] = any(aabb_intersect(...).idx != -1) without producing the hit lists."""
+    if index is not None:
+        return index.query(2, ray_start, ray_dir, 0, 0.0)[3].bool()
     b, m, n, stride, trees = _aabb_args(ray_start, ray_dir, points, shared_points)
     hits = torch.empty((b, m), dtype=torch.uint8, device=ray_start.device)
     with torch.cuda.device(ray_start.device):

@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "nsvf_b200.h"
+#include "voxel_grid.cuh"
 
 namespace nsvf {
 
@@ -322,8 +323,10 @@ aabb_intersect_kernel(const __grid_constant__ AabbTree tree, long long tree_stri
                       int n_max, int sort_slots, int list_cap, float empty_depth,
                       const float* __restrict__ ray_start, const float* __restrict__ ray_dir,
                       int* __restrict__ out_idx, float* __restrict__ out_min, float* __restrict__ out_max,
-                      unsigned char* __restrict__ out_hit) {
+                      unsigned char* __restrict__ out_hit, const unsigned char* __restrict__ grid_ws,
+                      size_t grid_set_bytes) {
   __shared__ __align__(8) uint64_t bar;
+  if (voxel_grid_usable(grid_ws, grid_set_bytes, blockIdx.y)) return;   // the lattice walk (voxel_grid.cu) has this set
   const int sm_nodes = tree.total - tree.stage_from;   // multiple of 32
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* gbox = tree.box + (long long)blockIdx.y * tree_stride_box;
@@ -487,7 +490,9 @@ __global__ void __launch_bounds__(kSmallThreads)
 aabb_small_kernel(const __grid_constant__ AabbTree tree, long long tree_stride_box, long long rays_per_tree, int n,
                   int n_max, const float* __restrict__ ray_start, const float* __restrict__ ray_dir,
                   int* __restrict__ out_idx, float* __restrict__ out_min, float* __restrict__ out_max,
-                  unsigned char* __restrict__ out_hit) {
+                  unsigned char* __restrict__ out_hit, const unsigned char* __restrict__ grid_ws,
+                  size_t grid_set_bytes) {
+  if (voxel_grid_usable(grid_ws, grid_set_bytes, blockIdx.y)) return;   // the lattice walk (voxel_grid.cu) has this set
   // stage the exact voxel boxes as 32-byte records {lo.xyz, hi.x | hi.yz, -, -}: one test = two LDS.128 broadcasts;
   // behind them the level-1 boxes (union of 8 consecutive voxels, widened by an ulp like every internal node): a ray
   // first tests the group and scans its 8 voxels only when the group is hit — ~2.4x fewer box tests at 343 voxels
@@ -615,7 +620,7 @@ template <int MODE>
 static int aabb_launch(cudaStream_t stream, dim3 grid, size_t smem, const AabbTree& tree, long long tree_stride_box,
                        long long rays_per_tree, int n_max, int sort_slots, int list_cap, float empty_depth,
                        const float* ray_start, const float* ray_dir, int* idx, float* dmin, float* dmax,
-                       unsigned char* hit) {
+                       unsigned char* hit, const unsigned char* grid_ws, size_t grid_set_bytes) {
   NSVF_CUDA_OK(cudaFuncSetAttribute(aabb_intersect_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     200 * 1024));
   const char* kname = MODE == kModeAnyHit ? "aabb_hit_mask_kernel"
@@ -623,7 +628,7 @@ static int aabb_launch(cudaStream_t stream, dim3 grid, size_t smem, const AabbTr
   NSVF_TIMED_LAUNCH(kname, stream,
                     (aabb_intersect_kernel<MODE><<<grid, kAabbWarps * 32, smem, stream>>>(
                         tree, tree_stride_box, rays_per_tree, n_max, sort_slots, list_cap, empty_depth, ray_start,
-                        ray_dir, idx, dmin, dmax, hit)));
+                        ray_dir, idx, dmin, dmax, hit, grid_ws, grid_set_bytes)));
   return 0;
 }
 
@@ -631,9 +636,13 @@ static int aabb_launch(cudaStream_t stream, dim3 grid, size_t smem, const AabbTr
 
 using namespace nsvf;
 
+static size_t aabb_tree_bytes(int n, int n_trees) {   // all hierarchies, rounded so that the lattices behind stay aligned
+  return (aabb_tree_floats(n) * sizeof(float) * (size_t)n_trees + 127) / 128 * 128;
+}
+
 extern "C" size_t nsvf_aabb_workspace_bytes(int n, int n_trees) {
   if (n <= 0 || n_trees <= 0) return 0;
-  return aabb_tree_floats(n) * sizeof(float) * (size_t)n_trees;
+  return aabb_tree_bytes(n, n_trees) + voxel_grid_bytes(n) * (size_t)n_trees;
 }
 
 // mode: 0 = reference order (ascending voxel index), 1 = sorted by entry depth, 2 = any-hit mask only
@@ -644,14 +653,19 @@ __global__ void fill_f32_kernel(float* __restrict__ a, float* __restrict__ b, lo
   }
 }
 
-static int aabb_run(cudaStream_t stream, int mode, int b, int n, int m, float voxelsize, int n_max, float empty_depth,
-                    const float* ray_start, const float* ray_dir, const float* points,
+// phase: kBuild fills the workspace (hierarchy + lattice of every voxel set), kTraverse intersects rays with a filled one
+enum { kBuild = 1, kTraverse = 2 };
+
+static int aabb_run(cudaStream_t stream, int phase, int mode, int b, int n, int m, float voxelsize, int n_max,
+                    float empty_depth, const float* ray_start, const float* ray_dir, const float* points,
                     long long points_batch_stride, int* idx, float* min_depth, float* max_depth,
                     unsigned char* hit, void* workspace, size_t workspace_bytes) {
   NSVF_REQUIRE(b >= 0 && n >= 0 && m >= 0 && n_max >= 0, "aabb_intersect: negative size");
-  if (b == 0 || m == 0) return 0;
-  if (mode != kModeAnyHit && n_max == 0) return 0;
+  const bool traverse = (phase & kTraverse) != 0;
+  if (traverse && (b == 0 || m == 0)) return 0;
+  if (traverse && mode != kModeAnyHit && n_max == 0) return 0;
   const long long rays = (long long)b * m;
+  if (n == 0 && !traverse) return 0;
   if (n == 0) {  // nothing to hit
     if (mode != kModeAnyHit) {
       NSVF_CUDA_OK(cudaMemsetAsync(idx, 0xff, sizeof(int) * rays * n_max, stream));
@@ -676,12 +690,24 @@ static int aabb_run(cudaStream_t stream, int mode, int b, int n, int m, float vo
                "aabb_intersect: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
   NSVF_REQUIRE(((uintptr_t)workspace & 127) == 0, "aabb_intersect: workspace must be 128-byte aligned");
 
+  // the voxel lattice and its walk (voxel_grid.cu); when the voxel set is not a lattice the walk returns at once and
+  // the hierarchy kernels below do the work — and the other way round
+  const size_t grid_set_bytes = voxel_grid_bytes(n);
+  unsigned char* grid_ws = grid_set_bytes ? (unsigned char*)workspace + aabb_tree_bytes(n, n_trees) : nullptr;
+  if (grid_ws != nullptr && (phase & kBuild) &&
+      voxel_grid_build(stream, n_trees, n, points, points_batch_stride, voxelsize, grid_ws, grid_set_bytes))
+    return 1;
+  if (grid_ws != nullptr && traverse &&
+      voxel_grid_walk(stream, mode, grid_ws, grid_set_bytes, n_trees, n, points, points_batch_stride, voxelsize,
+                      n_trees == 1 ? rays : m, n_max, empty_depth, ray_start, ray_dir, idx, min_depth, max_depth, hit))
+    return 1;
+
   AabbLayout L = aabb_layout(n);
   float* box = (float*)workspace;
   const long long tree_stride_box = (long long)6 * L.total;
   const float half_voxel = voxelsize * 0.5f;  // reference: float half_voxel = voxelsize * 0.5 (exact)
 
-  {  // build the hierarchy (O(n), one small launch per level)
+  if (phase & kBuild) {  // build the hierarchy (O(n), one small launch per level)
     const int n_pad = (n + 31) / 32 * 32;
     dim3 g0((n_pad + 255) / 256, n_trees);
     aabb_build_leaves_kernel<<<g0, 256, 0, stream>>>(points, points_batch_stride, n, half_voxel, box, tree_stride_box,
@@ -695,6 +721,8 @@ static int aabb_run(cudaStream_t stream, int mode, int b, int n, int m, float vo
       NSVF_LAUNCH_OK("aabb_build_up_kernel");
     }
   }
+
+  if (!traverse) return 0;
 
   AabbTree tree;
   tree.box = box;
@@ -731,11 +759,13 @@ static int aabb_run(cudaStream_t stream, int mode, int b, int n, int m, float vo
     if (mode == kModeAnyHit) {
       NSVF_TIMED_LAUNCH("aabb_hit_mask_kernel", stream,
                         (aabb_small_kernel<kModeAnyHit><<<gs, kSmallThreads, sm, stream>>>(
-                            tree, tree_stride_box, rays_per_tree, n, 1, ray_start, ray_dir, idx, min_depth, max_depth, hit)));
+                            tree, tree_stride_box, rays_per_tree, n, 1, ray_start, ray_dir, idx, min_depth, max_depth, hit,
+                            grid_ws, grid_set_bytes)));
     } else {
       NSVF_TIMED_LAUNCH("aabb_intersect_kernel", stream,
                         (aabb_small_kernel<kModeIndexOrder><<<gs, kSmallThreads, sm, stream>>>(
-                            tree, tree_stride_box, rays_per_tree, n, n_max, ray_start, ray_dir, idx, min_depth, max_depth, hit)));
+                            tree, tree_stride_box, rays_per_tree, n, n_max, ray_start, ray_dir, idx, min_depth, max_depth, hit,
+                            grid_ws, grid_set_bytes)));
     }
     return 0;
   }
@@ -743,13 +773,16 @@ static int aabb_run(cudaStream_t stream, int mode, int b, int n, int m, float vo
   switch (mode) {
     case kModeIndexOrder:
       return aabb_launch<kModeIndexOrder>(stream, grid, smem, tree, tree_stride_box, rays_per_tree, nm, sort_slots,
-                                          list_cap, empty_depth, ray_start, ray_dir, idx, min_depth, max_depth, hit);
+                                          list_cap, empty_depth, ray_start, ray_dir, idx, min_depth, max_depth, hit, grid_ws,
+                                          grid_set_bytes);
     case kModeDepthSorted:
       return aabb_launch<kModeDepthSorted>(stream, grid, smem, tree, tree_stride_box, rays_per_tree, nm, sort_slots,
-                                           list_cap, empty_depth, ray_start, ray_dir, idx, min_depth, max_depth, hit);
+                                           list_cap, empty_depth, ray_start, ray_dir, idx, min_depth, max_depth, hit, grid_ws,
+                                          grid_set_bytes);
     default:
       return aabb_launch<kModeAnyHit>(stream, grid, smem, tree, tree_stride_box, rays_per_tree, nm, sort_slots,
-                                      list_cap, empty_depth, ray_start, ray_dir, idx, min_depth, max_depth, hit);
+                                      list_cap, empty_depth, ray_start, ray_dir, idx, min_depth, max_depth, hit, grid_ws,
+                                          grid_set_bytes);
   }
 }
 
@@ -757,7 +790,7 @@ extern "C" int nsvf_aabb_intersect(nsvf_stream_t stream, int b, int n, int m, fl
                                    const float* ray_start, const float* ray_dir, const float* points,
                                    long long points_batch_stride, int* idx, float* min_depth, float* max_depth,
                                    void* workspace, size_t workspace_bytes) {
-  return aabb_run((cudaStream_t)stream, kModeIndexOrder, b, n, m, voxelsize, n_max, 0.0f, ray_start, ray_dir, points,
+  return aabb_run((cudaStream_t)stream, kBuild | kTraverse, kModeIndexOrder, b, n, m, voxelsize, n_max, 0.0f, ray_start, ray_dir, points,
                   points_batch_stride, idx, min_depth, max_depth, nullptr, workspace, workspace_bytes);
 }
 
@@ -766,15 +799,34 @@ extern "C" int nsvf_aabb_intersect_sorted(nsvf_stream_t stream, int b, int n, in
                                           const float* points, long long points_batch_stride, int* idx,
                                           float* min_depth, float* max_depth, unsigned char* hits, void* workspace,
                                           size_t workspace_bytes) {
-  return aabb_run((cudaStream_t)stream, kModeDepthSorted, b, n, m, voxelsize, n_max, empty_depth, ray_start, ray_dir,
+  return aabb_run((cudaStream_t)stream, kBuild | kTraverse, kModeDepthSorted, b, n, m, voxelsize, n_max, empty_depth, ray_start, ray_dir,
                   points, points_batch_stride, idx, min_depth, max_depth, hits, workspace, workspace_bytes);
 }
 
 extern "C" int nsvf_aabb_hit_mask(nsvf_stream_t stream, int b, int n, int m, float voxelsize, const float* ray_start,
                                   const float* ray_dir, const float* points, long long points_batch_stride,
                                   unsigned char* hits, void* workspace, size_t workspace_bytes) {
-  return aabb_run((cudaStream_t)stream, kModeAnyHit, b, n, m, voxelsize, 0, 0.0f, ray_start, ray_dir, points,
+  return aabb_run((cudaStream_t)stream, kBuild | kTraverse, kModeAnyHit, b, n, m, voxelsize, 0, 0.0f, ray_start, ray_dir, points,
                   points_batch_stride, nullptr, nullptr, nullptr, hits, workspace, workspace_bytes);
+}
+
+extern "C" int nsvf_aabb_prepare(nsvf_stream_t stream, int n_sets, int n, float voxelsize, const float* points,
+                                 long long points_batch_stride, void* workspace, size_t workspace_bytes) {
+  NSVF_REQUIRE(n_sets >= 1 && (points_batch_stride != 0 || n_sets == 1),
+               "aabb_prepare: a shared voxel set (points_batch_stride 0) is one set");
+  return aabb_run((cudaStream_t)stream, kBuild, kModeIndexOrder, n_sets, n, 0, voxelsize, 0, 0.0f, nullptr, nullptr,
+                  points, points_batch_stride, nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes);
+}
+
+extern "C" int nsvf_aabb_intersect_prepared(nsvf_stream_t stream, int mode, int b, int n, int m, float voxelsize,
+                                            int n_max, float empty_depth, const float* ray_start,
+                                            const float* ray_dir, const float* points, long long points_batch_stride,
+                                            int* idx, float* min_depth, float* max_depth, unsigned char* hits,
+                                            const void* workspace, size_t workspace_bytes) {
+  NSVF_REQUIRE(mode >= 0 && mode <= 2, "aabb_intersect_prepared: mode must be 0 (index order), 1 (sorted) or 2 (any hit)");
+  return aabb_run((cudaStream_t)stream, kTraverse, mode, b, n, m, voxelsize, mode == kModeAnyHit ? 0 : n_max,
+                  mode == kModeDepthSorted ? empty_depth : 0.0f, ray_start, ray_dir, points, points_batch_stride, idx,
+                  min_depth, max_depth, hits, const_cast<void*>(workspace), workspace_bytes);
 }
 
 extern "C" int nsvf_sort_hits_by_depth(nsvf_stream_t stream_, long long rays, int n_max, float empty_depth, int* idx,

@@ -49,7 +49,7 @@ class SparseVoxelEncoder(nn.Module):
         # buys a wasted d/dxyz in every backward.  Set True for normal-based fields.
         self.track_xyz_grad = track_xyz_grad
         self._runtime_caches = {"flatten_centers": None, "flatten_children": None, "max_voxel_probs": None,
-                                "geometry": None, "voxel_size_float": None}
+                                "geometry": None, "voxel_size_float": None, "aabb_index": None, "max_hits_int": None}
         self.values = nn.Embedding(int(self.num_keys), voxel_embed_dim)
         nn.init.normal_(self.values.weight, mean=0, std=voxel_embed_dim ** -0.5)   # module_utils.py:23-26
 
@@ -109,6 +109,7 @@ class SparseVoxelEncoder(nn.Module):
     def invalidate_geometry_cache(self):
         """Called by every method that changes the voxel set (pruning, splitting, state loading)."""
         self._runtime_caches["geometry"] = None
+        self._runtime_caches["aabb_index"] = None
 
     def _kept_geometry(self):
         """(feats i64, feats i32, points with the x shift) of the kept voxels.  The reference boolean-indexes feats /
@@ -144,6 +145,18 @@ class SparseVoxelEncoder(nn.Module):
             return cache[2]
         return ops.as_int32_feats(point_feats.reshape(-1, 8)).contiguous()
 
+    def _aabb_index(self, point_xyz):
+        """The prepared voxel set (lattice / hierarchy workspace, clib._ext.AabbIndex) of `point_xyz` [S, H, 3]: rebuilt
+        only when the centres change (pruning, splitting, loading), not on every forward — the reference rescans the
+        voxels per call, round 1 rebuilt its hierarchy per call."""
+        pts = point_xyz.float().contiguous()
+        key = (pts.data_ptr(), pts._version, tuple(pts.shape), self._voxel_size_float())
+        cache = self._runtime_caches.get("aabb_index")
+        if cache is None or cache[0] != key:
+            cache = (key, clib._ext.AabbIndex(pts, key[3]))
+            self._runtime_caches["aabb_index"] = cache
+        return cache[1]
+
     def ray_intersect(self, ray_start, ray_dir, encoder_states):
         point_feats = encoder_states["voxel_vertex_idx"]
         point_xyz = encoder_states["voxel_center_xyz"]
@@ -159,7 +172,7 @@ class SparseVoxelEncoder(nn.Module):
             if centers.dim() == 2:
                 centers, children = centers.unsqueeze(0), children.unsqueeze(0)
             pts_idx, min_depth, max_depth = clib.svo_ray_intersect(
-                self.voxel_size, self.max_hits, centers, children, ray_start, ray_dir)
+                self._voxel_size_float(), self._max_hits_int(), centers, children, ray_start, ray_dir)
             # masked_fill + sort by entry depth + gather + any() (encoder.py:519-524) as one in-place kernel; fp16 models
             # get their depths cast to fp32 for it and back afterwards (no eager-torch path)
             in_dtype = min_depth.dtype
@@ -170,9 +183,10 @@ class SparseVoxelEncoder(nn.Module):
                 min_depth, max_depth = min_depth.to(in_dtype), max_depth.to(in_dtype)
         else:
             # intersection + masked_fill + sort + gather + any() of encoder.py:511-524 in ONE kernel
+            index = self._aabb_index(point_xyz)
             pts_idx, min_depth, max_depth, hits = clib._ext.aabb_intersect_sorted(
-                ray_start.float(), ray_dir.float(), point_xyz.float().contiguous(), self.voxel_size, self.max_hits,
-                MAX_DEPTH)
+                ray_start.float(), ray_dir.float(), index.points, index.voxelsize, self._max_hits_int(), MAX_DEPTH,
+                index=index)
             min_depth, max_depth = min_depth.type_as(ray_start), max_depth.type_as(ray_start)
         if S > 1:
             pts_idx = (pts_idx + H * torch.arange(S, device=pts_idx.device, dtype=pts_idx.dtype)[:, None, None]
@@ -188,8 +202,8 @@ class SparseVoxelEncoder(nn.Module):
         S, V, P, _ = ray_dir.size()
         ray_start = ray_start.expand_as(ray_dir).contiguous().view(S, V * P, 3).contiguous()
         ray_dir = ray_dir.reshape(S, V * P, 3).contiguous()
-        hits = clib._ext.aabb_hit_mask(ray_start.float(), ray_dir.float(), point_xyz.float().contiguous(),
-                                       self.voxel_size)
+        index = self._aabb_index(point_xyz)
+        hits = clib._ext.aabb_hit_mask(ray_start.float(), ray_dir.float(), index.points, index.voxelsize, index=index)
         return ray_start, ray_dir, hits
 
     def ray_sample(self, intersection_outputs, trimmed=False, lazy=False):
@@ -237,6 +251,15 @@ class SparseVoxelEncoder(nn.Module):
                                                 point_xyz.reshape(-1, 3), values.reshape(-1, values.size(-1)),
                                                 self._voxel_size_float())
         return inputs
+
+    def _max_hits_int(self):
+        """int(self.max_hits) without a device sync per call."""
+        key = (self.max_hits.data_ptr(), self.max_hits._version)
+        cache = self._runtime_caches.get("max_hits_int")
+        if cache is None or cache[0] != key:
+            cache = (key, int(self.max_hits))
+            self._runtime_caches["max_hits_int"] = cache
+        return cache[1]
 
     def _voxel_size_float(self):
         """float(self.voxel_size) without a device sync per call (the buffer lives on the GPU)."""

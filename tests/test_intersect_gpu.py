@@ -310,3 +310,93 @@ def test_aabb_sorted_on_an_empty_voxel_set(cuda):
                                                        shared_points=True)
     assert idx.shape == (1, 100, 7) and bool((idx == -1).all()) and not bool(hits.any())
     assert bool((dmin == 10000.0).all()) and bool((dmax == 10000.0).all())
+
+
+def _both_paths(fn):
+    """Run fn() with the lattice walk (default) and with the hierarchy kernels only (NSVF_AABB_NO_GRID)."""
+    import os
+    walk = fn()
+    os.environ["NSVF_AABB_NO_GRID"] = "1"
+    try:
+        tree = fn()
+    finally:
+        del os.environ["NSVF_AABB_NO_GRID"]
+    return walk, tree
+
+
+def _awkward_rays(pts, vs, n, cuda, seed=11):
+    """Camera-like rays plus origins inside the set, on cell corners / faces, axis-parallel and zero components."""
+    g = torch.Generator().manual_seed(seed)
+    o = torch.randn(n, 3, generator=g)
+    o = o / o.norm(dim=-1, keepdim=True) * 4.5
+    d = (torch.rand(n, 3, generator=g) * 2 - 1) - o
+    k = n // 8
+    o[:k] = torch.rand(k, 3, generator=g) - 0.5                                   # inside the voxel set
+    pick = torch.randint(0, pts.shape[0], (2 * k,), generator=g)
+    o[k:3 * k] = pts.cpu()[pick] + vs * 0.5                                        # exactly on cell corners
+    axis = torch.eye(3)[torch.randint(0, 3, (k,), generator=g)] * (torch.randint(0, 2, (k, 1), generator=g) * 2 - 1)
+    d[k:2 * k] = axis                                                               # along lattice edges
+    d[3 * k:4 * k, 1] = 0.0
+    d[4 * k:4 * k + 8, 2] = -0.0
+    d[4 * k + 8] = 0.0                                                              # no direction at all
+    d[4 * k + 9, 0] = float("nan")
+    o[4 * k + 10, 1] = float("inf")
+    d[4 * k + 11] = torch.tensor([1e-30, 1e-30, 1e-30])
+    o[4 * k + 12] = torch.tensor([3e6, 0.0, 0.0])                                   # too far for the walk: scans all voxels
+    d = torch.where(d.norm(dim=-1, keepdim=True) > 0, d / d.norm(dim=-1, keepdim=True), d)
+    return o.to(cuda)[None].contiguous(), d.to(cuda)[None].contiguous()
+
+
+@pytest.mark.parametrize("times,n_max", [(0, 60), (1, 90), (2, 135), (1, 6)])
+def test_lattice_walk_equals_hierarchy_and_reference(cuda, ref_ext, times, n_max):
+    """voxel_grid.cu (cells along the ray, exact test on the occupied ones) against the hierarchy kernels and the
+    reference scan: all three modes, awkward rays, rows that overflow n_max."""
+    pts0 = synthetic.carve_shell(synthetic.bbox_voxels([-1.2] * 3, [1.2] * 3, 0.4))
+    p, vs = synthetic.split_points(pts0, 0.4, times)
+    p[:, 0] += np.float32(vs / 10)
+    pts = torch.from_numpy(p).to(cuda)
+    rs, rd = _awkward_rays(pts, vs, 4096, cuda)
+    walk, tree = _both_paths(lambda: ours.aabb_intersect(rs, rd, pts, vs, n_max, shared_points=True))
+    _cmp3(walk, tree, "index order: walk vs hierarchy")
+    _cmp3(walk, ref_ext.aabb_intersect(rs, rd, pts[None].contiguous(), vs, n_max), "index order: walk vs reference CUDA")
+    walk, tree = _both_paths(lambda: ours.aabb_intersect_sorted(rs, rd, pts, vs, n_max, 10000.0, shared_points=True))
+    _cmp3(walk[:3], tree[:3], "sorted: walk vs hierarchy")
+    assert torch.equal(walk[3], tree[3])
+    walk_m, tree_m = _both_paths(lambda: ours.aabb_hit_mask(rs, rd, pts, vs, shared_points=True))
+    assert torch.equal(walk_m, tree_m) and torch.equal(walk_m, walk[3])
+    if n_max == 6:
+        assert int((walk[0] >= 0).sum(-1).max()) == 6      # overflowing rows exist
+    # a voxel set prepared once serves any number of queries (nsvf_aabb_prepare / _intersect_prepared)
+    index = ours.AabbIndex(pts, vs, shared_points=True)
+    for sl in (slice(0, 4096), slice(1000, 3000)):
+        a = ours.aabb_intersect_sorted(rs[:, sl].contiguous(), rd[:, sl].contiguous(), pts, vs, n_max, 10000.0, index=index)
+        _cmp3(a[:3], [t[:, sl] for t in walk[:3]], "prepared index vs one-shot")
+        assert torch.equal(a[3], walk[3][:, sl])
+        assert torch.equal(ours.aabb_hit_mask(rs[:, sl].contiguous(), rd[:, sl].contiguous(), pts, vs, index=index), walk_m[:, sl])
+    # per-batch voxel sets (one lattice per set)
+    B = 2
+    ptsB = torch.stack([pts, pts + 0.37])
+    rsB, rdB = rs.view(B, -1, 3).contiguous(), rd.view(B, -1, 3).contiguous()
+    walk, tree = _both_paths(lambda: ours.aabb_intersect_sorted(rsB, rdB, ptsB, vs, n_max, 10000.0))
+    _cmp3(walk[:3], tree[:3], "sorted, two voxel sets: walk vs hierarchy")
+
+
+def test_voxel_sets_off_the_lattice_use_the_hierarchy(cuda, ref_ext):
+    """Jittered centres, duplicate centres and a set too sparse for the cell budget are not lattices: the device-side
+    check hands them to the hierarchy kernels, results stay the reference's."""
+    scene = synthetic.make_scene("C2")
+    pts, _, _ = helpers.scene_tensors(scene, cuda)
+    o, d = helpers.rays_for("C2", 4096, 9, cuda)
+    rs, rd = o[None].contiguous(), d[None].contiguous()
+    g = torch.Generator().manual_seed(3)
+    jitter = pts + (torch.rand(pts.shape, generator=g).to(cuda) - 0.5) * 0.1
+    twice = torch.cat([pts, pts[:17]])
+    sparse = torch.cat([pts, pts[:4] + 400.0 * scene.voxel_size])
+    for name, p in (("jittered", jitter), ("duplicates", twice), ("sparse", sparse)):
+        p = p[None].contiguous()
+        _cmp3(ours.aabb_intersect(rs, rd, p, scene.voxel_size, 60), ref_ext.aabb_intersect(rs, rd, p, scene.voxel_size, 60),
+              name + " vs reference CUDA")
+        r_idx, r_min, r_max, r_hits = wrappers.sort_hits(*ref_ext.aabb_intersect(rs, rd, p, scene.voxel_size, 60))
+        idx, dmin, dmax, hits = ours.aabb_intersect_sorted(rs, rd, p, scene.voxel_size, 60, 10000.0)
+        assert torch.equal(hits, r_hits) and torch.equal(dmin, r_min) and torch.equal(idx.sort(-1)[0], r_idx.sort(-1)[0])
+        assert torch.equal(ours.aabb_hit_mask(rs, rd, p, scene.voxel_size), r_hits)
