@@ -272,7 +272,10 @@ NSVF_API int nsvf_composite_bwd(nsvf_stream_t stream, long long B, int K, const 
  *                            order boolean indexing produces): out_vox i32 [M], out_xyz f32 [M,3] = ray_start +
  *                            ray_dir * depth, out_dir f32 [M,3], out_dists f32 [M] (either optional), and
  *                            ray_off i32 [B+1] = exclusive offsets of the rays in that order.  launch_no = number of
- *                            earlier nsvf_march_compact launches on this plan (0, 1, 2, ...).
+ *                            earlier nsvf_march_compact launches on this plan (0, 1, 2, ...).  start = -1: the window
+ *                            is the one the preceding nsvf_march_epilogue (schedule_next) left in the plan, so the
+ *                            launch can be queued BEFORE the host has read that window back; the outputs must then
+ *                            hold max(chunk_size, B) rows (nothing is written if the schedule is finished).
  *   nsvf_march_epilogue    : sigma f32 [M] (+ noise f32 [M] or NULL, dists f32 [M]) -> feT f32 [K][B],
  *                            texture f32 [M,3] -> texT f32 [K][B][3] at the window's slots; eval_len i32 [B] =
  *                            evaluated prefix; with tolerance > 0: acc_free_energy f32 [B] += row sums, early_stop

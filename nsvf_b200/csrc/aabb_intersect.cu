@@ -694,9 +694,13 @@ static int aabb_run(cudaStream_t stream, int phase, int mode, int b, int n, int 
   // the hierarchy kernels below do the work — and the other way round
   const size_t grid_set_bytes = voxel_grid_bytes(n);
   unsigned char* grid_ws = grid_set_bytes ? (unsigned char*)workspace + aabb_tree_bytes(n, n_trees) : nullptr;
+  // index-order queries stay on the hierarchy, which produces that order natively (the walk finds hits in depth order
+  // and would have to sort ~76 indices per ray at 112 k voxels: measured 13.2 ms against 2.3 ms)
+  if (phase == (kBuild | kTraverse) && mode == kModeIndexOrder) grid_ws = nullptr;
   if (grid_ws != nullptr && (phase & kBuild) &&
       voxel_grid_build(stream, n_trees, n, points, points_batch_stride, voxelsize, grid_ws, grid_set_bytes))
     return 1;
+  if (mode == kModeIndexOrder) grid_ws = nullptr;
   if (grid_ws != nullptr && traverse &&
       voxel_grid_walk(stream, mode, grid_ws, grid_set_bytes, n_trees, n, points, points_batch_stride, voxelsize,
                       n_trees == 1 ? rays : m, n_max, empty_depth, ray_start, ray_dir, idx, min_depth, max_depth, hit))

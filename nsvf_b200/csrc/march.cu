@@ -303,6 +303,11 @@ march_compact_kernel(long long B, long long ldb, int K, int start, int end, cons
   __shared__ unsigned sh_tile, sh_base;
   __shared__ int sh_warp[kTile / 32], sh_total;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (start < 0) {   // the window the previous epilogue scheduled: launched before the host has read it back
+    const volatile int* hdr = plan;
+    start = hdr[H_START];
+    end = hdr[H_DONE] ? start : hdr[H_END];
+  }
   if (tid == 0) sh_tile = atomicAdd(reinterpret_cast<unsigned*>(plan + H_TICKET), 1u) - ticket_base;
   __syncthreads();
   const unsigned tile = sh_tile;
@@ -641,7 +646,7 @@ extern "C" int nsvf_march_compact(nsvf_stream_t stream_, long long B, int K, int
                                   float* out_xyz, float* out_dir, float* out_dists, int* ray_off, void* plan,
                                   int launch_no) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  NSVF_REQUIRE(B >= 0 && K >= 0 && start >= 0 && start <= end && end <= K && launch_no >= 0,
+  NSVF_REQUIRE(B >= 0 && K >= 0 && (start == -1 || (start >= 0 && start <= end && end <= K)) && launch_no >= 0,
                "march_compact: bad sizes");
   if (B == 0) return 0;
   const long long tiles = plan_tiles(B);

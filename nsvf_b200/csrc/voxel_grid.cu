@@ -17,7 +17,8 @@
 //     tolerance), are CANDIDATES — a superset of the reference's hits; the exact test decides.  Hits are appended to
 //     the ray's row as they come; a (depth, index) order violation (grazing hits, ties) is noticed on the fly and
 //     repaired by an insertion sort of that row; rows that overflow n_max keep the n_max smallest voxel indices exactly
-//     like the reference's index-order scan.  Rays the walk cannot trust (non-finite, zero or extreme direction, origin
+//     like the reference's index-order scan.  Serves the depth-sorted and the any-hit query; the plain index-order
+//     query stays on the hierarchy (it would need a full sort of every row by index).  Rays the walk cannot trust (non-finite, zero or extreme direction, origin
 //     more than 1e5 cells away) scan all voxels like the reference does.
 //   * the unused tail of 32 consecutive rows (-1 / fill depth) is written cooperatively by the warp (coalesced).
 #include <cstdlib>
@@ -182,7 +183,7 @@ int voxel_grid_build(cudaStream_t stream, int n_sets, int n, const float* points
 }
 
 // ---- the walk ------------------------------------------------------------------------------------------------------
-enum { kWalkIndexOrder = 0, kWalkDepthSorted = 1, kWalkAnyHit = 2 };
+enum { kWalkDepthSorted = 1, kWalkAnyHit = 2 };   // mode numbers of aabb_intersect.cu; index order (0) is not walked
 
 __device__ __forceinline__ float pick3(int k, float a0, float a1, float a2) { return k == 0 ? a0 : (k == 1 ? a1 : a2); }
 __device__ __forceinline__ int pick3(int k, int a0, int a1, int a2) { return k == 0 ? a0 : (k == 1 ? a1 : a2); }
@@ -210,7 +211,7 @@ __device__ __forceinline__ bool walk_test(const WalkRay& r, const float* __restr
   return slab_exact(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, lx, ly, lz, hx, hy, hz, tn, tf);
 }
 
-// Per-ray hit list under construction, living in the ray's own output row.
+// Per-ray hit list under construction, living in the ray's own output row (global memory).
 template <int MODE>
 struct WalkRow {
   int* idx;
@@ -221,17 +222,25 @@ struct WalkRow {
   float last_tn;
   int last_v;
 
+  __device__ __forceinline__ void reset(int n_max_) {
+    n_max = n_max_;
+    cnt = 0;
+    unsorted = false;
+    last_tn = 0.f;
+    last_v = -1;
+  }
+  __device__ __forceinline__ void note_order(int v, float tn) {
+    if (cnt > 0 && (tn < last_tn || (tn == last_tn && v < last_v))) unsorted = true;
+    last_tn = tn;
+    last_v = v;
+  }
   __device__ __forceinline__ void add(int v, float tn, float tf) {
     if (MODE == kWalkAnyHit) { cnt = 1; return; }
     if (cnt < n_max) {
       idx[cnt] = v;
-      if (MODE == kWalkDepthSorted) {
-        dmin[cnt] = tn;
-        dmax[cnt] = tf;
-        if (cnt > 0 && (tn < last_tn || (tn == last_tn && v < last_v))) unsorted = true;
-        last_tn = tn;
-        last_v = v;
-      }
+      dmin[cnt] = tn;
+      dmax[cnt] = tf;
+      note_order(v, tn);
       ++cnt;
       return;
     }
@@ -242,57 +251,69 @@ struct WalkRow {
       if (w > worst) { worst = w; at = s; }
     }
     if (v < worst) {
-      idx[at] = v;
-      if (MODE == kWalkDepthSorted) { dmin[at] = tn; dmax[at] = tf; unsorted = true; }
+      idx[at] = v; dmin[at] = tn; dmax[at] = tf;
+      unsorted = true;
+    }
+  }
+  // insertion sort of the row by (depth, index): only after an order violation was seen
+  __device__ __forceinline__ void repair() {
+    for (int s = 1; s < cnt; ++s) {
+      const int v = idx[s];
+      const float tn = dmin[s], tf = dmax[s];
+      int t = s - 1;
+      while (t >= 0) {
+        const float e = dmin[t];
+        const int w = idx[t];
+        if (!(e > tn || (e == tn && w > v))) break;
+        idx[t + 1] = w; dmin[t + 1] = e; dmax[t + 1] = dmax[t];
+        --t;
+      }
+      idx[t + 1] = v; dmin[t + 1] = tn; dmax[t + 1] = tf;
     }
   }
 };
 
-template <int MODE>
-__device__ __forceinline__ void walk_one(const VoxelGridHeader* __restrict__ h, const float* __restrict__ pts, int n,
-                                         float hv, float voxelsize, const WalkRay& r, float dx, float dy, float dz,
-                                         WalkRow<MODE>& row) {
-  const int* __restrict__ cell = reinterpret_cast<const int*>(h + 1);
-  const int nx = h->dims[0], ny = h->dims[1], nz = h->dims[2];
-  const float gx = float_from_order_key(h->min_key[0]), gy = float_from_order_key(h->min_key[1]),
-              gz = float_from_order_key(h->min_key[2]);
-  // lattice coordinates: cell i covers [i, i + 1)
-  const float ux = __fdiv_rn(r.ox - gx, voxelsize) + 0.5f, uy = __fdiv_rn(r.oy - gy, voxelsize) + 0.5f,
-              uz = __fdiv_rn(r.oz - gz, voxelsize) + 0.5f;
-  const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
-  const float am = fmaxf(ax, fmaxf(ay, az));
-  const bool finite = fabsf(r.ox) <= 3.0e38f && fabsf(r.oy) <= 3.0e38f && fabsf(r.oz) <= 3.0e38f && ax <= 3.0e38f &&
-                      ay <= 3.0e38f && az <= 3.0e38f;
-  const float far = fmaxf(fabsf(ux), fmaxf(fabsf(uy), fabsf(uz)));
-  if (!(finite && am >= 1.0e-18f && am <= 1.0e18f && far <= 1.0e5f)) {
-    // not a ray the walk can reason about: scan all voxels in index order like the reference
-    for (int v = 0; v < n; ++v) {
-      float tn, tf;
-      if (walk_test(r, pts, v, hv, tn, tf)) {
-        row.add(v, tn, tf);
-        if (MODE == kWalkAnyHit) return;
-      }
-    }
-    return;
-  }
-  const int m = (ay > ax) ? ((az > ay) ? 2 : 1) : ((az > ax) ? 2 : 0);
-  const int p = m == 2 ? 0 : m + 1, q = p == 2 ? 0 : p + 1;
-  const float um0 = pick3(m, ux, uy, uz), up0 = pick3(p, ux, uy, uz), uq0 = pick3(q, ux, uy, uz);
-  const float dm = pick3(m, dx, dy, dz), dp = pick3(p, dx, dy, dz), dq = pick3(q, dx, dy, dz);
-  const int nm = pick3(m, nx, ny, nz), np = pick3(p, nx, ny, nz), nq = pick3(q, nx, ny, nz);
-  const int sx = ny * nz, sy = nz;
-  const int sm = pick3(m, sx, sy, 1), sp = pick3(p, sx, sy, 1), sq = pick3(q, sx, sy, 1);
-  const float inv_dm = __fdiv_rn(1.0f, dm);
-  const float slope_p = dp * inv_dm, slope_q = dq * inv_dm;   // |slope| <= 1
-  // candidate margin in cells: lattice tolerance + rounding of the reference's test and of this walk (both grow with
-  // the distance of the origin, ~1e-7 relative)
-  const float eps = 4.0e-3f + 4.0e-6f * (fabsf(um0) + fabsf(up0) + fabsf(uq0) + (float)(nm + np + nq));
-  const bool fwd = dm > 0.0f;
-  const int step = fwd ? 1 : -1;
-  // layers in which both minor coordinates can be inside the lattice (two cells of slack; an almost constant minor
-  // coordinate drifts by less than two cells over the representable range)
-  float lo_u = -1.0f, hi_u = (float)nm + 1.0f;
-  {
+// The ray in lattice coordinates (cell i covers [i, i + 1)), axes permuted so that m is the dominant direction.
+struct WalkPath {
+  float um0, up0, uq0, slope_p, slope_q, eps;
+  int nm, np, nq, sm, sp, sq;     // extents and cell strides of the permuted axes
+  int i, i_end, step;             // layers i, i + step, ... up to and including i_end
+  bool fwd, p_up, q_up;
+  bool trusted;                   // false: scan all voxels instead (see file header)
+
+  __device__ __forceinline__ bool more() const { return fwd ? i <= i_end : i >= i_end; }
+
+  __device__ __forceinline__ void setup(const VoxelGridHeader* __restrict__ h, float voxelsize, const WalkRay& r,
+                                        float dx, float dy, float dz) {
+    const int nx = h->dims[0], ny = h->dims[1], nz = h->dims[2];
+    const float gx = float_from_order_key(h->min_key[0]), gy = float_from_order_key(h->min_key[1]),
+                gz = float_from_order_key(h->min_key[2]);
+    const float ux = __fdiv_rn(r.ox - gx, voxelsize) + 0.5f, uy = __fdiv_rn(r.oy - gy, voxelsize) + 0.5f,
+                uz = __fdiv_rn(r.oz - gz, voxelsize) + 0.5f;
+    const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+    const float am = fmaxf(ax, fmaxf(ay, az));
+    const bool finite = fabsf(r.ox) <= 3.0e38f && fabsf(r.oy) <= 3.0e38f && fabsf(r.oz) <= 3.0e38f && ax <= 3.0e38f &&
+                        ay <= 3.0e38f && az <= 3.0e38f;
+    const float far = fmaxf(fabsf(ux), fmaxf(fabsf(uy), fabsf(uz)));
+    trusted = finite && am >= 1.0e-18f && am <= 1.0e18f && far <= 1.0e5f;
+    i = 0; i_end = -1; step = 1; fwd = true;     // no layers
+    if (!trusted) return;
+    const int m = (ay > ax) ? ((az > ay) ? 2 : 1) : ((az > ax) ? 2 : 0);
+    const int p = m == 2 ? 0 : m + 1, q = p == 2 ? 0 : p + 1;
+    um0 = pick3(m, ux, uy, uz); up0 = pick3(p, ux, uy, uz); uq0 = pick3(q, ux, uy, uz);
+    const float dm = pick3(m, dx, dy, dz), dp = pick3(p, dx, dy, dz), dq = pick3(q, dx, dy, dz);
+    nm = pick3(m, nx, ny, nz); np = pick3(p, nx, ny, nz); nq = pick3(q, nx, ny, nz);
+    const int sx = ny * nz, sy = nz;
+    sm = pick3(m, sx, sy, 1); sp = pick3(p, sx, sy, 1); sq = pick3(q, sx, sy, 1);
+    const float inv_dm = __fdiv_rn(1.0f, dm);
+    slope_p = dp * inv_dm; slope_q = dq * inv_dm;   // |slope| <= 1
+    // candidate margin in cells: lattice tolerance + rounding of the reference's test and of this walk (both grow with
+    // the distance of the origin, ~1e-7 relative)
+    eps = 4.0e-3f + 4.0e-6f * (fabsf(um0) + fabsf(up0) + fabsf(uq0) + (float)(nm + np + nq));
+    p_up = dp >= 0.0f; q_up = dq >= 0.0f;
+    // layers in which both minor coordinates can be inside the lattice (two cells of slack; an almost constant minor
+    // coordinate drifts by less than two cells over the representable range)
+    float lo_u = -1.0f, hi_u = (float)nm + 1.0f;
     const float s2[2] = {slope_p, slope_q}, u2[2] = {up0, uq0}, n2[2] = {(float)np, (float)nq};
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -304,12 +325,18 @@ __device__ __forceinline__ void walk_one(const VoxelGridHeader* __restrict__ h, 
         hi_u = -2.0f;
       }
     }
+    if (!(lo_u <= hi_u)) return;
+    const int i_lo = max(0, (int)floorf(lo_u) - 1), i_hi = min(nm - 1, (int)floorf(hi_u) + 1);
+    fwd = dm > 0.0f;
+    step = fwd ? 1 : -1;
+    i = fwd ? max(i_lo, (int)floorf(um0 - eps)) : min(i_hi, (int)floorf(um0 + eps));
+    i_end = fwd ? i_hi : i_lo;
   }
-  if (!(lo_u <= hi_u)) return;
-  const int i_lo = max(0, (int)floorf(lo_u) - 1), i_hi = min(nm - 1, (int)floorf(hi_u) + 1);
-  int i = fwd ? max(i_lo, (int)floorf(um0 - eps)) : min(i_hi, (int)floorf(um0 + eps));
-  const int p_first_lo = dp >= 0.0f, q_first_lo = dq >= 0.0f;
-  for (; fwd ? i <= i_hi : i >= i_lo; i += step) {
+
+  // the occupied candidate cells of layer i in travel order (so that hits come out sorted by entry depth in all but
+  // degenerate cases); visit(v) returns true to stop
+  template <class F>
+  __device__ __forceinline__ bool layer(const int* __restrict__ cell, F&& visit) const {
     // the part of the ray (t >= 0) inside this layer, in the dominant coordinate
     float ua = (float)i - eps, ub = (float)(i + 1) + eps;
     if (fwd) ua = fmaxf(ua, um0 - eps);
@@ -317,27 +344,45 @@ __device__ __forceinline__ void walk_one(const VoxelGridHeader* __restrict__ h, 
     const float ra = ua - um0, rb = ub - um0;
     const float pa = fmaf(slope_p, ra, up0), pb = fmaf(slope_p, rb, up0);
     const int jp0 = max(0, (int)floorf(fminf(pa, pb) - eps)), jp1 = min(np - 1, (int)floorf(fmaxf(pa, pb) + eps));
-    if (jp0 > jp1) continue;
+    if (jp0 > jp1) return false;
     const float qa = fmaf(slope_q, ra, uq0), qb = fmaf(slope_q, rb, uq0);
     const int jq0 = max(0, (int)floorf(fminf(qa, qb) - eps)), jq1 = min(nq - 1, (int)floorf(fmaxf(qa, qb) + eps));
-    if (jq0 > jq1) continue;
+    if (jq0 > jq1) return false;
     const int base = i * sm;
-    // minor cells in travel order, so that hits come out sorted by entry depth in all but degenerate cases
     for (int a = 0; a <= jp1 - jp0; ++a) {
-      const int jp = p_first_lo ? jp0 + a : jp1 - a;
+      const int jp = p_up ? jp0 + a : jp1 - a;
       for (int b = 0; b <= jq1 - jq0; ++b) {
-        const int jq = q_first_lo ? jq0 + b : jq1 - b;
+        const int jq = q_up ? jq0 + b : jq1 - b;
         const int v = __ldg(cell + base + jp * sp + jq * sq);
-        if (v < 0) continue;
-        float tn, tf;
-        if (walk_test(r, pts, v, hv, tn, tf)) {
-          row.add(v, tn, tf);
-          if (MODE == kWalkAnyHit) return;
-        }
+        if (v >= 0 && visit(v)) return true;
       }
     }
+    return false;
   }
+};
+
+// One ray start to finish by one thread, hits written straight into its global row: the any-hit query, and the sorted
+// query's slow path (rows that overflow n_max, rays the walk does not trust).
+template <int MODE>
+__device__ __forceinline__ void walk_direct(const VoxelGridHeader* __restrict__ h, const float* __restrict__ pts, int n,
+                                            float hv, const WalkRay& r, WalkPath path, WalkRow<MODE>& row) {
+  const int* __restrict__ cell = reinterpret_cast<const int*>(h + 1);
+  auto visit = [&](int v) -> bool {
+    float tn, tf;
+    if (!walk_test(r, pts, v, hv, tn, tf)) return false;
+    row.add(v, tn, tf);
+    return MODE == kWalkAnyHit;
+  };
+  if (!path.trusted) {   // scan all voxels in index order like the reference
+    for (int v = 0; v < n; ++v)
+      if (visit(v)) return;
+    return;
+  }
+  for (; path.more(); path.i += path.step)
+    if (path.layer(cell, visit)) return;
 }
+
+constexpr int kRing = 16, kRingLd = 17;   // staged hits per ray, padded row stride (bank spread)
 
 template <int MODE>
 __global__ void __launch_bounds__(kWalkThreads)
@@ -346,67 +391,96 @@ grid_walk_kernel(const unsigned char* __restrict__ ws, size_t per_set_bytes, con
                  const float* __restrict__ ray_start, const float* __restrict__ ray_dir, int* __restrict__ out_idx,
                  float* __restrict__ out_min, float* __restrict__ out_max, unsigned char* __restrict__ out_hit) {
   if (!voxel_grid_usable(ws, per_set_bytes, blockIdx.y)) return;   // the hierarchy kernels take this voxel set
+  constexpr int kWarps = kWalkThreads / 32;
+  constexpr int kStage = MODE == kWalkDepthSorted ? kWarps * 32 * kRingLd : 1;
+  __shared__ int s_idx[kStage];
+  __shared__ float s_min[kStage], s_max[kStage];
   const VoxelGridHeader* h = reinterpret_cast<const VoxelGridHeader*>(ws + (size_t)blockIdx.y * per_set_bytes);
+  const int* __restrict__ cell = reinterpret_cast<const int*>(h + 1);
   const float* pts = points + (long long)blockIdx.y * points_stride;
   const float hv = voxelsize * 0.5f;   // reference: float half_voxel = voxelsize * 0.5 (exact)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int kWarps = kWalkThreads / 32;
   const long long ray_base = (long long)blockIdx.y * rays_per_set;
   const long long n_tiles = (rays_per_set + 31) / 32;
   for (long long tile = (long long)blockIdx.x * kWarps + warp; tile < n_tiles; tile += (long long)gridDim.x * kWarps) {
     const long long rr = tile * 32 + lane;
     const bool live = rr < rays_per_set;
     const long long ray = ray_base + (live ? rr : rays_per_set - 1);
+    WalkRay r;
+    r.ox = ray_start[ray * 3 + 0]; r.oy = ray_start[ray * 3 + 1]; r.oz = ray_start[ray * 3 + 2];
+    const float dx = ray_dir[ray * 3 + 0], dy = ray_dir[ray * 3 + 1], dz = ray_dir[ray * 3 + 2];
+    r.ix = ref_rcp(dx); r.iy = ref_rcp(dy); r.iz = ref_rcp(dz);
+    r.regular = regular_component(r.ox, r.ix) && regular_component(r.oy, r.iy) && regular_component(r.oz, r.iz);
+    WalkPath path;
+    path.setup(h, voxelsize, r, dx, dy, dz);
     WalkRow<MODE> row;
-    row.n_max = n_max;
-    row.cnt = 0;
-    row.unsorted = false;
-    row.last_tn = 0.f;
-    row.last_v = -1;
+    row.reset(n_max);
     row.idx = MODE == kWalkAnyHit ? nullptr : out_idx + ray * n_max;
     row.dmin = MODE == kWalkAnyHit ? nullptr : out_min + ray * n_max;
     row.dmax = MODE == kWalkAnyHit ? nullptr : out_max + ray * n_max;
-    if (live) {
-      WalkRay r;
-      r.ox = ray_start[ray * 3 + 0]; r.oy = ray_start[ray * 3 + 1]; r.oz = ray_start[ray * 3 + 2];
-      const float dx = ray_dir[ray * 3 + 0], dy = ray_dir[ray * 3 + 1], dz = ray_dir[ray * 3 + 2];
-      r.ix = ref_rcp(dx); r.iy = ref_rcp(dy); r.iz = ref_rcp(dz);
-      r.regular = regular_component(r.ox, r.ix) && regular_component(r.oy, r.iy) && regular_component(r.oz, r.iz);
-      walk_one<MODE>(h, pts, n, hv, voxelsize, r, dx, dy, dz, row);
-      if (MODE == kWalkDepthSorted && row.unsorted) {   // rare: insertion sort of this ray's row by (depth, index)
-        for (int s = 1; s < row.cnt; ++s) {
-          const int v = row.idx[s];
-          const float tn = row.dmin[s], tf = row.dmax[s];
-          int t = s - 1;
-          while (t >= 0) {
-            const float e = row.dmin[t];
-            const int w = row.idx[t];
-            if (!(e > tn || (e == tn && w > v))) break;
-            row.idx[t + 1] = w; row.dmin[t + 1] = e; row.dmax[t + 1] = row.dmax[t];
-            --t;
-          }
-          row.idx[t + 1] = v; row.dmin[t + 1] = tn; row.dmax[t + 1] = tf;
-        }
+
+    if constexpr (MODE == kWalkAnyHit) {
+      if (live) {
+        walk_direct<MODE>(h, pts, n, hv, r, path, row);
+        out_hit[ray] = row.cnt > 0;
       }
-      if (MODE == kWalkIndexOrder) {   // ascending voxel index, then the depths of the sorted slots
-        for (int s = 1; s < row.cnt; ++s) {
-          const int v = row.idx[s];
-          int t = s - 1;
-          while (t >= 0 && row.idx[t] > v) { row.idx[t + 1] = row.idx[t]; --t; }
-          row.idx[t + 1] = v;
-        }
-        for (int s = 0; s < row.cnt; ++s) {
-          float tn, tf;
-          walk_test(r, pts, row.idx[s], hv, tn, tf);
-          row.dmin[s] = tn;
-          row.dmax[s] = tf;
-        }
-      }
-      if (out_hit != nullptr) out_hit[ray] = row.cnt > 0;
-    }
-    if (MODE != kWalkAnyHit) {   // tails of the 32 rows of this tile: coalesced -1 / fill depth
-      const int my_cnt = live ? row.cnt : n_max;
+    } else {
+      // The 32 rays of the tile advance one layer at a time, in step.  Hits are staged in a small ring per ray in
+      // shared memory; whenever some ray has 8 waiting, the warp writes every ray's staged hits to its row with 8
+      // lanes per row (32 contiguous bytes) — thread-per-ray stores would touch 32 different sectors per instruction.
+      int* ring_i = s_idx + (warp * 32 + lane) * kRingLd;
+      float* ring_a = s_min + (warp * 32 + lane) * kRingLd;
+      float* ring_b = s_max + (warp * 32 + lane) * kRingLd;
       const long long tile_row0 = (ray_base + tile * 32) * n_max;
+      int flushed = 0;
+      bool slow = live && !path.trusted;      // redo on the slow path: untrusted ray, row or ring overflow
+      bool walking = live && path.trusted && path.more();
+      auto flush = [&](int at_least) {        // warp-uniform; writes up to 8 staged hits of every ray
+        while (__any_sync(NSVF_FULL_MASK, row.cnt - flushed >= at_least)) {
+#pragma unroll 1
+          for (int k0 = 0; k0 < 32; k0 += 4) {
+            const int k = k0 + (lane >> 3), t = lane & 7;
+            const int f = __shfl_sync(NSVF_FULL_MASK, flushed, k), c = __shfl_sync(NSVF_FULL_MASK, row.cnt, k);
+            if (t < c - f) {
+              const int src = (warp * 32 + k) * kRingLd + ((f + t) & (kRing - 1));
+              const long long dst = tile_row0 + (long long)k * n_max + f + t;
+              out_idx[dst] = s_idx[src];
+              out_min[dst] = s_min[src];
+              out_max[dst] = s_max[src];
+            }
+          }
+          flushed += min(row.cnt - flushed, 8);
+          __syncwarp();
+        }
+      };
+      while (__any_sync(NSVF_FULL_MASK, walking)) {
+        if (walking) {
+          path.layer(cell, [&](int v) -> bool {
+            float tn, tf;
+            if (!walk_test(r, pts, v, hv, tn, tf)) return false;
+            if (row.cnt >= n_max || row.cnt - flushed >= kRing) { slow = true; return true; }
+            const int s = row.cnt & (kRing - 1);
+            ring_i[s] = v; ring_a[s] = tn; ring_b[s] = tf;
+            row.note_order(v, tn);
+            ++row.cnt;
+            return false;
+          });
+          path.i += path.step;
+          walking = !slow && path.more();
+        }
+        __syncwarp();
+        flush(8);
+      }
+      flush(1);
+      if (slow) {          // rare: start this ray over, thread-per-ray into the global row
+        row.reset(n_max);
+        path.setup(h, voxelsize, r, dx, dy, dz);
+        walk_direct<MODE>(h, pts, n, hv, r, path, row);
+      }
+      if (live && row.unsorted) row.repair();
+      if (live && out_hit != nullptr) out_hit[ray] = row.cnt > 0;
+      // tails of the 32 rows of this tile: coalesced -1 / fill depth
+      const int my_cnt = live ? row.cnt : n_max;
       for (int k = 0; k < 32; ++k) {
         const int c = __shfl_sync(NSVF_FULL_MASK, my_cnt, k);
         const long long r0 = tile_row0 + (long long)k * n_max;
@@ -416,6 +490,7 @@ grid_walk_kernel(const unsigned char* __restrict__ ws, size_t per_set_bytes, con
           out_max[r0 + s] = empty_depth;
         }
       }
+      __syncwarp();
     }
   }
 }
@@ -434,9 +509,9 @@ int voxel_grid_walk(cudaStream_t stream, int mode, const unsigned char* ws, size
                     (grid_walk_kernel<MODE><<<grid, kWalkThreads, 0, stream>>>(                                     \
                         ws, per_set_bytes, points, points_stride, n, voxelsize, rays_per_set, n_max, empty_depth,   \
                         ray_start, ray_dir, idx, min_depth, max_depth, hit)))
+  NSVF_REQUIRE(mode == kWalkDepthSorted || mode == kWalkAnyHit, "voxel_grid_walk: mode must be 1 (sorted) or 2 (any hit)");
   if (mode == kWalkDepthSorted) NSVF_WALK(kWalkDepthSorted, "aabb_intersect_sorted_kernel");
-  else if (mode == kWalkAnyHit) NSVF_WALK(kWalkAnyHit, "aabb_hit_mask_kernel");
-  else NSVF_WALK(kWalkIndexOrder, "aabb_intersect_kernel");
+  else NSVF_WALK(kWalkAnyHit, "aabb_hit_mask_kernel");
 #undef NSVF_WALK
   return 0;
 }

@@ -40,7 +40,7 @@ __device__ __forceinline__ bool voxel_grid_usable(const unsigned char* ws, size_
 size_t voxel_grid_bytes(int n);
 int voxel_grid_build(cudaStream_t stream, int n_sets, int n, const float* points, long long points_stride,
                      float voxelsize, unsigned char* ws, size_t per_set_bytes);
-// mode as in aabb_intersect.cu: 0 = ascending voxel index, 1 = sorted by entry depth, 2 = any-hit mask
+// mode as in aabb_intersect.cu: 1 = sorted by entry depth, 2 = any-hit mask
 int voxel_grid_walk(cudaStream_t stream, int mode, const unsigned char* ws, size_t per_set_bytes, int n_sets, int n,
                     const float* points, long long points_stride, float voxelsize, long long rays_per_set, int n_max,
                     float empty_depth, const float* ray_start, const float* ray_dir, int* idx, float* min_depth,

@@ -303,21 +303,38 @@ class VolumeRenderer(nn.Module):
             out_types = list(output_types)
             evals, launch_no, w = 0, 0, 0
             ray_off = None
+            # With early termination the next window is only known once this window's epilogue has run.  Its compaction
+            # is queued right behind that epilogue with the window taken from the plan on the device (start = -1), into
+            # buffers of the largest size a window can have, and the host waits on an event recorded BEFORE it: the GPU
+            # compacts while the host wakes up, reads the window back and narrows the buffers to its count.
+            ahead = (not all_windows) and (not grad) and os.environ.get("NSVF_MARCH_AHEAD", "1") != "0"
+            cap_rows = max(int(chunk_size), B)
+            spec, held, spare, readback = None, None, [], torch.cuda.Event() if ahead else None
             while w < len(windows):
                 start, end, M = windows[w]
                 w += 1
-                vox, xyz, dirs = E(M, dtype=i32, device=dev), E((M, 3), dtype=f32, device=dev), E((M, 3), dtype=f32, device=dev)
-                dists_c = E(M, dtype=f32, device=dev)
-                while t_upto < end:
-                    t_next = min(K, t_upto + t_block)
-                    fill_planes(t_upto, t_next, p_es)
-                    t_upto = t_next
-                if grad or ray_off is None:      # the backward needs every window's offsets
-                    ray_off = E(B + 1, dtype=i32, device=dev)
-                _lib.check(_L.nsvf_march_compact(st, B, K, start, end, p_lens, p_es, p_idxT, p_depthT, p_distsT, p_rs,
-                                                 p_rd, _p(vox), _p(xyz), _p(dirs), _p(dists_c), _p(ray_off), p_plan,
-                                                 launch_no))
-                launch_no += 1
+                if held is not None:
+                    spare.append(held)           # the buffers of the window before: free for the one after this
+                    held = None
+                if spec is not None and spec[4] >= end:
+                    vox, xyz, dirs, dists_c = spec[0][:M], spec[1][:M], spec[2][:M], spec[3][:M]
+                    held, spec = spec[:4], None
+                else:
+                    if spec is not None:         # the planes did not reach far enough: compact again, the usual way
+                        spare.append(spec[:4])
+                        spec = None
+                    vox, xyz, dirs = E(M, dtype=i32, device=dev), E((M, 3), dtype=f32, device=dev), E((M, 3), dtype=f32, device=dev)
+                    dists_c = E(M, dtype=f32, device=dev)
+                    while t_upto < end:
+                        t_next = min(K, t_upto + t_block)
+                        fill_planes(t_upto, t_next, p_es)
+                        t_upto = t_next
+                    if grad or ray_off is None:      # the backward needs every window's offsets
+                        ray_off = E(B + 1, dtype=i32, device=dev)
+                    _lib.check(_L.nsvf_march_compact(st, B, K, start, end, p_lens, p_es, p_idxT, p_depthT, p_distsT, p_rs,
+                                                     p_rd, _p(vox), _p(xyz), _p(dirs), _p(dists_c), _p(ray_off), p_plan,
+                                                     launch_no))
+                    launch_no += 1
                 field_inputs = input_fn({"sampled_point_voxel_idx": vox, "sampled_point_xyz": xyz,
                                          "sampled_point_ray_direction": dirs, "sampled_point_distance": dists_c},
                                         encoder_states)
@@ -349,7 +366,24 @@ class VolumeRenderer(nn.Module):
                 if grad:
                     record.windows.append((start, end, M, ray_off, sigma, texture, sg, nz, dd))
                 if not all_windows:
-                    stream.synchronize()
+                    if ahead:
+                        readback.record(stream)
+                        want = min(K, end + 2 * (end - start) + 1)       # planes the next window may reach into
+                        while t_upto < want:
+                            t_next = min(K, t_upto + t_block)
+                            fill_planes(t_upto, t_next, p_es)
+                            t_upto = t_next
+                        bufs = spare.pop() if spare else (
+                            E(cap_rows, dtype=i32, device=dev), E((cap_rows, 3), dtype=f32, device=dev),
+                            E((cap_rows, 3), dtype=f32, device=dev), E(cap_rows, dtype=f32, device=dev))
+                        _lib.check(_L.nsvf_march_compact(st, B, K, -1, -1, p_lens, p_es, p_idxT, p_depthT, p_distsT, p_rs,
+                                                         p_rd, _p(bufs[0]), _p(bufs[1]), _p(bufs[2]), _p(bufs[3]),
+                                                         _p(ray_off), p_plan, launch_no))
+                        launch_no += 1
+                        spec = bufs + (t_upto,)
+                        readback.synchronize()
+                    else:
+                        stream.synchronize()
                     head = info[:4].tolist()
                     if not head[3]:
                         windows.append(head[0:3])

@@ -236,3 +236,25 @@ def test_lazy_rendering_equals_eager_rendering(cuda):
         assert a["ae"] == b["ae"]
         for name in ("depths", "colors", "max_depths", "min_depths", "missed", "probs"):
             assert torch.equal(a[name], b[name]), (name, tol)
+
+
+@pytest.mark.parametrize("trimmed,block", [(False, "64"), (True, "64"), (True, "32")])
+def test_compaction_queued_ahead_of_the_readback_changes_nothing(cuda, trimmed, block):
+    """With early termination the next window's compaction is launched from the device-side schedule before the host
+    has read it (nsvf_march_compact start = -1); switching that off, or making the plane blocks so small that the
+    launch-ahead has to be repeated, gives bit-identical frames and evaluation counts."""
+    enc, st, rs, rd, samples, inter = _scene_samples(cuda, n_rays=2500, seed=4, trimmed=trimmed)
+    ren = VolumeRenderer(chunk_size=2, valid_chunk_size=2, raymarching_tolerance=0.1).eval()
+    out = {}
+    os.environ["NSVF_PLANE_BLOCK"] = block
+    try:
+        for mode in ("1", "0"):
+            os.environ["NSVF_MARCH_AHEAD"] = mode
+            with torch.no_grad():
+                out[mode] = ren(enc, _field, rs, rd, samples, st)
+    finally:
+        os.environ.pop("NSVF_MARCH_AHEAD", None)
+        os.environ.pop("NSVF_PLANE_BLOCK", None)
+    assert out["1"]["ae"] == out["0"]["ae"] and out["1"]["ae"] > 0
+    for name in ("probs", "depths", "colors", "max_depths", "min_depths", "missed"):
+        assert torch.equal(out["1"][name], out["0"][name]), name
