@@ -120,6 +120,14 @@ __device__ __forceinline__ bool slab_enclosing(float ox, float oy, float oz, flo
   return !(tn > tf);
 }
 
+// Order-preserving integer image of a float (signed compare of the keys == compare of the floats, -0 < +0): lets
+// atomicMin / __reduce_max_sync work on floats.
+__device__ __forceinline__ int float_order_key(float f) {
+  const int b = __float_as_int(f);
+  return b >= 0 ? b : (b ^ 0x7fffffff);
+}
+__device__ __forceinline__ float float_from_order_key(int k) { return __int_as_float(k >= 0 ? k : (k ^ 0x7fffffff)); }
+
 // ---- TMA 1-D bulk copy (cp.async.bulk, SASS: UBLKCP) + mbarrier ---------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -18,17 +18,7 @@ struct VoxelGridHeader {
 };
 static_assert(sizeof(VoxelGridHeader) == 128, "VoxelGridHeader is 128 bytes");
 
-__host__ __device__ __forceinline__ int float_order_key(float f) {
-#ifdef __CUDA_ARCH__
-  const int b = __float_as_int(f);
-#else
-  int b;
-  memcpy(&b, &f, 4);
-#endif
-  return b >= 0 ? b : (b ^ 0x7fffffff);
-}
 #ifdef __CUDACC__
-__device__ __forceinline__ float float_from_order_key(int k) { return __int_as_float(k >= 0 ? k : (k ^ 0x7fffffff)); }
 __device__ __forceinline__ bool voxel_grid_usable(const unsigned char* ws, size_t per_set_bytes, int set) {
   if (ws == nullptr) return false;
   const VoxelGridHeader* h = reinterpret_cast<const VoxelGridHeader*>(ws + (size_t)set * per_set_bytes);

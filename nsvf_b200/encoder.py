@@ -17,7 +17,9 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import clib, geometry, ops
+from . import _lib, clib, geometry, ops
+
+_L = _lib.load()
 
 logger = logging.getLogger(__name__)
 MAX_DEPTH = 10000.0
@@ -251,6 +253,33 @@ class SparseVoxelEncoder(nn.Module):
                                                 point_xyz.reshape(-1, 3), values.reshape(-1, values.size(-1)),
                                                 self._voxel_size_float())
         return inputs
+
+    def window_fn(self, encoder_states, stream_ptr):
+        """forward() for VolumeRenderer's inference window loop, which calls it once per window with freshly compacted
+        samples: returns fn(vox, xyz, dirs, dists) -> field inputs with everything that does not change between windows
+        (pointer look-ups, dtype / layout checks, stream and device queries, Module.__call__) done once here.  None
+        when the general forward() is needed (autograd, position gradients, unusual layouts)."""
+        values = encoder_states["voxel_vertex_emb"]
+        if torch.is_grad_enabled() or self.track_xyz_grad or values is None:
+            return None
+        feats = self._feats32(encoder_states["voxel_vertex_idx"])
+        centres = encoder_states["voxel_center_xyz"].reshape(-1, 3)
+        vals = values.reshape(-1, values.size(-1))
+        f32 = torch.float32
+        if not (feats.dtype == torch.int32 and feats.is_contiguous() and centres.dtype == f32 and centres.is_contiguous()
+                and vals.dtype == f32 and vals.is_contiguous() and vals.is_cuda):
+            return None
+        dev, D, vs = vals.device, vals.shape[-1], self._voxel_size_float()
+        p_feats, p_centres, p_vals = feats.data_ptr(), centres.data_ptr(), vals.data_ptr()
+        fwd, empty = _L.nsvf_trilinear_embed_fwd, torch.empty
+
+        def fn(vox, xyz, dirs, dists, _keep=(feats, centres, vals)):
+            M = vox.numel()
+            emb = empty((M, D), dtype=f32, device=dev)
+            if fwd(stream_ptr, M, D, vox.data_ptr(), xyz.data_ptr(), p_feats, p_centres, p_vals, vs, emb.data_ptr()):
+                _lib.check(1)
+            return {"pos": xyz, "ray": dirs, "dists": dists, "emb": emb}
+        return fn
 
     def _max_hits_int(self):
         """int(self.max_hits) without a device sync per call."""

@@ -310,6 +310,9 @@ class VolumeRenderer(nn.Module):
             ahead = (not all_windows) and (not grad) and os.environ.get("NSVF_MARCH_AHEAD", "1") != "0"
             cap_rows = max(int(chunk_size), B)
             spec, held, spare, readback = None, None, [], torch.cuda.Event() if ahead else None
+            # our own encoder offers a lean per-window entry for inference (same result as calling it)
+            window_fn = getattr(input_fn, "window_fn", None)
+            window_fn = window_fn(encoder_states, st) if (window_fn is not None and not grad) else None
             while w < len(windows):
                 start, end, M = windows[w]
                 w += 1
@@ -335,9 +338,12 @@ class VolumeRenderer(nn.Module):
                                                      p_rd, _p(vox), _p(xyz), _p(dirs), _p(dists_c), _p(ray_off), p_plan,
                                                      launch_no))
                     launch_no += 1
-                field_inputs = input_fn({"sampled_point_voxel_idx": vox, "sampled_point_xyz": xyz,
-                                         "sampled_point_ray_direction": dirs, "sampled_point_distance": dists_c},
-                                        encoder_states)
+                if window_fn is not None:
+                    field_inputs = window_fn(vox, xyz, dirs, dists_c)
+                else:
+                    field_inputs = input_fn({"sampled_point_voxel_idx": vox, "sampled_point_xyz": xyz,
+                                             "sampled_point_ray_direction": dirs, "sampled_point_distance": dists_c},
+                                            encoder_states)
                 field_outputs = field_fn(field_inputs, outputs=out_types)
                 sigma = field_outputs["sigma"]
                 texture = field_outputs["texture"] if want_tex else None

@@ -258,3 +258,25 @@ def test_compaction_queued_ahead_of_the_readback_changes_nothing(cuda, trimmed, 
     assert out["1"]["ae"] == out["0"]["ae"] and out["1"]["ae"] > 0
     for name in ("probs", "depths", "colors", "max_depths", "min_depths", "missed"):
         assert torch.equal(out["1"][name], out["0"][name]), name
+
+
+def test_encoder_window_fn_equals_forward(cuda):
+    """SparseVoxelEncoder.window_fn (the lean per-window entry the renderer uses for inference) returns what forward()
+    returns, and declines when autograd is on."""
+    enc, st, rs, rd, samples, _ = _scene_samples(cuda, n_rays=500, seed=8)
+    sidx = samples["sampled_point_voxel_idx"]
+    mask = sidx.ne(-1)
+    vox = sidx[mask].int().contiguous()
+    depth = samples["sampled_point_depth"][mask]
+    dirs = rd[:, None].expand(-1, sidx.shape[1], -1)[mask].contiguous()
+    xyz = (rs[:, None].expand(-1, sidx.shape[1], -1)[mask] + dirs * depth[:, None]).contiguous()
+    dists = samples["sampled_point_distance"][mask].contiguous()
+    assert enc.window_fn(st, torch.cuda.current_stream(cuda).cuda_stream) is None      # grad mode: general forward
+    with torch.no_grad():
+        fn = enc.window_fn(st, torch.cuda.current_stream(cuda).cuda_stream)
+        a = fn(vox, xyz, dirs, dists)
+        b = enc({"sampled_point_voxel_idx": vox, "sampled_point_xyz": xyz, "sampled_point_ray_direction": dirs,
+                 "sampled_point_distance": dists}, st)
+    assert set(a) == set(b)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
