@@ -303,13 +303,19 @@ march_compact_kernel(long long B, long long ldb, int K, int start, int end, cons
   __shared__ unsigned sh_tile, sh_base;
   __shared__ int sh_warp[kTile / 32], sh_total;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (start < 0) {   // the window the previous epilogue scheduled: launched before the host has read it back
-    const volatile int* hdr = plan;
-    start = hdr[H_START];
-    end = hdr[H_DONE] ? start : hdr[H_END];
+  __shared__ int sh_start, sh_end;
+  if (tid == 0) {
+    sh_tile = atomicAdd(reinterpret_cast<unsigned*>(plan + H_TICKET), 1u) - ticket_base;
+    if (start < 0) {   // the window the previous epilogue scheduled: launched before the host has read it back.  ONE
+                       // thread per CTA reads it — the header shares its cache line with the ticket counter, and a
+                       // load per thread (320 k of them) doubled this kernel's time by queueing behind the atomics
+      const int s0 = __ldcg(plan + H_START);
+      sh_start = s0;
+      sh_end = __ldcg(plan + H_DONE) ? s0 : __ldcg(plan + H_END);
+    }
   }
-  if (tid == 0) sh_tile = atomicAdd(reinterpret_cast<unsigned*>(plan + H_TICKET), 1u) - ticket_base;
   __syncthreads();
+  if (start < 0) { start = sh_start; end = sh_end; }
   const unsigned tile = sh_tile;
   const long long ray = (long long)tile * kTile + tid;
   int n = 0;
