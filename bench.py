@@ -691,8 +691,8 @@ def frame_rooflines(dev, pipe, rs, rd, peak, peak_src, frame_ms):
              lambda n: 20 * ae + 36 * rays),
             ("march_transpose_kernel", "row -> slot-major transpose (24 B per sample; lower bound: evaluated samples)", "hbm",
              lambda n: 24 * ae),
-            ("aabb_intersect_kernel", "sorted aabb intersection, %d rays x %d voxels (ALU / L1-bound by design)" % (all_rays, n_vox),
-             "hbm", lambda n: all_rays * (24 + 12 * P + 1) + 24 * n_vox),
+            ("aabb_intersect_sorted_kernel", "sorted aabb intersection (lattice walk), %d rays x %d voxels: rays in, hit lists out"
+             % (all_rays, n_vox), "hbm", lambda n: all_rays * (24 + 12 * P + 1) + 16 * n_vox),
         ]
         res = []
         for name, what, bound, nbytes in table:

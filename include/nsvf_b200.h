@@ -179,13 +179,20 @@ NSVF_API int nsvf_inverse_cdf_sampling_ex(nsvf_stream_t stream, int b, int num_r
  *   nsvf_inverse_cdf_plan  : per ray, ONLY the number of samples nsvf_inverse_cdf_sampling_ex would emit
  *                            (ray_len i32 [valid_rays]) in O(bins + log steps), plus the two neighbour-ray values the
  *                            reference's trailing loop reads (quirk i32 [valid_rays, 2] = {slot 0 of the next ray,
- *                            valid bins of ray 0 of the block row; -1 marks a ray with irregular cumulative sums});
+ *                            valid bins nb0 of ray 0 of the block row, stored as -1 - nb0 for a ray with irregular
+ *                            cumulative sums});
  *                            meta i32 [3] (zeroed) = {max ray_len, holes flag, fallback rays}.  Hit lists must be
  *                            -1-terminated (what the sorted intersection produces).
  *   nsvf_inverse_cdf_block : the samples at positions [k_begin, k_end) of the rays not flagged in early_stop, with
  *                            ray_sample's post-processing applied, written into the slot-major planes idxT / depthT /
  *                            distsT [K][nsvf_march_plane_stride(B)] of the plan.  The per-ray inputs may be row slices of
  *                            the tensors the plan kernel saw (uniform_noise rows noise_row_stride floats apart, or NULL).
+ *                            Any block, in any order (each block rebuilds the ray's tables).
+ *   nsvf_inverse_cdf_stream: the same output for blocks requested IN INCREASING ORDER — k_begin = 0 first, then every
+ *                            call's k_begin equal to the previous call's k_end — which is how the ray-marching loop
+ *                            asks: one thread per ray resumes the reference's serial state machine from `state`
+ *                            (nsvf_inverse_cdf_stream_state_bytes(B) bytes, 16-byte aligned, owned by the caller between
+ *                            calls; rays flagged in early_stop are skipped and must stay flagged).
  * Same samples, bit for bit, as the eager kernel + nsvf_march_transpose. */
 NSVF_API int nsvf_inverse_cdf_plan(nsvf_stream_t stream, int b, int num_rays, long long valid_rays, int ray_chunk,
                                    int max_hits, int max_steps, float fixed_step_size, const int* pts_idx,
@@ -198,6 +205,14 @@ NSVF_API int nsvf_inverse_cdf_block(nsvf_stream_t stream, long long B, int max_h
                                     const float* max_depth, const float* uniform_noise, long long noise_row_stride,
                                     float noise_const, const float* probs, const float* steps, float pad_depth,
                                     int* idxT, float* depthT, float* distsT);
+
+NSVF_API size_t nsvf_inverse_cdf_stream_state_bytes(long long B);
+NSVF_API int nsvf_inverse_cdf_stream(nsvf_stream_t stream, long long B, int max_hits, int max_steps,
+                                     float fixed_step_size, int k_begin, int k_end, const unsigned char* early_stop,
+                                     const int* ray_len, const int* quirk, const int* pts_idx, const float* min_depth,
+                                     const float* max_depth, const float* uniform_noise, long long noise_row_stride,
+                                     float noise_const, const float* probs, const float* steps, float pad_depth,
+                                     void* state, int* idxT, float* depthT, float* distsT);
 
 /* Replaces uniform_ray_sampling, fairnr/clib/src/sample.cpp:23-55 + sample_gpu.cu:15-106, and the trimming glue of
  * UniformRaySampling.forward, fairnr/clib/__init__.py:178-228.  Same layouts as above ([b, num_rays, max_hits] bins,

@@ -51,6 +51,9 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nsvf_inverse_cdf_block": (c_int, [c_void_p, c_ll, c_int, c_int, c_float, c_int, c_int] + [c_void_p] * 7 +
                                [c_ll, c_float, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
+    "nsvf_inverse_cdf_stream_state_bytes": (c_size_t, [c_ll]),
+    "nsvf_inverse_cdf_stream": (c_int, [c_void_p, c_ll, c_int, c_int, c_float, c_int, c_int] + [c_void_p] * 7 +
+                                [c_ll, c_float, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nsvf_march_plane_stride": (c_ll, [c_ll]),
     "nsvf_march_plan_bytes": (c_size_t, [c_ll, c_int]),
     "nsvf_march_ray_lengths": (c_int, [c_void_p, c_ll, c_int, c_ll, c_void_p, c_void_p, c_void_p]),

@@ -34,7 +34,8 @@ __device__ __forceinline__ bool cdf_next(CdfState& st, int max_hits, int max_ste
                                          const int* __restrict__ pts_idx, const int* __restrict__ row0_idx,
                                          const float* __restrict__ min_depth, const float* __restrict__ max_depth,
                                          const float* __restrict__ probs, const float* __restrict__ noise_row,
-                                         float noise_const, int& o_idx, float& o_dist, float& o_depth) {
+                                         float noise_const, int& o_idx, float& o_dist, float& o_depth,
+                                         int row0_nb = 0 /* leading valid bins of row0 when row0_idx == nullptr */) {
   for (;;) {
     if (st.phase == 0) {
       if (st.curr_step >= st.total_steps) { st.phase = 2; continue; }
@@ -77,7 +78,8 @@ __device__ __forceinline__ bool cdf_next(CdfState& st, int max_hits, int max_ste
       o_dist = __fsub_rn(st.curr_max_depth, st.z_low);
       o_depth = __fmul_rn(__fadd_rn(st.curr_max_depth, st.z_low), 0.5f);
       st.curr_bin++;
-      if (st.curr_bin >= max_hits || row0_idx[st.curr_bin] == -1) {
+      if (st.curr_bin >= max_hits ||
+          (row0_idx != nullptr ? row0_idx[st.curr_bin] == -1 : st.curr_bin >= row0_nb)) {
         st.phase = 3;
       } else {
         st.curr_min_depth = min_depth[H + st.curr_bin];
@@ -551,25 +553,28 @@ __device__ __forceinline__ CdfRay cdf_ray_setup(long long H, int P, int max_step
     const unsigned m = __ballot_sync(NSVF_FULL_MASK, j >= 1 && j < P && v == -1);
     if (m) { nb = j0 + __ffs(m) - 1; break; }
   }
+  bool neg = false;
   for (int j = lane; j < min(P, nb + 1); j += 32) {
     s_min[j] = min_depth[H + j];
     s_max[j] = max_depth[H + j];
-    s_cum[j] = probs[H + j];
+    const float pr = probs[H + j];
+    s_cum[j] = pr;
+    neg |= (j < nb) && !(pr >= 0.0f);
   }
   for (int j = nb + 1 + lane; j < P; j += 32) s_idx[j] = -1;     // the trailing loop may look at bins beyond nb
+  const bool nonneg = !__any_sync(NSVF_FULL_MASK, neg);
   __syncwarp();
   int ok = 1;
-  if (lane == 0) {
+  if (lane == 0) {   // non-negative terms: non-decreasing sums, all finite iff the last one is (see the eager kernel)
     float c = s_cum[0];
-    ok = (c == c) && (fabsf(c) <= 3.0e38f);
+#pragma unroll 4
     for (int j = 1; j < nb; ++j) {
-      const float n = __fadd_rn(c, s_cum[j]);
-      ok &= (n >= c) && (fabsf(n) <= 3.0e38f);
-      s_cum[j] = n;
-      c = n;
+      c = __fadd_rn(c, s_cum[j]);
+      s_cum[j] = c;
     }
+    ok = fabsf(c) <= 3.0e38f;
   }
-  r.ok = __shfl_sync(NSVF_FULL_MASK, ok, 0);
+  r.ok = __shfl_sync(NSVF_FULL_MASK, ok, 0) && nonneg;
   __syncwarp();
   r.nb = nb;
   r.step_size = fixed_step_size > 0.0f ? fixed_step_size : __fdiv_rn(1.0f, sj);
@@ -634,6 +639,81 @@ __device__ __forceinline__ void cdf_trailing(const CdfRay& r, int P, const float
     curr_max = bmax(curr_bin);
     zl = bmin(curr_bin);
   }
+}
+
+// ---- resumable serial sampler: the samples of positions [k0, k1), one thread per ray, straight into the planes ------
+// The block kernel below can produce any block in any order, at the price of rebuilding a ray's bin tables and locating
+// the block inside the merge for every block.  The ray-marching loop asks for blocks in increasing order, and then the
+// reference's own serial machine (cdf_next: one sample per call, no searches, no tables) is the cheapest producer there
+// is: its 11-word state is parked in global memory between blocks, lanes are consecutive rays, and since every call
+// emits exactly one sample all 32 lanes write the SAME plane row — 128 contiguous bytes per store, no staging tile, no
+// transpose.  Work is proportional to the samples actually requested (C3 frame: 41 M evaluated of 306 M).
+struct __align__(16) CdfParked {
+  int curr_bin, curr_step, total_steps, phase;
+  float curr_min_depth, curr_max_depth, curr_min_cdf, curr_max_cdf;
+  float step_size, z_low, curr_cdf, pad;
+};
+static_assert(sizeof(CdfParked) == 48, "CdfParked is 48 bytes");
+constexpr int kStreamThreads = 128;
+
+__global__ void __launch_bounds__(kStreamThreads)
+inverse_cdf_stream_kernel(long long B, long long ldb, int P, int max_steps, float fixed_step_size, int k0, int k1,
+                          const unsigned char* __restrict__ early_stop, const int* __restrict__ ray_len,
+                          const int2* __restrict__ quirk, const int* __restrict__ pts_idx,
+                          const float* __restrict__ min_depth, const float* __restrict__ max_depth,
+                          const float* __restrict__ noise, long long noise_stride, float noise_const,
+                          const float* __restrict__ probs, const float* __restrict__ steps, float pad_depth,
+                          CdfParked* __restrict__ parked, int* __restrict__ idxT, float* __restrict__ depthT,
+                          float* __restrict__ distsT) {
+  const long long ray = (long long)blockIdx.x * kStreamThreads + threadIdx.x;
+  if (ray >= B) return;
+  if (early_stop != nullptr && early_stop[ray] != 0) return;
+  const int hi = min(ray_len[ray], k1);
+  if (hi <= k0) return;
+  const long long H = ray * P;
+  const int2 qk = quirk[ray];
+  const int row0_nb = qk.y >= 0 ? qk.y : -1 - qk.y;
+  const float* noise_row = noise != nullptr ? noise + ray * noise_stride : nullptr;
+  CdfState st;
+  st.s = 0;
+  if (k0 == 0) {
+    st.curr_bin = 0;
+    st.curr_step = 0;
+    st.curr_min_depth = min_depth[H];
+    st.curr_max_depth = max_depth[H];
+    st.curr_min_cdf = 0.0f;
+    st.curr_max_cdf = probs[H];
+    const float sj = steps[ray];
+    st.step_size = fixed_step_size > 0.0f ? fixed_step_size : __fdiv_rn(1.0f, sj);
+    st.z_low = st.curr_min_depth;
+    st.total_steps = min((int)ceilf(sj), max_steps);
+    st.curr_cdf = 0.0f;
+    st.phase = 0;
+  } else {
+    const int4 a = reinterpret_cast<const int4*>(parked + ray)[0];
+    const float4 b = reinterpret_cast<const float4*>(parked + ray)[1], c = reinterpret_cast<const float4*>(parked + ray)[2];
+    st.curr_bin = a.x; st.curr_step = a.y; st.total_steps = a.z; st.phase = a.w;
+    st.curr_min_depth = b.x; st.curr_max_depth = b.y; st.curr_min_cdf = b.z; st.curr_max_cdf = b.w;
+    st.step_size = c.x; st.z_low = c.y; st.curr_cdf = c.z;
+  }
+  int pos = k0;
+  while (pos < hi && st.phase != 3) {
+    int oi;
+    float od, oz;
+    if (cdf_next(st, P, max_steps, H, qk.x, pts_idx, nullptr, min_depth, max_depth, probs, noise_row, noise_const, oi, od,
+                 oz, row0_nb)) {
+      od = od < 0.f ? 0.f : od;                     // ray_sample's clamp / masking (encoder.py:547-549)
+      if (oi == -1) { od = 0.f; oz = pad_depth; }
+      const long long o = (long long)pos * ldb + ray;
+      idxT[o] = oi;
+      depthT[o] = oz;
+      distsT[o] = od;
+      ++pos;
+    }
+  }
+  reinterpret_cast<int4*>(parked + ray)[0] = make_int4(st.curr_bin, st.curr_step, st.total_steps, st.phase);
+  reinterpret_cast<float4*>(parked + ray)[1] = make_float4(st.curr_min_depth, st.curr_max_depth, st.curr_min_cdf, st.curr_max_cdf);
+  reinterpret_cast<float4*>(parked + ray)[2] = make_float4(st.step_size, st.z_low, st.curr_cdf, 0.f);
 }
 
 constexpr int kLazyWarps = 8;       // block kernel: 32 rays per CTA, 4 per warp
@@ -702,7 +782,7 @@ inverse_cdf_plan_kernel(int b, int num_rays, long long valid_rays, int ray_chunk
         atomicAdd(meta + 2, 1);
       }
       ray_len[ray] = lastv;
-      quirk[ray] = make_int2(next_idx0, r.ok ? row0_nb : -1);     // row0_nb = -1 marks a fallback ray
+      quirk[ray] = make_int2(next_idx0, r.ok ? row0_nb : -1 - row0_nb);     // negative (-1 - row0_nb) marks a fallback ray
       if (n_valid != lastv) atomicOr(meta + 1, 1);
     }
     lastv = __shfl_sync(NSVF_FULL_MASK, lastv, 0);
@@ -1150,5 +1230,27 @@ extern "C" int nsvf_inverse_cdf_block(nsvf_stream_t stream_, long long B, int ma
                           reinterpret_cast<const int2*>(quirk), pts_idx, min_depth, max_depth, uniform_noise,
                           noise_row_stride, noise_const, probs, steps, pad_depth, idxT, depthT, distsT)));
   }
+  return 0;
+}
+
+extern "C" size_t nsvf_inverse_cdf_stream_state_bytes(long long B) { return (size_t)(B > 0 ? B : 0) * sizeof(CdfParked); }
+
+extern "C" int nsvf_inverse_cdf_stream(nsvf_stream_t stream_, long long B, int max_hits, int max_steps,
+                                       float fixed_step_size, int k_begin, int k_end, const unsigned char* early_stop,
+                                       const int* ray_len, const int* quirk, const int* pts_idx, const float* min_depth,
+                                       const float* max_depth, const float* uniform_noise, long long noise_row_stride,
+                                       float noise_const, const float* probs, const float* steps, float pad_depth,
+                                       void* state, int* idxT, float* depthT, float* distsT) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSVF_REQUIRE(B >= 0 && max_hits > 0 && max_steps >= 0 && k_begin >= 0 && k_begin <= k_end, "inverse_cdf_stream: bad sizes");
+  NSVF_REQUIRE(state != nullptr && ((uintptr_t)state & 15) == 0, "inverse_cdf_stream: state must be a 16-byte aligned buffer");
+  if (B == 0 || k_end == k_begin) return 0;
+  NSVF_TIMED_LAUNCH("inverse_cdf_stream_kernel", stream,
+                    (inverse_cdf_stream_kernel<<<(unsigned)((B + kStreamThreads - 1) / kStreamThreads), kStreamThreads, 0,
+                                                 stream>>>(
+                        B, nsvf_march_plane_stride(B), max_hits, max_steps, fixed_step_size, k_begin, k_end, early_stop,
+                        ray_len, reinterpret_cast<const int2*>(quirk), pts_idx, min_depth, max_depth, uniform_noise,
+                        noise_row_stride, noise_const, probs, steps, pad_depth, reinterpret_cast<CdfParked*>(state), idxT,
+                        depthT, distsT)));
   return 0;
 }

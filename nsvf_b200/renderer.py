@@ -272,9 +272,14 @@ class VolumeRenderer(nn.Module):
                            _p(lazy["lazy_max_depth"]), _p(lz_noise), K, 0.5, _p(lazy["lazy_probs"]),
                            _p(lazy["lazy_steps"]), float(lazy["lazy_pad_depth"]))
 
+                # blocks are asked for in increasing order: the resumable serial sampler (one thread per ray, state
+                # parked in lz_state between blocks) instead of the any-order block kernel
+                lz_state = E(max(_L.nsvf_inverse_cdf_stream_state_bytes(B), 16), dtype=torch.uint8, device=dev)
+                p_state = _p(lz_state)
+
                 def fill_planes(k_begin, k_end, stop_ptr):
-                    _lib.check(_L.nsvf_inverse_cdf_block(st, B, lz[0], lz[1], lz[2], k_begin, k_end, stop_ptr, *lz_ptrs,
-                                                         p_idxT, p_depthT, p_distsT))
+                    _lib.check(_L.nsvf_inverse_cdf_stream(st, B, lz[0], lz[1], lz[2], k_begin, k_end, stop_ptr, *lz_ptrs,
+                                                          p_state, p_idxT, p_depthT, p_distsT))
             else:
                 def fill_planes(k_begin, k_end, stop_ptr):
                     _lib.check(_L.nsvf_march_transpose(st, B, K, ldk, k_begin, k_end, stop_ptr, _p(lens), _p(sidx),

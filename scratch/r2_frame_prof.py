@@ -11,7 +11,7 @@ rs, rd = synthetic.camera_rays(800, 800, 1, radius=4.5, seed=7, device=dev)
 rs, rd = rs[None, :, None, 0, :].contiguous(), rd[None].contiguous()
 field = sys.argv[1] if len(sys.argv) > 1 else "trivial"
 pipe, scene = bench.build_model(dev, "C3", train=False, field=field, tolerance=0.01, chunk=512, sigma_bias=2.0)
-pipe.lazy_sampling = os.environ.get("NSVF_LAZY", "0") == "1"
+pipe.lazy_sampling = os.environ.get("NSVF_LAZY", "1") == "1"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 with torch.no_grad():
     for _ in range(2):

@@ -222,6 +222,25 @@ def test_lazy_sampling_blocks_equal_eager_samples(cuda, deterministic):
     assert torch.equal(idxT[:, :B].t()[mask], eidx[mask])
     assert torch.equal(depT[:, :B].t()[mask], edep[mask]) and torch.equal(dstT[:, :B].t()[mask], edst[mask])
     assert bool((idxT[:, :B].t()[~mask] == -7).all()), "nothing beyond a ray's samples may be written"
+    # the resumable serial sampler (blocks in increasing order, state parked between calls); from the third block on
+    # every fourth ray is flagged as stopped and must not be touched any more
+    idxS, depS, dstS = torch.full_like(idxT, -7), torch.full_like(depT, -7.0), torch.full_like(dstT, -7.0)
+    state = torch.empty(L.nsvf_inverse_cdf_stream_state_bytes(B), dtype=torch.uint8, device=cuda)
+    stop = torch.zeros(B, dtype=torch.uint8, device=cuda)
+    edges = [0, K // 7, K // 3, K // 3 + 1, (2 * K) // 3, K]
+    for n, (k0, k1) in enumerate(zip(edges[:-1], edges[1:])):
+        if n == 2:
+            stop[::4] = 1
+        _lib.check(L.nsvf_inverse_cdf_stream(
+            _lib.current_stream(cuda), B, inter["min_depth"].shape[1], K, -1.0, k0, k1, p(stop) if n >= 2 else None,
+            p(lz["sampled_point_count"]), p(lz["lazy_quirk"]), p(lz["lazy_pts_idx"]), p(lz["lazy_min_depth"]),
+            p(lz["lazy_max_depth"]), p(noise), K, 0.5, p(lz["lazy_probs"]), p(lz["lazy_steps"]), 10000.0, p(state),
+            p(idxS), p(depS), p(dstS)))
+    want = mask & ~(stop.bool()[:, None] & (torch.arange(K, device=cuda)[None] >= edges[2]))
+    assert K > 20 and int(want.sum()) < int(mask.sum())
+    assert torch.equal(idxS[:, :B].t()[want], eidx[want])
+    assert torch.equal(depS[:, :B].t()[want], edep[want]) and torch.equal(dstS[:, :B].t()[want], edst[want])
+    assert bool((idxS[:, :B].t()[~want] == -7).all()), "stopped rays and positions beyond a ray's samples stay untouched"
 
 
 def test_lazy_rendering_equals_eager_rendering(cuda):
