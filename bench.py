@@ -50,7 +50,8 @@ VIEWS, RES, PIX_PER_VIEW = 4, 800, 2048
 # (profiles/r2_ncu_c3_frame.md; same scene, camera and chunking as frame_bench below)
 NCU_TRAFFIC = {"inverse_cdf_sampling_kernel": 7.305e9, "march_composite_fwd_kernel": 0.983e9,
                "march_compact_kernel": 21.5e6, "trilinear_fwd_kernel": 19.7e6, "march_epilogue_kernel": 14.7e6,
-               "aabb_intersect_kernel": 0.999e9, "march_transpose_kernel": None}
+               "aabb_intersect_sorted_kernel": None, "march_transpose_kernel": None, "inverse_cdf_plan_kernel": None,
+               "inverse_cdf_stream_kernel": None}
 LN_BWD_DRAM_TRAFFIC = 149.0e6  # bytes per launch: dram read 135 MB + write 14 MB, ncu --set full, [65536, 256] (profiles/r1b_ncu_ln_relu.md)
 METRIC = "rays/s (intersect+sample+composite), nsvf_base training step"
 
@@ -438,7 +439,7 @@ def run_ours(args):
                                       fr["hot_path_only(trivial field)"]["ms_per_800x800_frame"])
             for k in kernels:
                 k["traffic"] = NCU_TRAFFIC.get(k["kernel"])
-            hbm = [k for k in kernels if k["kernel"] != "aabb_intersect_kernel"]
+            hbm = [k for k in kernels if not k["kernel"].startswith("aabb_intersect")]
             if hbm:
                 # THE roofline of this line: the HBM-bound kernel of the ray-marching path with the largest share of the
                 # frame's device time; the field-MLP glue kernel that led round 1's line moves to roofline_mlp_glue
@@ -681,6 +682,11 @@ def frame_rooflines(dev, pipe, rs, rd, peak, peak_src, frame_ms):
         table = [  # (profile name, what, bound, bytes per FRAME as a function of launches)
             ("inverse_cdf_sampling_kernel", "inverse-CDF sampler, %d rays -> %d samples" % (rays, emitted), "hbm",
              lambda n: rays * (16 * P + 4 + 4) + 12 * emitted),
+            ("inverse_cdf_plan_kernel", "on-demand sampling, per-ray sample counts: %d hit lists in, 12 B per ray out" % rays,
+             "hbm", lambda n: rays * (16 * P + 4 + 12)),
+            ("inverse_cdf_stream_kernel", "on-demand sampling, resumable serial sampler: hit lists once, 12 B per evaluated "
+             "sample out, 96 B of parked state per live ray and block (lower bound: blocks run ahead of the windows)", "hbm",
+             lambda n: rays * 16 * P + 12 * ae + 96 * rays * n),
             ("trilinear_fwd_kernel", "trilinear interpolation fwd, %d samples in the frame's windows" % ae, "hbm",
              lambda n: 144 * ae + 0 * n),
             ("march_compact_kernel", "window compaction (12 B in + 32 B out per sample, 9 B per ray and window)", "hbm",

@@ -124,6 +124,32 @@ NSVF_API int nsvf_svo_intersect(nsvf_stream_t stream, int b, int T, int m, float
                        long long tree_batch_stride_nodes, int* idx, float* min_depth, float* max_depth,
                        void* workspace, size_t workspace_bytes);
 
+/* nsvf_svo_intersect followed by nsvf_sort_hits_by_depth (what SparseVoxelEncoder.ray_intersect does on the octree path,
+ * fairnr/modules/encoder.py:495-524) as ONE call with the same outputs: idx / depths sorted by entry depth (ties: DFS
+ * order), -1 / empty_depth fill, hits u8 [b, m] optional.  When the tree passes its consistency checks and the leaves
+ * lie on a lattice the rays walk that lattice instead of descending the tree (csrc/svo_intersect.cu, bottom); the
+ * results are the same either way.  Workspace: nsvf_svo_sorted_workspace_bytes(T, n_trees, b * m). */
+NSVF_API size_t nsvf_svo_sorted_workspace_bytes(int T, int n_trees, long long rays);
+NSVF_API int nsvf_svo_intersect_sorted(nsvf_stream_t stream, int b, int T, int m, float voxelsize, int n_max,
+                                       float empty_depth, const float* ray_start, const float* ray_dir,
+                                       const float* points, const int* children, long long tree_batch_stride_nodes,
+                                       int* idx, float* min_depth, float* max_depth, unsigned char* hits,
+                                       void* workspace, size_t workspace_bytes);
+/* The octree only changes when voxels are pruned or split: nsvf_svo_prepare fills a workspace of
+ * nsvf_svo_sorted_workspace_bytes(T, n_trees, 0) once (packed nodes, consistency checks, DFS ranks, leaf lattice) and
+ * nsvf_svo_intersect_sorted_prepared answers rays on it; ray_scratch: nsvf_svo_ray_scratch_bytes(n_trees, b * m) bytes,
+ * 128-byte aligned, any contents.  points / children must be the arrays the workspace was prepared from. */
+NSVF_API int nsvf_svo_prepare(nsvf_stream_t stream, int n_trees, int T, float voxelsize, const float* points,
+                              const int* children, long long tree_batch_stride_nodes, void* workspace,
+                              size_t workspace_bytes);
+NSVF_API size_t nsvf_svo_ray_scratch_bytes(int n_trees, long long rays);
+NSVF_API int nsvf_svo_intersect_sorted_prepared(nsvf_stream_t stream, int b, int T, int m, float voxelsize, int n_max,
+                                                float empty_depth, const float* ray_start, const float* ray_dir,
+                                                const float* points, const int* children,
+                                                long long tree_batch_stride_nodes, int* idx, float* min_depth,
+                                                float* max_depth, unsigned char* hits, const void* workspace,
+                                                size_t workspace_bytes, void* ray_scratch, size_t ray_scratch_bytes);
+
 /* The two clib entry points outside the NSVF path (kept for API completeness of the 7-function module):
  * ball_intersect, fairnr/clib/src/intersect.cpp:15-44 + intersect_gpu.cu:15-70 (no caller in the reference), and
  * triangle_intersect, intersect.cpp:120-146 + intersect_gpu.cu:240-347 (mesh encoder):

@@ -40,6 +40,15 @@ SIGNATURES = {
     "nsvf_svo_workspace_bytes": (c_size_t, [c_int, c_int]),
     "nsvf_svo_intersect": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
+    "nsvf_svo_sorted_workspace_bytes": (c_size_t, [c_int, c_int, c_ll]),
+    "nsvf_svo_intersect_sorted": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_int, c_float, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_size_t]),
+    "nsvf_svo_prepare": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_ll, c_void_p, c_size_t]),
+    "nsvf_svo_ray_scratch_bytes": (c_size_t, [c_int, c_ll]),
+    "nsvf_svo_intersect_sorted_prepared": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_int, c_float, c_void_p,
+                                                   c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p,
+                                                   c_void_p, c_void_p, c_size_t, c_void_p, c_size_t]),
     "nsvf_inverse_cdf_sampling": (c_int, [c_void_p, c_int, c_int, c_ll, c_int, c_int, c_int, c_float,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -190,6 +190,71 @@ def svo_intersect(ray_start, ray_dir, points, children, voxelsize, n_max, shared
     return idx, dmin, dmax
 
 
+class SvoIndex:
+    """An octree prepared for intersection (nsvf_svo_prepare): packed nodes, consistency flags, DFS ranks of the leaves
+    and their lattice, plus the arrays it was built from.  Build once per octree change, pass as `index=`."""
+
+    def __init__(self, points, children, voxelsize, shared_tree=False):
+        _check_float_cuda(points=points)
+        _chk(children.is_contiguous() and children.is_cuda and children.dtype == torch.int32,
+             "children must be a contiguous CUDA int tensor")
+        self.points, self.children, self.voxelsize = points, children, float(voxelsize)
+        if shared_tree:
+            self.T, self.stride, self.trees = points.shape[-2], 0, 1
+        else:
+            _chk(points.dim() == 3, "points must be [B, T, 3]")
+            self.T, self.stride, self.trees = points.shape[1], points.shape[1], points.shape[0]
+        _chk(children.shape[-2] == self.T and children.shape[-1] == 9, "children must be [.., T, 9]")
+        with torch.cuda.device(points.device):
+            self.ws = _workspace(_L.nsvf_svo_sorted_workspace_bytes(self.T, self.trees, 0), points.device)
+            _lib.check(_L.nsvf_svo_prepare(_lib.current_stream(points.device), self.trees, self.T, self.voxelsize,
+                                           _p(points), _p(children), self.stride, _p(self.ws), self.ws.numel()))
+
+    def query(self, ray_start, ray_dir, n_max, empty_depth):
+        _check_float_cuda(ray_start=ray_start, ray_dir=ray_dir)
+        b, m = ray_start.shape[0], ray_start.shape[1]
+        _chk(self.stride == 0 or b == self.trees, "one octree per batch row was prepared")
+        dev = ray_start.device
+        idx, dmin, dmax = _hit_outputs(ray_start, int(n_max))
+        hits = torch.empty((b, m), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            scratch = _workspace(_L.nsvf_svo_ray_scratch_bytes(self.trees, b * m), dev)
+            _lib.check(_L.nsvf_svo_intersect_sorted_prepared(
+                _lib.current_stream(dev), b, self.T, m, self.voxelsize, int(n_max), float(empty_depth), _p(ray_start),
+                _p(ray_dir), _p(self.points), _p(self.children), self.stride, _p(idx), _p(dmin), _p(dmax), _p(hits),
+                _p(self.ws), self.ws.numel(), _p(scratch), scratch.numel()))
+        return idx, dmin, dmax, hits.bool()
+
+
+def svo_intersect_sorted(ray_start, ray_dir, points, children, voxelsize, n_max, empty_depth=10000.0, shared_tree=False,
+                         index=None):
+    """Extension: svo_intersect + sort_hits_by_depth (the octree branch of SparseVoxelEncoder.ray_intersect,
+    encoder.py:495-524) in one call -> idx i32, min_depth, max_depth f32 [B,M,n_max] sorted by entry depth, hits bool [B,M].
+    `index` (SvoIndex of the same octree) skips the per-call preparation."""
+    if index is not None:
+        return index.query(ray_start, ray_dir, n_max, empty_depth)
+    _check_float_cuda(ray_start=ray_start, ray_dir=ray_dir, points=points)
+    _chk(children.is_contiguous(), "children must be a contiguous tensor")
+    _chk(children.is_cuda, "children must be a CUDA tensor")
+    _chk(children.dtype == torch.int32, "children must be an int tensor")
+    voxelsize, n_max = float(voxelsize), int(n_max)
+    b, m = ray_start.shape[0], ray_start.shape[1]
+    if shared_tree:
+        T, stride, trees = points.shape[-2], 0, 1
+    else:
+        _chk(points.dim() == 3 and points.shape[0] == b, "points must be [B, T, 3] with B == ray_start.size(0)")
+        T, stride, trees = points.shape[1], points.shape[1], b
+    _chk(children.shape[-2] == T and children.shape[-1] == 9, "children must be [.., T, 9]")
+    idx, dmin, dmax = _hit_outputs(ray_start, n_max)
+    hits = torch.empty((b, m), dtype=torch.uint8, device=ray_start.device)
+    with torch.cuda.device(ray_start.device):
+        ws = _workspace(_L.nsvf_svo_sorted_workspace_bytes(T, trees, b * m), ray_start.device)
+        _lib.check(_L.nsvf_svo_intersect_sorted(
+            _lib.current_stream(ray_start.device), b, T, m, voxelsize, n_max, float(empty_depth), _p(ray_start),
+            _p(ray_dir), _p(points), _p(children), stride, _p(idx), _p(dmin), _p(dmax), _p(hits), _p(ws), ws.numel()))
+    return idx, dmin, dmax, hits.bool()
+
+
 def ball_intersect(ray_start, ray_dir, points, radius, n_max):
     """fairnr/clib/src/intersect.cpp:15-44 (no caller in the reference; provided for API completeness)."""
     _check_float_cuda(ray_start=ray_start, ray_dir=ray_dir, points=points)

@@ -576,7 +576,8 @@ aabb_small_kernel(const __grid_constant__ AabbTree tree, long long tree_stride_b
 // depth + any(), i.e. SparseVoxelEncoder.ray_intersect's post-processing (encoder.py:519-524), one warp per ray.
 __global__ void __launch_bounds__(kAabbWarps * 32)
 sort_hits_kernel(long long rays, int n_max, int sort_slots, float empty_depth, int* __restrict__ idx,
-                 float* __restrict__ dmin, float* __restrict__ dmax, unsigned char* __restrict__ out_hit) {
+                 float* __restrict__ dmin, float* __restrict__ dmax, unsigned char* __restrict__ out_hit,
+                 const int* __restrict__ walk_active, long long rays_per_tree, const unsigned char* __restrict__ defer) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* h = aabb_smem + (size_t)warp * (3 * n_max + sort_slots);
   int* h_idx = reinterpret_cast<int*>(h);
@@ -584,6 +585,8 @@ sort_hits_kernel(long long rays, int n_max, int sort_slots, float empty_depth, i
   float* h_max = h + 2 * n_max;
   int* perm = reinterpret_cast<int*>(h + 3 * n_max);
   for (long long ray = (long long)blockIdx.x * kAabbWarps + warp; ray < rays; ray += (long long)gridDim.x * kAabbWarps) {
+    // octree queries answered by the lattice walk: only the rays it deferred to the traversal need this pass
+    if (walk_active != nullptr && walk_active[ray / rays_per_tree] != 0 && defer[ray] == 0) continue;
     const long long row = ray * n_max;
     // compact the valid entries to the front, keeping their order (the reference sorts all slots; -1 slots carry
     // MAX_DEPTH and end up last)
@@ -833,9 +836,10 @@ extern "C" int nsvf_aabb_intersect_prepared(nsvf_stream_t stream, int mode, int 
                   min_depth, max_depth, hits, const_cast<void*>(workspace), workspace_bytes);
 }
 
-extern "C" int nsvf_sort_hits_by_depth(nsvf_stream_t stream_, long long rays, int n_max, float empty_depth, int* idx,
-                                       float* min_depth, float* max_depth, unsigned char* hits) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+namespace nsvf {
+int sort_hits_run(cudaStream_t stream, long long rays, int n_max, float empty_depth, int* idx, float* min_depth,
+                  float* max_depth, unsigned char* hits, const int* walk_active, long long rays_per_tree,
+                  const unsigned char* defer) {
   NSVF_REQUIRE(rays >= 0 && n_max >= 0, "sort_hits_by_depth: negative size");
   if (rays == 0 || n_max == 0) return 0;
   int sort_slots = 64;
@@ -844,9 +848,15 @@ extern "C" int nsvf_sort_hits_by_depth(nsvf_stream_t stream_, long long rays, in
   NSVF_REQUIRE(smem <= 200 * 1024, "sort_hits_by_depth: n_max=%d needs %zu B of shared memory", n_max, smem);
   NSVF_CUDA_OK(cudaFuncSetAttribute(sort_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   long long want = (rays + kAabbWarps - 1) / kAabbWarps, cap = (long long)num_sms() * 6;
-  sort_hits_kernel<<<(unsigned)(want < cap ? want : cap), kAabbWarps * 32, smem, stream>>>(rays, n_max, sort_slots,
-                                                                                       empty_depth, idx, min_depth,
-                                                                                       max_depth, hits);
+  sort_hits_kernel<<<(unsigned)(want < cap ? want : cap), kAabbWarps * 32, smem, stream>>>(
+      rays, n_max, sort_slots, empty_depth, idx, min_depth, max_depth, hits, walk_active,
+      rays_per_tree > 0 ? rays_per_tree : 1, defer);
   NSVF_LAUNCH_OK("sort_hits_kernel");
   return 0;
+}
+}  // namespace nsvf
+
+extern "C" int nsvf_sort_hits_by_depth(nsvf_stream_t stream_, long long rays, int n_max, float empty_depth, int* idx,
+                                       float* min_depth, float* max_depth, unsigned char* hits) {
+  return sort_hits_run((cudaStream_t)stream_, rays, n_max, empty_depth, idx, min_depth, max_depth, hits, nullptr, 1, nullptr);
 }

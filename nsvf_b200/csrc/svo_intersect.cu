@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "nsvf_b200.h"
+#include "voxel_grid.cuh"
 
 namespace nsvf {
 
@@ -105,7 +106,7 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
 
 // every leaf climbs to the root and folds its exact box into its ancestors' unions
 __global__ void svo_climb_kernel(int T, SvoNode* __restrict__ tight, const int* __restrict__ parent,
-                                 int* __restrict__ flag_bad) {
+                                 int* __restrict__ flag_bad, int* __restrict__ leaf_count /* optional, zeroed */) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= T) return;
   SvoNode* tn = tight + (long long)blockIdx.y * T;
@@ -114,6 +115,8 @@ __global__ void svo_climb_kernel(int T, SvoNode* __restrict__ tight, const int* 
   float lo[3], hi[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) { lo[a] = tn[k].lo[a] + 0.0f; hi[a] = tn[k].hi[a] + 0.0f; }   // +0: canonical zero
+  int* cnt = leaf_count != nullptr ? leaf_count + (long long)blockIdx.y * T : nullptr;
+  if (cnt != nullptr) cnt[k] = 1;
   int p = par[k], steps = 0;
   while (p >= 0) {
     if (++steps > 64) { atomicExch(flag_bad + blockIdx.y, 1); break; }   // cycle or absurd depth
@@ -122,8 +125,40 @@ __global__ void svo_climb_kernel(int T, SvoNode* __restrict__ tight, const int* 
       atomic_min_float(&tn[p].lo[a], lo[a]);
       atomic_max_float(&tn[p].hi[a], hi[a]);
     }
+    if (cnt != nullptr) atomicAdd(cnt + p, 1);     // leaves below p
     p = par[p];
   }
+}
+
+// DFS emission rank of every leaf that is reachable from the root (node T-1), -1 for all other nodes.  The reference
+// pushes the children 0..7 of a hit node and pops the last one first (intersect_gpu.cu:219-228), so among siblings the
+// higher slot is visited first and a whole subtree is finished before the next sibling starts: the rank of a leaf is
+// the number of leaves in the subtrees of its ancestors' higher-slot siblings, summed along its path to the root.
+__global__ void svo_rank_kernel(int T, const SvoNode* __restrict__ loose, const int* __restrict__ parent,
+                                const int* __restrict__ leaf_count, int* __restrict__ rank) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= T) return;
+  const SvoNode* ln = loose + (long long)blockIdx.y * T;
+  const int* par = parent + (long long)blockIdx.y * T;
+  const int* cnt = leaf_count + (long long)blockIdx.y * T;
+  int r = -1;
+  if (ln[k].leaf) {
+    r = 0;
+    int node = k, p = par[k], steps = 0;
+    while (p >= 0 && ++steps <= 64) {
+      bool seen = false;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = ln[p].child[u];
+        if (c == node) { seen = true; continue; }
+        if (seen && c > -1 && c < T) r += cnt[c];      // slots above the one we came from
+      }
+      node = p;
+      p = par[p];
+    }
+    if (node != T - 1) r = -1;                        // not connected to the root: the traversal never gets there
+  }
+  rank[(long long)blockIdx.y * T + k] = r;
 }
 
 // widen the unions by one ulp (strict enclosure); internal nodes without any leaf can never be hit
@@ -145,7 +180,11 @@ svo_intersect_kernel(const SvoNode* __restrict__ nodes_all, const SvoNode* __res
                      const int* __restrict__ flag_bad, int T, long long rays_per_tree, int n_max,
                      const float* __restrict__ ray_start, const float* __restrict__ ray_dir,
                      int* __restrict__ out_idx, float* __restrict__ out_min, float* __restrict__ out_max,
-                     int* __restrict__ overflow_flag) {
+                     int* __restrict__ overflow_flag, const int* __restrict__ walk_active,
+                     const unsigned char* __restrict__ defer) {
+  // walk_active[tree] != 0: the lattice walk (voxel_grid.cu) has answered every ray of this tree except those it
+  // marked in defer[]; only they are traversed here, and the rows of the others are left alone
+  const bool only_deferred = walk_active != nullptr && walk_active[blockIdx.y] != 0;
   const SvoNode* loose = nodes_all + (long long)blockIdx.y * T;
   const bool use_tight = tight_all != nullptr && flag_bad[blockIdx.y] == 0;
   const SvoNode* tight = use_tight ? tight_all + (long long)blockIdx.y * T : loose;
@@ -155,7 +194,7 @@ svo_intersect_kernel(const SvoNode* __restrict__ nodes_all, const SvoNode* __res
        tile += (long long)gridDim.x * kSvoThreads) {
     const long long tile_rays = min((long long)kSvoThreads, rays_per_tree - tile);
     // 1) coalesced pre-fill of this tile's rows
-    {
+    if (!only_deferred) {
       const long long base = (ray_base + tile) * n_max;
       const long long cells = tile_rays * n_max;
       for (long long c = threadIdx.x; c < cells; c += kSvoThreads) {
@@ -166,8 +205,11 @@ svo_intersect_kernel(const SvoNode* __restrict__ nodes_all, const SvoNode* __res
     }
     __syncthreads();
     // 2) one thread per ray: the reference DFS
-    if (threadIdx.x < tile_rays) {
+    if (threadIdx.x < tile_rays && (!only_deferred || defer[ray_base + tile + threadIdx.x] != 0)) {
       const long long ray = ray_base + tile + threadIdx.x;
+      if (only_deferred) {     // (rare) this ray's row was not pre-filled
+        for (int c = 0; c < n_max; ++c) { out_idx[ray * n_max + c] = -1; out_min[ray * n_max + c] = 0.0f; out_max[ray * n_max + c] = 0.0f; }
+      }
       const float ox = ray_start[ray * 3 + 0], oy = ray_start[ray * 3 + 1], oz = ray_start[ray * 3 + 2];
       const float ix = ref_rcp(ray_dir[ray * 3 + 0]), iy = ref_rcp(ray_dir[ray * 3 + 1]),
                   iz = ref_rcp(ray_dir[ray * 3 + 2]);
@@ -265,7 +307,7 @@ extern "C" int nsvf_svo_intersect(nsvf_stream_t stream_, int b, int T, int m, fl
     NSVF_LAUNCH_OK("svo_pack_kernel");
     svo_prepare_kernel<<<grid, 256, 0, stream>>>(nodes, T, tight, parent, flag_bad);
     NSVF_LAUNCH_OK("svo_prepare_kernel");
-    svo_climb_kernel<<<grid, 256, 0, stream>>>(T, tight, parent, flag_bad);
+    svo_climb_kernel<<<grid, 256, 0, stream>>>(T, tight, parent, flag_bad, nullptr);
     NSVF_LAUNCH_OK("svo_climb_kernel");
     svo_finish_kernel<<<grid, 256, 0, stream>>>(T, tight);
     NSVF_LAUNCH_OK("svo_finish_kernel");
@@ -279,6 +321,157 @@ extern "C" int nsvf_svo_intersect(nsvf_stream_t stream_, int b, int T, int m, fl
   dim3 grid(gx, n_trees);
   NSVF_TIMED_LAUNCH("svo_intersect_kernel", stream, (svo_intersect_kernel<<<grid, kSvoThreads, 0, stream>>>(
                         nodes, getenv("NSVF_SVO_LOOSE") ? nullptr : tight, flag_bad, T, rays_per_tree, n_max, ray_start,
-                        ray_dir, idx, min_depth, max_depth, flag)));
+                        ray_dir, idx, min_depth, max_depth, flag, nullptr, nullptr)));
   return 0;
+}
+
+// ---- octree intersection with the encoder's post-processing fused in ----------------------------------------------
+// nsvf_svo_intersect + nsvf_sort_hits_by_depth in one call, and on a different algorithm whenever the tree allows it:
+// once every node box is known to enclose its children's boxes, a leaf is reported iff its OWN slab test hits (file
+// header), i.e. the answer is that of the voxel-set query over the leaves — and the leaves are a lattice, so the rays
+// walk it (voxel_grid.cu: a few hundred cell lookups instead of a DFS over eight-way nodes, hits already in depth
+// order).  What the DFS contributed besides the hit set is reproduced through the leaves' DFS ranks: ties in depth are
+// ordered by rank and a row that overflows n_max keeps the n_max smallest ranks, exactly what "first n_max leaves in
+// DFS order, then a stable sort by depth" gives.  Trees that fail the checks, leaves off a common lattice and rays with
+// NaN paths go through the traversal kernel + sort as before; every decision is taken on the device.
+// workspace of the tree: [nsvf_svo_workspace_bytes layout][leaf counts][DFS ranks][lattice]; per-call ray scratch:
+// [walk_active, one int per tree, 128-byte padded][defer, one byte per ray]
+static size_t svo_tree_offsets(int T, int n_trees, size_t* off_count, size_t* off_rank, size_t* off_grid) {
+  size_t o = (nsvf_svo_workspace_bytes(T, n_trees) + 127) / 128 * 128;
+  *off_count = o; o += ((size_t)T * n_trees * 4 + 127) / 128 * 128;
+  *off_rank = o;  o += ((size_t)T * n_trees * 4 + 127) / 128 * 128;
+  *off_grid = o;  o += voxel_grid_bytes(T) * (size_t)n_trees;
+  return o;
+}
+static size_t svo_scratch_bytes(int n_trees, long long rays) {
+  return ((size_t)n_trees * 4 + 127) / 128 * 128 + ((size_t)(rays > 0 ? rays : 0) + 127) / 128 * 128;
+}
+
+extern "C" size_t nsvf_svo_sorted_workspace_bytes(int T, int n_trees, long long rays) {
+  if (T <= 0 || n_trees <= 0) return 0;
+  size_t a, b, c;
+  return svo_tree_offsets(T, n_trees, &a, &b, &c) + svo_scratch_bytes(n_trees, rays);
+}
+
+enum { kSvoBuild = 1, kSvoTraverse = 2 };
+
+static int svo_sorted_run(cudaStream_t stream, int phase, int b, int T, int m, float voxelsize, int n_max,
+                          float empty_depth, const float* ray_start, const float* ray_dir, const float* points,
+                          const int* children, long long tree_batch_stride_nodes, int* idx, float* min_depth,
+                          float* max_depth, unsigned char* hits, void* tree_ws, size_t tree_ws_bytes, void* scratch,
+                          size_t scratch_bytes) {
+  NSVF_REQUIRE(b >= 0 && T >= 0 && m >= 0 && n_max >= 0, "svo_intersect_sorted: negative size");
+  const bool traverse = (phase & kSvoTraverse) != 0;
+  if (traverse && (b == 0 || m == 0 || n_max == 0)) return 0;
+  const long long rays = (long long)b * m;
+  NSVF_REQUIRE(T > 0, "svo_intersect_sorted: empty octree (the reference reads node T-1 as the root)");
+  NSVF_REQUIRE(tree_batch_stride_nodes == 0 || tree_batch_stride_nodes >= T,
+               "svo_intersect_sorted: tree_batch_stride_nodes must be 0 (shared octree) or >= T");
+  const int n_trees = tree_batch_stride_nodes == 0 ? 1 : b;
+  size_t off_count, off_rank, off_grid;
+  const size_t need = svo_tree_offsets(T, n_trees, &off_count, &off_rank, &off_grid);
+  NSVF_REQUIRE(tree_ws != nullptr && tree_ws_bytes >= need, "svo_intersect_sorted: workspace too small (%zu < %zu bytes)",
+               tree_ws_bytes, need);
+  NSVF_REQUIRE(((uintptr_t)tree_ws & 127) == 0, "svo_intersect_sorted: workspace must be 128-byte aligned");
+  char* ws = (char*)tree_ws;
+  const size_t flag_bytes = 128 + ((size_t)n_trees * 4 + 127) / 128 * 128;
+  int* flag = (int*)ws;
+  int* flag_bad = flag + 32;
+  SvoNode* nodes = (SvoNode*)(ws + flag_bytes);
+  SvoNode* tight = nodes + (size_t)T * n_trees;
+  int* parent = (int*)(tight + (size_t)T * n_trees);
+  int* leaf_count = (int*)(ws + off_count);
+  int* rank = (int*)(ws + off_rank);
+  const size_t grid_set_bytes = voxel_grid_bytes(T);
+  unsigned char* grid_ws = grid_set_bytes ? (unsigned char*)(ws + off_grid) : nullptr;
+  const long long pts_stride = tree_batch_stride_nodes * 3;
+  if (phase & kSvoBuild) {
+    NSVF_CUDA_OK(cudaMemsetAsync(flag, 0, flag_bytes, stream));
+    NSVF_CUDA_OK(cudaMemsetAsync(parent, 0xff, sizeof(int) * (size_t)T * n_trees, stream));
+    NSVF_CUDA_OK(cudaMemsetAsync(leaf_count, 0, sizeof(int) * (size_t)T * n_trees, stream));
+    const float half_voxel = voxelsize * 0.5f;
+    dim3 grid((T + 255) / 256, n_trees);
+    svo_pack_kernel<<<grid, 256, 0, stream>>>(points, children, tree_batch_stride_nodes, T, half_voxel, nodes);
+    NSVF_LAUNCH_OK("svo_pack_kernel");
+    svo_prepare_kernel<<<grid, 256, 0, stream>>>(nodes, T, tight, parent, flag_bad);
+    NSVF_LAUNCH_OK("svo_prepare_kernel");
+    svo_climb_kernel<<<grid, 256, 0, stream>>>(T, tight, parent, flag_bad, leaf_count);
+    NSVF_LAUNCH_OK("svo_climb_kernel");
+    svo_finish_kernel<<<grid, 256, 0, stream>>>(T, tight);
+    NSVF_LAUNCH_OK("svo_finish_kernel");
+    if (grid_ws != nullptr) {
+      svo_rank_kernel<<<grid, 256, 0, stream>>>(T, nodes, parent, leaf_count, rank);
+      NSVF_LAUNCH_OK("svo_rank_kernel");
+      if (voxel_grid_build(stream, n_trees, T, points, pts_stride, voxelsize, grid_ws, grid_set_bytes, rank, T)) return 1;
+    }
+  }
+  if (!traverse) return 0;
+  NSVF_REQUIRE(scratch != nullptr && scratch_bytes >= svo_scratch_bytes(n_trees, rays) && ((uintptr_t)scratch & 127) == 0,
+               "svo_intersect_sorted: ray scratch too small or not 128-byte aligned (%zu < %zu bytes)", scratch_bytes,
+               svo_scratch_bytes(n_trees, rays));
+  int* walk_active = (int*)scratch;
+  unsigned char* defer = (unsigned char*)scratch + ((size_t)n_trees * 4 + 127) / 128 * 128;
+  NSVF_CUDA_OK(cudaMemsetAsync(walk_active, 0, sizeof(int) * (size_t)n_trees, stream));
+  const long long rays_per_tree = n_trees == 1 ? rays : m;
+  if (grid_ws != nullptr) {
+    WalkOctree oct;
+    oct.rank = rank; oct.rank_stride = T; oct.veto = flag_bad; oct.active = walk_active; oct.defer = defer;
+    if (voxel_grid_walk(stream, 1, grid_ws, grid_set_bytes, n_trees, T, points, pts_stride, voxelsize, rays_per_tree,
+                        n_max, empty_depth, ray_start, ray_dir, idx, min_depth, max_depth, hits, &oct))
+      return 1;
+  }
+  long long want = (rays_per_tree + kSvoThreads - 1) / kSvoThreads;
+  long long cap = (long long)num_sms() * 8;
+  if (n_trees > 1) cap = (cap + n_trees - 1) / n_trees;
+  int gx = (int)(want < cap ? want : cap);
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, n_trees);
+  NSVF_TIMED_LAUNCH("svo_intersect_kernel", stream, (svo_intersect_kernel<<<grid, kSvoThreads, 0, stream>>>(
+                        nodes, getenv("NSVF_SVO_LOOSE") ? nullptr : tight, flag_bad, T, rays_per_tree, n_max, ray_start,
+                        ray_dir, idx, min_depth, max_depth, flag, grid_ws != nullptr ? walk_active : nullptr, defer)));
+  return sort_hits_run(stream, rays, n_max, empty_depth, idx, min_depth, max_depth, hits,
+                       grid_ws != nullptr ? walk_active : nullptr, rays_per_tree, defer);
+}
+
+extern "C" int nsvf_svo_intersect_sorted(nsvf_stream_t stream, int b, int T, int m, float voxelsize, int n_max,
+                                         float empty_depth, const float* ray_start, const float* ray_dir,
+                                         const float* points, const int* children, long long tree_batch_stride_nodes,
+                                         int* idx, float* min_depth, float* max_depth, unsigned char* hits,
+                                         void* workspace, size_t workspace_bytes) {
+  NSVF_REQUIRE(b >= 0 && T >= 0 && m >= 0 && n_max >= 0, "svo_intersect_sorted: negative size");
+  if (b == 0 || m == 0 || n_max == 0) return 0;
+  NSVF_REQUIRE(T > 0, "svo_intersect_sorted: empty octree (the reference reads node T-1 as the root)");
+  const int n_trees = tree_batch_stride_nodes == 0 ? 1 : b;
+  size_t a, c, d;
+  const size_t tree_bytes = svo_tree_offsets(T, n_trees, &a, &c, &d);
+  NSVF_REQUIRE(workspace != nullptr && workspace_bytes >= tree_bytes + svo_scratch_bytes(n_trees, (long long)b * m),
+               "svo_intersect_sorted: workspace too small (%zu < %zu bytes)", workspace_bytes,
+               tree_bytes + svo_scratch_bytes(n_trees, (long long)b * m));
+  return svo_sorted_run((cudaStream_t)stream, kSvoBuild | kSvoTraverse, b, T, m, voxelsize, n_max, empty_depth, ray_start,
+                        ray_dir, points, children, tree_batch_stride_nodes, idx, min_depth, max_depth, hits, workspace,
+                        tree_bytes, (char*)workspace + tree_bytes, workspace_bytes - tree_bytes);
+}
+
+extern "C" int nsvf_svo_prepare(nsvf_stream_t stream, int n_trees, int T, float voxelsize, const float* points,
+                                const int* children, long long tree_batch_stride_nodes, void* workspace,
+                                size_t workspace_bytes) {
+  NSVF_REQUIRE(n_trees >= 1 && (tree_batch_stride_nodes != 0 || n_trees == 1),
+               "svo_prepare: a shared octree (tree_batch_stride_nodes 0) is one tree");
+  return svo_sorted_run((cudaStream_t)stream, kSvoBuild, n_trees, T, 0, voxelsize, 0, 0.0f, nullptr, nullptr, points, children,
+                        tree_batch_stride_nodes, nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes, nullptr, 0);
+}
+
+extern "C" size_t nsvf_svo_ray_scratch_bytes(int n_trees, long long rays) {
+  return n_trees <= 0 ? 0 : svo_scratch_bytes(n_trees, rays);
+}
+
+extern "C" int nsvf_svo_intersect_sorted_prepared(nsvf_stream_t stream, int b, int T, int m, float voxelsize, int n_max,
+                                                  float empty_depth, const float* ray_start, const float* ray_dir,
+                                                  const float* points, const int* children,
+                                                  long long tree_batch_stride_nodes, int* idx, float* min_depth,
+                                                  float* max_depth, unsigned char* hits, const void* workspace,
+                                                  size_t workspace_bytes, void* ray_scratch, size_t ray_scratch_bytes) {
+  return svo_sorted_run((cudaStream_t)stream, kSvoTraverse, b, T, m, voxelsize, n_max, empty_depth, ray_start, ray_dir,
+                        points, children, tree_batch_stride_nodes, idx, min_depth, max_depth, hits,
+                        const_cast<void*>(workspace), workspace_bytes, ray_scratch, ray_scratch_bytes);
 }

@@ -58,15 +58,17 @@ __global__ void grid_init_kernel(unsigned char* ws, size_t per_set_bytes, int n_
 
 __global__ void __launch_bounds__(kGridThreads)
 grid_min_kernel(unsigned char* ws, size_t per_set_bytes, const float* __restrict__ points, long long points_stride,
-                int n) {
+                int n, const int* __restrict__ filter, long long filter_stride) {
   __shared__ int s_key[3];
   VoxelGridHeader* h = grid_header(ws, per_set_bytes, blockIdx.y);
   const float* pts = points + (long long)blockIdx.y * points_stride;
   if (threadIdx.x < 3) s_key[threadIdx.x] = 0x7fffffff;
   __syncthreads();
+  const int* keep = filter != nullptr ? filter + (long long)blockIdx.y * filter_stride : nullptr;
   float mn[3] = {INFINITY, INFINITY, INFINITY};
   bool bad = false;
   for (int i = blockIdx.x * kGridThreads + threadIdx.x; i < n; i += gridDim.x * kGridThreads) {
+    if (keep != nullptr && keep[i] < 0) continue;      // not a member of this voxel set (octree: not a reachable leaf)
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       const float p = pts[(long long)i * 3 + a];
@@ -104,7 +106,7 @@ __device__ __forceinline__ bool lattice_coords(const float* pts, int i, float gx
 
 __global__ void __launch_bounds__(kGridThreads)
 grid_extent_kernel(unsigned char* ws, size_t per_set_bytes, const float* __restrict__ points, long long points_stride,
-                   int n, float voxelsize) {
+                   int n, float voxelsize, const int* __restrict__ filter, long long filter_stride) {
   __shared__ int s_dim[3];
   VoxelGridHeader* h = grid_header(ws, per_set_bytes, blockIdx.y);
   const float* pts = points + (long long)blockIdx.y * points_stride;
@@ -112,9 +114,11 @@ grid_extent_kernel(unsigned char* ws, size_t per_set_bytes, const float* __restr
               gz = float_from_order_key(h->min_key[2]);
   if (threadIdx.x < 3) s_dim[threadIdx.x] = 0;
   __syncthreads();
+  const int* keep = filter != nullptr ? filter + (long long)blockIdx.y * filter_stride : nullptr;
   int mx[3] = {0, 0, 0};
   bool bad = false;
   for (int i = blockIdx.x * kGridThreads + threadIdx.x; i < n; i += gridDim.x * kGridThreads) {
+    if (keep != nullptr && keep[i] < 0) continue;
     int q[3];
     bad = bad || !lattice_coords(pts, i, gx, gy, gz, voxelsize, q[0], q[1], q[2]);
 #pragma unroll
@@ -145,7 +149,7 @@ grid_clear_kernel(unsigned char* ws, size_t per_set_bytes) {
 
 __global__ void __launch_bounds__(kGridThreads)
 grid_scatter_kernel(unsigned char* ws, size_t per_set_bytes, const float* __restrict__ points, long long points_stride,
-                    int n, float voxelsize) {
+                    int n, float voxelsize, const int* __restrict__ filter, long long filter_stride) {
   VoxelGridHeader* h = grid_header(ws, per_set_bytes, blockIdx.y);
   if (h->ok == 0) return;
   const float* pts = points + (long long)blockIdx.y * points_stride;
@@ -153,7 +157,9 @@ grid_scatter_kernel(unsigned char* ws, size_t per_set_bytes, const float* __rest
               gz = float_from_order_key(h->min_key[2]);
   const int dy = h->dims[1], dz = h->dims[2];
   int* cell = reinterpret_cast<int*>(h + 1);
+  const int* keep = filter != nullptr ? filter + (long long)blockIdx.y * filter_stride : nullptr;
   for (int i = blockIdx.x * kGridThreads + threadIdx.x; i < n; i += gridDim.x * kGridThreads) {
+    if (keep != nullptr && keep[i] < 0) continue;
     int qx, qy, qz;
     lattice_coords(pts, i, gx, gy, gz, voxelsize, qx, qy, qz);
     if (atomicCAS(&cell[((long long)qx * dy + qy) * dz + qz], -1, i) != -1) atomicOr(&h->bad, 1);   // two voxels, one cell
@@ -161,7 +167,7 @@ grid_scatter_kernel(unsigned char* ws, size_t per_set_bytes, const float* __rest
 }
 
 int voxel_grid_build(cudaStream_t stream, int n_sets, int n, const float* points, long long points_stride,
-                     float voxelsize, unsigned char* ws, size_t per_set_bytes) {
+                     float voxelsize, unsigned char* ws, size_t per_set_bytes, const int* filter, long long filter_stride) {
   const long long cap = (long long)(per_set_bytes - sizeof(VoxelGridHeader)) / 4;
   grid_init_kernel<<<(n_sets + 127) / 128, 128, 0, stream>>>(ws, per_set_bytes, n_sets, cap);
   NSVF_LAUNCH_OK("grid_init_kernel");
@@ -169,15 +175,17 @@ int voxel_grid_build(cudaStream_t stream, int n_sets, int n, const float* points
   const int sms = num_sms();
   if (bx > 2 * sms) bx = 2 * sms;
   dim3 gp(bx, n_sets);
-  grid_min_kernel<<<gp, kGridThreads, 0, stream>>>(ws, per_set_bytes, points, points_stride, n);
+  grid_min_kernel<<<gp, kGridThreads, 0, stream>>>(ws, per_set_bytes, points, points_stride, n, filter, filter_stride);
   NSVF_LAUNCH_OK("grid_min_kernel");
-  grid_extent_kernel<<<gp, kGridThreads, 0, stream>>>(ws, per_set_bytes, points, points_stride, n, voxelsize);
+  grid_extent_kernel<<<gp, kGridThreads, 0, stream>>>(ws, per_set_bytes, points, points_stride, n, voxelsize, filter,
+                                                     filter_stride);
   NSVF_LAUNCH_OK("grid_extent_kernel");
   long long bc = (cap + kGridThreads * 8 - 1) / (kGridThreads * 8);
   if (bc > 4 * sms) bc = 4 * sms;
   grid_clear_kernel<<<dim3((unsigned)bc, n_sets), kGridThreads, 0, stream>>>(ws, per_set_bytes);
   NSVF_LAUNCH_OK("grid_clear_kernel");
-  grid_scatter_kernel<<<gp, kGridThreads, 0, stream>>>(ws, per_set_bytes, points, points_stride, n, voxelsize);
+  grid_scatter_kernel<<<gp, kGridThreads, 0, stream>>>(ws, per_set_bytes, points, points_stride, n, voxelsize, filter,
+                                                      filter_stride);
   NSVF_LAUNCH_OK("grid_scatter_kernel");
   return 0;
 }
@@ -217,11 +225,13 @@ struct WalkRow {
   int* idx;
   float* dmin;
   float* dmax;
+  const int* prio;   // nullptr: ties and truncation go by voxel index (aabb); else by prio[v] (octree: DFS rank of the leaf)
   int n_max, cnt;
   bool unsorted;
   float last_tn;
-  int last_v;
+  int last_v;        // key of the last hit
 
+  __device__ __forceinline__ int key(int v) const { return prio != nullptr ? __ldg(prio + v) : v; }
   __device__ __forceinline__ void reset(int n_max_) {
     n_max = n_max_;
     cnt = 0;
@@ -230,9 +240,10 @@ struct WalkRow {
     last_v = -1;
   }
   __device__ __forceinline__ void note_order(int v, float tn) {
-    if (cnt > 0 && (tn < last_tn || (tn == last_tn && v < last_v))) unsorted = true;
+    const int k = key(v);
+    if (cnt > 0 && (tn < last_tn || (tn == last_tn && k < last_v))) unsorted = true;
     last_tn = tn;
-    last_v = v;
+    last_v = k;
   }
   __device__ __forceinline__ void add(int v, float tn, float tf) {
     if (MODE == kWalkAnyHit) { cnt = 1; return; }
@@ -244,27 +255,29 @@ struct WalkRow {
       ++cnt;
       return;
     }
-    // full: the reference keeps the n_max SMALLEST voxel indices (its scan runs in index order)
+    // full: the reference keeps the n_max FIRST hits of its own visiting order (ascending voxel index for the linear
+    // scan, DFS order for the octree): the n_max smallest keys
     int worst = -1, at = 0;
     for (int s = 0; s < n_max; ++s) {
-      const int w = idx[s];
+      const int w = key(idx[s]);
       if (w > worst) { worst = w; at = s; }
     }
-    if (v < worst) {
+    if (key(v) < worst) {
       idx[at] = v; dmin[at] = tn; dmax[at] = tf;
       unsorted = true;
     }
   }
-  // insertion sort of the row by (depth, index): only after an order violation was seen
+  // insertion sort of the row by (depth, key): only after an order violation was seen
   __device__ __forceinline__ void repair() {
     for (int s = 1; s < cnt; ++s) {
       const int v = idx[s];
+      const int kv = key(v);
       const float tn = dmin[s], tf = dmax[s];
       int t = s - 1;
       while (t >= 0) {
         const float e = dmin[t];
         const int w = idx[t];
-        if (!(e > tn || (e == tn && w > v))) break;
+        if (!(e > tn || (e == tn && key(w) > kv))) break;
         idx[t + 1] = w; dmin[t + 1] = e; dmax[t + 1] = dmax[t];
         --t;
       }
@@ -389,8 +402,13 @@ __global__ void __launch_bounds__(kWalkThreads)
 grid_walk_kernel(const unsigned char* __restrict__ ws, size_t per_set_bytes, const float* __restrict__ points,
                  long long points_stride, int n, float voxelsize, long long rays_per_set, int n_max, float empty_depth,
                  const float* __restrict__ ray_start, const float* __restrict__ ray_dir, int* __restrict__ out_idx,
-                 float* __restrict__ out_min, float* __restrict__ out_max, unsigned char* __restrict__ out_hit) {
-  if (!voxel_grid_usable(ws, per_set_bytes, blockIdx.y)) return;   // the hierarchy kernels take this voxel set
+                 float* __restrict__ out_min, float* __restrict__ out_max, unsigned char* __restrict__ out_hit,
+                 WalkOctree oct) {
+  // the hierarchy / octree kernels take this voxel set when it is not a lattice (or the octree is not a proper tree)
+  const bool mine = voxel_grid_usable(ws, per_set_bytes, blockIdx.y) && (oct.veto == nullptr || oct.veto[blockIdx.y] == 0);
+  if (oct.active != nullptr && blockIdx.x == 0 && threadIdx.x == 0) oct.active[blockIdx.y] = mine ? 1 : 0;
+  if (!mine) return;
+  const int* prio = oct.rank != nullptr ? oct.rank + (long long)blockIdx.y * oct.rank_stride : nullptr;
   constexpr int kWarps = kWalkThreads / 32;
   constexpr int kStage = MODE == kWalkDepthSorted ? kWarps * 32 * kRingLd : 1;
   __shared__ int s_idx[kStage];
@@ -415,6 +433,11 @@ grid_walk_kernel(const unsigned char* __restrict__ ws, size_t per_set_bytes, con
     path.setup(h, voxelsize, r, dx, dy, dz);
     WalkRow<MODE> row;
     row.reset(n_max);
+    row.prio = prio;
+    // octree queries: the reference's answer for rays with NaN paths (and rays this walk does not trust) depends on the
+    // loose internal boxes, so those rays are left to the traversal kernel (defer[ray] = 1, nothing written here)
+    const bool deferred = oct.defer != nullptr && live && !(r.regular && path.trusted);
+    if (oct.defer != nullptr && live) oct.defer[ray] = deferred ? 1 : 0;
     row.idx = MODE == kWalkAnyHit ? nullptr : out_idx + ray * n_max;
     row.dmin = MODE == kWalkAnyHit ? nullptr : out_min + ray * n_max;
     row.dmax = MODE == kWalkAnyHit ? nullptr : out_max + ray * n_max;
@@ -433,8 +456,8 @@ grid_walk_kernel(const unsigned char* __restrict__ ws, size_t per_set_bytes, con
       float* ring_b = s_max + (warp * 32 + lane) * kRingLd;
       const long long tile_row0 = (ray_base + tile * 32) * n_max;
       int flushed = 0;
-      bool slow = live && !path.trusted;      // redo on the slow path: untrusted ray, row or ring overflow
-      bool walking = live && path.trusted && path.more();
+      bool slow = live && !path.trusted && !deferred;      // redo on the slow path: untrusted ray, row or ring overflow
+      bool walking = live && path.trusted && !deferred && path.more();
       auto flush = [&](int at_least) {        // warp-uniform; writes up to 8 staged hits of every ray
         while (__any_sync(NSVF_FULL_MASK, row.cnt - flushed >= at_least)) {
 #pragma unroll 1
@@ -478,9 +501,9 @@ grid_walk_kernel(const unsigned char* __restrict__ ws, size_t per_set_bytes, con
         walk_direct<MODE>(h, pts, n, hv, r, path, row);
       }
       if (live && row.unsorted) row.repair();
-      if (live && out_hit != nullptr) out_hit[ray] = row.cnt > 0;
+      if (live && !deferred && out_hit != nullptr) out_hit[ray] = row.cnt > 0;
       // tails of the 32 rows of this tile: coalesced -1 / fill depth
-      const int my_cnt = live ? row.cnt : n_max;
+      const int my_cnt = (live && !deferred) ? row.cnt : n_max;
       for (int k = 0; k < 32; ++k) {
         const int c = __shfl_sync(NSVF_FULL_MASK, my_cnt, k);
         const long long r0 = tile_row0 + (long long)k * n_max;
@@ -498,7 +521,9 @@ grid_walk_kernel(const unsigned char* __restrict__ ws, size_t per_set_bytes, con
 int voxel_grid_walk(cudaStream_t stream, int mode, const unsigned char* ws, size_t per_set_bytes, int n_sets, int n,
                     const float* points, long long points_stride, float voxelsize, long long rays_per_set, int n_max,
                     float empty_depth, const float* ray_start, const float* ray_dir, int* idx, float* min_depth,
-                    float* max_depth, unsigned char* hit) {
+                    float* max_depth, unsigned char* hit, const WalkOctree* octree) {
+  WalkOctree oct{};
+  if (octree != nullptr) oct = *octree;
   const long long tiles = (rays_per_set + 31) / 32;
   long long want = (tiles + kWalkThreads / 32 - 1) / (kWalkThreads / 32), cap = (long long)num_sms() * 16;
   if (n_sets > 1) cap = (cap + n_sets - 1) / n_sets;
@@ -508,9 +533,10 @@ int voxel_grid_walk(cudaStream_t stream, int mode, const unsigned char* ws, size
   NSVF_TIMED_LAUNCH(NAME, stream,                                                                                   \
                     (grid_walk_kernel<MODE><<<grid, kWalkThreads, 0, stream>>>(                                     \
                         ws, per_set_bytes, points, points_stride, n, voxelsize, rays_per_set, n_max, empty_depth,   \
-                        ray_start, ray_dir, idx, min_depth, max_depth, hit)))
+                        ray_start, ray_dir, idx, min_depth, max_depth, hit, oct)))
   NSVF_REQUIRE(mode == kWalkDepthSorted || mode == kWalkAnyHit, "voxel_grid_walk: mode must be 1 (sorted) or 2 (any hit)");
-  if (mode == kWalkDepthSorted) NSVF_WALK(kWalkDepthSorted, "aabb_intersect_sorted_kernel");
+  if (mode == kWalkDepthSorted && octree != nullptr) NSVF_WALK(kWalkDepthSorted, "svo_intersect_sorted_kernel");
+  else if (mode == kWalkDepthSorted) NSVF_WALK(kWalkDepthSorted, "aabb_intersect_sorted_kernel");
   else NSVF_WALK(kWalkAnyHit, "aabb_hit_mask_kernel");
 #undef NSVF_WALK
   return 0;

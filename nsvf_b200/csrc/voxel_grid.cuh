@@ -26,14 +26,33 @@ __device__ __forceinline__ bool voxel_grid_usable(const unsigned char* ws, size_
 }
 #endif
 
+// Octree queries (svo_intersect.cu) walk the lattice of the LEAVES: `rank` (per node, DFS emission rank of a reachable
+// leaf, -1 for everything else) selects the members of the voxel set and replaces the voxel index as tie-break /
+// truncation key; veto[set] != 0 (the tree failed its checks) hands the set back to the traversal kernel;
+// active[set] receives whether the walk took the set; defer[ray] = 1 marks rays left to the traversal kernel.
+struct WalkOctree {
+  const int* rank;
+  long long rank_stride;
+  const int* veto;
+  int* active;
+  unsigned char* defer;
+};
+
 // bytes of one voxel set's header + cells (multiple of 128); 0 when the lattice path is switched off
 size_t voxel_grid_bytes(int n);
+// filter (optional, per set `filter_stride` ints apart): points with filter[i] < 0 are not members of the set
 int voxel_grid_build(cudaStream_t stream, int n_sets, int n, const float* points, long long points_stride,
-                     float voxelsize, unsigned char* ws, size_t per_set_bytes);
+                     float voxelsize, unsigned char* ws, size_t per_set_bytes, const int* filter = nullptr,
+                     long long filter_stride = 0);
 // mode as in aabb_intersect.cu: 1 = sorted by entry depth, 2 = any-hit mask
 int voxel_grid_walk(cudaStream_t stream, int mode, const unsigned char* ws, size_t per_set_bytes, int n_sets, int n,
                     const float* points, long long points_stride, float voxelsize, long long rays_per_set, int n_max,
                     float empty_depth, const float* ray_start, const float* ray_dir, int* idx, float* min_depth,
-                    float* max_depth, unsigned char* hit);
+                    float* max_depth, unsigned char* hit, const WalkOctree* octree = nullptr);
+
+// sort_hits_by_depth (aabb_intersect.cu) restricted to the rays the walk deferred (walk_active / defer may be NULL: all rays)
+int sort_hits_run(cudaStream_t stream, long long rays, int n_max, float empty_depth, int* idx, float* min_depth,
+                  float* max_depth, unsigned char* hits, const int* walk_active, long long rays_per_tree,
+                  const unsigned char* defer);
 
 }  // namespace nsvf

@@ -112,6 +112,7 @@ class SparseVoxelEncoder(nn.Module):
         """Called by every method that changes the voxel set (pruning, splitting, state loading)."""
         self._runtime_caches["geometry"] = None
         self._runtime_caches["aabb_index"] = None
+        self._runtime_caches["svo_index"] = None
 
     def _kept_geometry(self):
         """(feats i64, feats i32, points with the x shift) of the kept voxels.  The reference boolean-indexes feats /
@@ -134,8 +135,10 @@ class SparseVoxelEncoder(nn.Module):
         values = self.values.weight[: self.num_keys]
         encoder_states = {"voxel_vertex_idx": feats, "voxel_center_xyz": points, "voxel_vertex_emb": values}
         if self.use_octree:
-            encoder_states["voxel_octree_center_xyz"] = self.flatten_centers.clone()
-            encoder_states["voxel_octree_children_idx"] = self.flatten_children.clone()
+            # (the reference clones both per call; nothing downstream writes to them, and handing out the cached
+            # tensors lets ray_intersect recognise an unchanged octree and reuse its prepared index)
+            encoder_states["voxel_octree_center_xyz"] = self.flatten_centers
+            encoder_states["voxel_octree_children_idx"] = self.flatten_children
         if id is not None:   # [1, ...] leading shape dimension, as the reference adds for id
             encoder_states = {k: v.unsqueeze(0) for k, v in encoder_states.items()}
         return encoder_states
@@ -159,6 +162,17 @@ class SparseVoxelEncoder(nn.Module):
             self._runtime_caches["aabb_index"] = cache
         return cache[1]
 
+    def _svo_index(self, centers, children):
+        """The prepared octree (clib._ext.SvoIndex) of `centers` / `children` [S, T, ..]: rebuilt only when they change."""
+        c, ch = centers.float().contiguous(), children.int().contiguous()
+        key = (centers.data_ptr(), centers._version, children.data_ptr(), children._version, tuple(c.shape),
+               self._voxel_size_float())
+        cache = self._runtime_caches.get("svo_index")
+        if cache is None or cache[0] != key:
+            cache = (key, clib._ext.SvoIndex(c, ch, key[5]))
+            self._runtime_caches["svo_index"] = cache
+        return cache[1]
+
     def ray_intersect(self, ray_start, ray_dir, encoder_states):
         point_feats = encoder_states["voxel_vertex_idx"]
         point_xyz = encoder_states["voxel_center_xyz"]
@@ -173,16 +187,13 @@ class SparseVoxelEncoder(nn.Module):
             children = encoder_states["voxel_octree_children_idx"]
             if centers.dim() == 2:
                 centers, children = centers.unsqueeze(0), children.unsqueeze(0)
-            pts_idx, min_depth, max_depth = clib.svo_ray_intersect(
-                self._voxel_size_float(), self._max_hits_int(), centers, children, ray_start, ray_dir)
-            # masked_fill + sort by entry depth + gather + any() (encoder.py:519-524) as one in-place kernel; fp16 models
-            # get their depths cast to fp32 for it and back afterwards (no eager-torch path)
-            in_dtype = min_depth.dtype
-            pts_idx = pts_idx.int().contiguous()
-            min_depth, max_depth = min_depth.float().contiguous(), max_depth.float().contiguous()
-            hits = clib._ext.sort_hits_by_depth(pts_idx, min_depth, max_depth, MAX_DEPTH)
-            if in_dtype != torch.float32:
-                min_depth, max_depth = min_depth.to(in_dtype), max_depth.to(in_dtype)
+            # octree intersection + masked_fill + sort by entry depth + gather + any() (encoder.py:495-524) in one call;
+            # fp16 models get fp32 depths cast back afterwards (no eager-torch path)
+            index = self._svo_index(centers, children)
+            pts_idx, min_depth, max_depth, hits = clib._ext.svo_intersect_sorted(
+                ray_start.float().contiguous(), ray_dir.float().contiguous(), index.points, index.children,
+                index.voxelsize, self._max_hits_int(), MAX_DEPTH, index=index)
+            min_depth, max_depth = min_depth.type_as(ray_start), max_depth.type_as(ray_start)
         else:
             # intersection + masked_fill + sort + gather + any() of encoder.py:511-524 in ONE kernel
             index = self._aabb_index(point_xyz)

@@ -400,3 +400,72 @@ def test_voxel_sets_off_the_lattice_use_the_hierarchy(cuda, ref_ext):
         idx, dmin, dmax, hits = ours.aabb_intersect_sorted(rs, rd, p, scene.voxel_size, 60, 10000.0)
         assert torch.equal(hits, r_hits) and torch.equal(dmin, r_min) and torch.equal(idx.sort(-1)[0], r_idx.sort(-1)[0])
         assert torch.equal(ours.aabb_hit_mask(rs, rd, p, scene.voxel_size), r_hits)
+
+
+def _svo_then_sort(rs, rd, centers, children, vs, n_max, **kw):
+    idx, dmin, dmax = ours.svo_intersect(rs, rd, centers, children, vs, n_max, **kw)
+    idx, dmin, dmax = idx.clone(), dmin.clone(), dmax.clone()
+    hits = ours.sort_hits_by_depth(idx, dmin, dmax, 10000.0)
+    return idx, dmin, dmax, hits
+
+
+@pytest.mark.parametrize("times,n_max", [(0, 60), (1, 90), (2, 135), (1, 5)])
+def test_svo_sorted_equals_traversal_then_sort(cuda, ref_ext, times, n_max):
+    """nsvf_svo_intersect_sorted (rays walk the lattice of the leaves; DFS ranks order ties and decide truncation) ==
+    the reference DFS traversal followed by the stable depth sort, entry for entry — awkward rays, overflowing rows,
+    shared and per-batch trees — and == the same call with the lattice switched off."""
+    pts0 = synthetic.carve_shell(synthetic.bbox_voxels([-1.2] * 3, [1.2] * 3, 0.4))
+    p, vs = synthetic.split_points(pts0, 0.4, times)
+    pts, centers, children = _svo_inputs(p, vs, cuda)
+    rs, rd = _awkward_rays(pts, vs, 4096, cuda)
+    want = _svo_then_sort(rs, rd, centers, children, vs, n_max, shared_tree=True)
+    walk, tree = _both_paths(lambda: ours.svo_intersect_sorted(rs, rd, centers, children, vs, n_max, 10000.0, shared_tree=True))
+    _cmp3(walk[:3], want[:3], "svo sorted (walk) vs traversal + sort")
+    _cmp3(tree[:3], want[:3], "svo sorted (lattice off) vs traversal + sort")
+    assert torch.equal(walk[3], want[3]) and torch.equal(tree[3], want[3])
+    assert int((walk[0] >= 0).sum()) > 4096
+    if n_max == 5:
+        assert int((walk[0] >= 0).sum(-1).max()) == 5
+    # an octree prepared once (nsvf_svo_prepare) answers any number of ray batches
+    index = ours.SvoIndex(centers, children, vs, shared_tree=True)
+    for sl in (slice(0, 4096), slice(500, 2500)):
+        a = ours.svo_intersect_sorted(rs[:, sl].contiguous(), rd[:, sl].contiguous(), centers, children, vs, n_max, 10000.0,
+                                      index=index)
+        _cmp3(a[:3], [t[:, sl] for t in want[:3]], "prepared octree vs one-shot")
+        assert torch.equal(a[3], want[3][:, sl])
+    # reference traversal + torch post-processing (tie rows as sets: torch.sort is not stable)
+    ref = ref_ext.svo_intersect(rs, rd, centers[None].contiguous(), children[None].contiguous(), vs, n_max)
+    r_idx, r_min, r_max, r_hits = wrappers.sort_hits(*ref)
+    assert torch.equal(walk[3], r_hits) and torch.equal(walk[1], r_min)
+    assert torch.equal(walk[0].sort(-1)[0], r_idx.sort(-1)[0])
+    # one tree per batch row
+    cB = torch.stack([centers, centers + 0.21]).contiguous()
+    chB = children[None].expand(2, -1, -1).contiguous()
+    rsB, rdB = rs.view(2, -1, 3).contiguous(), rd.view(2, -1, 3).contiguous()
+    _cmp3(ours.svo_intersect_sorted(rsB, rdB, cB, chB, vs, n_max, 10000.0)[:3], _svo_then_sort(rsB, rdB, cB, chB, vs, n_max)[:3],
+          "svo sorted, two trees")
+
+
+def test_svo_sorted_on_trees_the_walk_must_refuse(cuda, ref_ext):
+    """A tree whose boxes do not enclose their children, and a tree with a leaf that is not connected to the root: the
+    first goes to the traversal kernel as a whole, the second keeps the walk but must not report the orphan."""
+    pts0 = synthetic.carve_shell(synthetic.bbox_voxels([-2.4] * 3, [2.4] * 3, 0.4))
+    pts, centers, children = _svo_inputs(pts0, 0.4, cuda)
+    n = pts.shape[0]
+    rs, rd = synthetic.camera_rays(48, 48, 1, device=cuda)
+    rs = rs.expand_as(rd).contiguous()
+    bad_c, bad_ch = centers.clone(), children.clone()
+    internal = torch.arange(n, centers.shape[0] - 1, device=cuda)
+    bad_c[internal[::3]] += 0.35
+    bad_ch[internal[1::5], 8] = torch.clamp(bad_ch[internal[1::5], 8] // 4, min=2)
+    _cmp3(ours.svo_intersect_sorted(rs, rd, bad_c, bad_ch, 0.4, 60, 10000.0, shared_tree=True)[:3],
+          _svo_then_sort(rs, rd, bad_c, bad_ch, 0.4, 60, shared_tree=True)[:3], "non-enclosing tree")
+    # cut one leaf out of its parent's child list: the node stays in the arrays but the DFS can no longer reach it
+    orphan_ch = children.clone()
+    hit_leaf = int(ours.svo_intersect(rs, rd, centers, children, 0.4, 60, shared_tree=True)[0].max())
+    rows, cols = (orphan_ch[:, :8] == hit_leaf).nonzero(as_tuple=True)
+    assert rows.numel() == 1
+    orphan_ch[rows[0], cols[0]] = -1
+    got = ours.svo_intersect_sorted(rs, rd, centers, orphan_ch, 0.4, 60, 10000.0, shared_tree=True)
+    _cmp3(got[:3], _svo_then_sort(rs, rd, centers, orphan_ch, 0.4, 60, shared_tree=True)[:3], "tree with an orphan leaf")
+    assert int((got[0] == hit_leaf).sum()) == 0
