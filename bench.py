@@ -678,12 +678,15 @@ def frame_rooflines(dev, pipe, rs, rd, peak, peak_src, frame_ms):
         ae = int(out["ae"])
         emitted = int(out["samples"]["sampled_point_count"].sum()) if "sampled_point_count" in out["samples"] else ae
         P, n_vox = int(pipe.encoder.max_hits), int(pipe.encoder.num_voxels)
+        lz_idx = out["samples"].get("lazy_pts_idx") if isinstance(out["samples"], dict) else None
+        valid_bins = int(lz_idx.ne(-1).sum()) if lz_idx is not None else rays * P
         all_rays = rd.numel() // 3
         table = [  # (profile name, what, bound, bytes per FRAME as a function of launches)
             ("inverse_cdf_sampling_kernel", "inverse-CDF sampler, %d rays -> %d samples" % (rays, emitted), "hbm",
              lambda n: rays * (16 * P + 4 + 4) + 12 * emitted),
-            ("inverse_cdf_plan_kernel", "on-demand sampling, per-ray sample counts: %d hit lists in, 12 B per ray out" % rays,
-             "hbm", lambda n: rays * (16 * P + 4 + 12)),
+            ("inverse_cdf_plan_kernel", "on-demand sampling, per-ray sample counts: the probabilities of the %d valid bins twice "
+             "(two sequential passes; the second hits L1/L2), 16 bisection probes, steps and 4 trailing-loop depths in, "
+             "12 B per ray out" % valid_bins, "hbm", lambda n: 4 * valid_bins + rays * (64 + 4 + 16 + 12)),
             ("inverse_cdf_stream_kernel", "on-demand sampling, resumable serial sampler: hit lists once, 12 B per evaluated "
              "sample out, 96 B of parked state per live ray and block (lower bound: blocks run ahead of the windows)", "hbm",
              lambda n: rays * 16 * P + 12 * ae + 96 * rays * n),

@@ -719,20 +719,22 @@ inverse_cdf_stream_kernel(long long B, long long ldb, int P, int max_steps, floa
 constexpr int kLazyWarps = 8;       // block kernel: 32 rays per CTA, 4 per warp
 constexpr int kLazyBlock = 64;      // positions per block (multiple of 32)
 
-__global__ void __launch_bounds__(kCdfWarps * 32)
+// One THREAD per ray.  Only the number of samples is wanted, and that needs three things from the bins: the total
+// probability (is there a step beyond it?), the bin of the last in-range step with the depth it produces, and the
+// few bins the trailing loop walks — two sequential passes over the ray's probabilities in registers, no tables.  The
+// first generation spent one warp (and 4 P floats of shared memory) per ray on the full set-up of the eager kernel:
+// 1.18 ms for the 640 k rays of the C3 frame, latency-bound on lane 0's dependent adds.
+constexpr int kPlanThreads = 128;
+
+__global__ void __launch_bounds__(kPlanThreads)
 inverse_cdf_plan_kernel(int b, int num_rays, long long valid_rays, int ray_chunk, int P, int max_steps,
                         float fixed_step_size, const int* __restrict__ pts_idx, const float* __restrict__ min_depth,
                         const float* __restrict__ max_depth, const float* __restrict__ noise, float noise_const,
                         const float* __restrict__ probs, const float* __restrict__ steps, int* __restrict__ ray_len,
-                        int2* __restrict__ quirk, int* __restrict__ meta /* [max_len, holes, fallback rays] */) {
-  extern __shared__ __align__(16) float cdf_smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* base = cdf_smem + (size_t)warp * 4 * P;
-  int* s_idx = reinterpret_cast<int*>(base);
-  float *s_min = base + P, *s_max = base + 2 * P, *s_cum = base + 3 * P;
-  int my_max = 0;
-  for (long long ray = (long long)blockIdx.x * kCdfWarps + warp; ray < valid_rays;
-       ray += (long long)gridDim.x * kCdfWarps) {
+                        int2* __restrict__ quirk, int* meta /* [max_len, holes, fallback rays] */) {
+  const long long ray = (long long)blockIdx.x * kPlanThreads + threadIdx.x;
+  int lastv = 0;
+  if (ray < valid_rays) {
     const long long H = ray * P;
     const long long batch = ray / num_rays;
     const int rr = (int)(ray - batch * num_rays);
@@ -743,53 +745,112 @@ inverse_cdf_plan_kernel(int b, int num_rays, long long valid_rays, int ray_chunk
     if (rr + 1 < min(c0 + ray_chunk, num_rays)) nxt = ray + 1;
     else if (batch + 1 < b) nxt = (batch + 1) * num_rays + c0;
     const int next_idx0 = nxt >= 0 ? pts_idx[(nxt < valid_rays ? nxt : 0) * P] : -1;
-    // leading valid bins of the block row's ray 0 (hit lists are -1-terminated: sorted by the intersection)
-    int row0_nb = P;
-    for (int j0 = 0; j0 < P; j0 += 32) {
-      const int j = j0 + lane;
-      const unsigned m = __ballot_sync(NSVF_FULL_MASK, j < P && row0_idx[j] == -1);
-      if (m) { row0_nb = j0 + __ffs(m) - 1; break; }
+    // hit lists are -1-terminated (sorted by the intersection): the first -1 by bisection.  nb: usable bins of this
+    // ray (bin 0 is always used); row0_nb: leading valid bins of ray 0 of the block row (its stop test reads THAT ray)
+    int nb, row0_nb;
+    {
+      int lo = 1, hi = P;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (pts_idx[H + mid] == -1) hi = mid; else lo = mid + 1; }
+      nb = lo;
+      lo = 0; hi = P;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (row0_idx[mid] == -1) hi = mid; else lo = mid + 1; }
+      row0_nb = lo;
     }
     const float* noise_row = noise != nullptr ? noise + ray * max_steps : nullptr;
-    const CdfRay r = cdf_ray_setup(H, P, max_steps, fixed_step_size, steps[ray], pts_idx, min_depth, max_depth, probs,
-                                   noise_row, noise_const, s_idx, s_min, s_max, s_cum);
-    int lastv = 0, n_valid = 0;
-    if (lane == 0) {
-      if (r.ok) {
-        // step samples and bin ends of the main loop: positions [0, n_in + b_last), all with a valid voxel id
-        lastv = n_valid = min(r.n_in + r.b_last, max_steps);
-        cdf_trailing(r, P, noise_row, noise_const, max_steps, row0_nb, next_idx0, s_idx, s_min, s_max, s_cum,
-                     min_depth + H, max_depth + H, [&](int pos, int oi, float, float) {
-                       if (pos < max_steps && oi != -1) { ++n_valid; lastv = pos + 1; }
-                     });
-      } else {
-        // irregular cumulative sums: count with the reference's serial machine
-        CdfState st;
-        st.curr_bin = 0; st.s = 0; st.curr_step = 0;
-        st.curr_min_depth = s_min[0]; st.curr_max_depth = s_max[0];
-        st.curr_min_cdf = 0.0f; st.curr_max_cdf = probs[H];
-        st.step_size = r.step_size; st.z_low = st.curr_min_depth; st.total_steps = r.total_steps;
-        st.curr_cdf = 0.0f; st.phase = 0;
-        int pos = 0;
-        while (pos < max_steps && st.phase != 3) {
-          int oi; float od, oz;
-          if (cdf_next(st, P, max_steps, H, next_idx0, pts_idx, row0_idx, min_depth, max_depth, probs, noise_row,
-                       noise_const, oi, od, oz)) {
-            if (oi != -1) { ++n_valid; lastv = pos + 1; }
-            ++pos;
-          }
-        }
-        atomicAdd(meta + 2, 1);
-      }
-      ray_len[ray] = lastv;
-      quirk[ray] = make_int2(next_idx0, r.ok ? row0_nb : -1 - row0_nb);     // negative (-1 - row0_nb) marks a fallback ray
-      if (n_valid != lastv) atomicOr(meta + 1, 1);
+    const float sj = steps[ray];
+    const float step_size = fixed_step_size > 0.0f ? fixed_step_size : __fdiv_rn(1.0f, sj);
+    const int total_steps = min((int)ceilf(sj), max_steps);
+    // pass 1: the reference's left-to-right cumulative sum; non-negative terms => non-decreasing, finite iff the last is
+    float cum_last = probs[H];
+    bool neg = !(cum_last >= 0.0f);
+    for (int j = 1; j < nb; ++j) {
+      const float pr = probs[H + j];
+      neg |= !(pr >= 0.0f);
+      cum_last = __fadd_rn(cum_last, pr);
     }
-    lastv = __shfl_sync(NSVF_FULL_MASK, lastv, 0);
-    my_max = max(my_max, lastv);
-    __syncwarp();
+    const bool ok = !neg && fabsf(cum_last) <= 3.0e38f;
+    int n_valid = 0;
+    if (ok) {
+      // the main loop stops at the first step whose cdf lies beyond the last cumulative sum
+      int n_in = total_steps, done = 0;
+      if (total_steps > 0 && cdf_at(total_steps - 1, noise_row, noise_const, max_steps, step_size) > cum_last) {
+        int lo = 0, hi = total_steps - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (cdf_at(mid, noise_row, noise_const, max_steps, step_size) > cum_last) hi = mid; else lo = mid + 1;
+        }
+        n_in = lo;
+        done = 1;
+      }
+      // pass 2: bin and depth of the last step of the main loop
+      int b_prev = -1;
+      float z_prev = 0.f;
+      if (n_in > 0) {
+        const float cl = cdf_at(n_in - 1, noise_row, noise_const, max_steps, step_size);
+        float cmin = 0.0f, cmax = probs[H];
+        int j = 0;
+        while (j < nb - 1 && cl > cmax) {
+          cmin = cmax;
+          ++j;
+          cmax = __fadd_rn(cmax, probs[H + j]);
+        }
+        if (cl > cmax) j = nb;      // cannot happen for an in-range step; mirrors lower_bound's "none"
+        b_prev = j;
+        if (j < nb) {
+          const float u = __fdiv_rn(__fsub_rn(cl, cmin), __fsub_rn(cmax, cmin));
+          const float lo_d = min_depth[H + j];
+          z_prev = __fmaf_rn(u, __fsub_rn(max_depth[H + j], lo_d), lo_d);
+        }
+      }
+      const int b_last = done ? nb : (n_in > 0 ? b_prev : 0);
+      // step samples and bin ends of the main loop: positions [0, n_in + b_last), all with a valid voxel id
+      lastv = n_valid = min(n_in + b_last, max_steps);
+      // the reference's trailing loop (sample_gpu.cu:187-200) from the state the main loop leaves
+      int curr_bin, sidx = n_in + b_last;
+      float curr_max, zl;
+      if (done) {
+        curr_bin = nb;
+        curr_max = max_depth[H + nb - 1];
+        zl = b_prev == nb - 1 ? z_prev : min_depth[H + nb - 1];
+      } else {
+        curr_bin = b_last;
+        curr_max = max_depth[H + curr_bin];
+        zl = n_in > 0 ? z_prev : min_depth[H];
+      }
+      while (zl < curr_max) {
+        const int oi = curr_bin < P ? pts_idx[H + curr_bin] : next_idx0;
+        if (sidx < max_steps && oi != -1) { ++n_valid; lastv = sidx + 1; }
+        ++curr_bin;
+        ++sidx;
+        if (curr_bin >= P || curr_bin >= row0_nb) break;
+        curr_max = max_depth[H + curr_bin];
+        zl = min_depth[H + curr_bin];
+      }
+    } else {
+      // irregular cumulative sums: count with the reference's serial machine
+      CdfState st;
+      st.curr_bin = 0; st.s = 0; st.curr_step = 0;
+      st.curr_min_depth = min_depth[H]; st.curr_max_depth = max_depth[H];
+      st.curr_min_cdf = 0.0f; st.curr_max_cdf = probs[H];
+      st.step_size = step_size; st.z_low = st.curr_min_depth; st.total_steps = total_steps;
+      st.curr_cdf = 0.0f; st.phase = 0;
+      int pos = 0;
+      while (pos < max_steps && st.phase != 3) {
+        int oi; float od, oz;
+        if (cdf_next(st, P, max_steps, H, next_idx0, pts_idx, row0_idx, min_depth, max_depth, probs, noise_row,
+                     noise_const, oi, od, oz)) {
+          if (oi != -1) { ++n_valid; lastv = pos + 1; }
+          ++pos;
+        }
+      }
+      atomicAdd(meta + 2, 1);
+    }
+    ray_len[ray] = lastv;
+    quirk[ray] = make_int2(next_idx0, ok ? row0_nb : -1 - row0_nb);     // negative (-1 - row0_nb) marks a fallback ray
+    if (n_valid != lastv) atomicOr(meta + 1, 1);
   }
-  if (lane == 0 && my_max > 0) atomicMax(meta, my_max);
+  const int warp_max = __reduce_max_sync(NSVF_FULL_MASK, lastv);
+  if ((threadIdx.x & 31) == 0 && warp_max > 0) atomicMax(meta, warp_max);
 }
 
 // Samples of positions [k0, k1) of the live rays -> planes idxT / depthT / distsT [K][ldb].
@@ -1192,12 +1253,9 @@ extern "C" int nsvf_inverse_cdf_plan(nsvf_stream_t stream_, int b, int num_rays,
   if (valid_rays < 0 || valid_rays > total_rays) valid_rays = total_rays;
   if (ray_chunk <= 0 || ray_chunk > num_rays) ray_chunk = num_rays;
   if (valid_rays == 0) return 0;
-  const size_t smem = (size_t)kCdfWarps * 4 * max_hits * sizeof(float);
-  NSVF_REQUIRE(smem <= 160 * 1024, "inverse_cdf_plan: max_hits=%d too large", max_hits);
-  NSVF_CUDA_OK(cudaFuncSetAttribute(inverse_cdf_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  long long want = (valid_rays + kCdfWarps - 1) / kCdfWarps, cap = (long long)num_sms() * 12;
   NSVF_TIMED_LAUNCH("inverse_cdf_plan_kernel", stream,
-                    (inverse_cdf_plan_kernel<<<(int)(want < cap ? want : cap), kCdfWarps * 32, smem, stream>>>(
+                    (inverse_cdf_plan_kernel<<<(unsigned)((valid_rays + kPlanThreads - 1) / kPlanThreads), kPlanThreads, 0,
+                                               stream>>>(
                         b, num_rays, valid_rays, ray_chunk, max_hits, max_steps, fixed_step_size, pts_idx, min_depth,
                         max_depth, uniform_noise, noise_const, probs, steps, ray_len, reinterpret_cast<int2*>(quirk),
                         meta)));

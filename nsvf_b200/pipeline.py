@@ -87,7 +87,10 @@ class NSVFPipeline(nn.Module):
         else:
             ray_start, ray_dir, inter, hits = self.encoder.ray_intersect(ray_start, ray_dir, encoder_states)
         min_depth, max_depth, pts_idx = inter["min_depth"], inter["max_depth"], inter["intersected_voxel_idx"]
-        dists = (max_depth - min_depth).masked_fill(pts_idx.eq(-1), 0)        # nsvf.py:65-74
+        # nsvf.py:65-74: dists = (max_depth - min_depth).masked_fill(pts_idx.eq(-1), 0).  Our ray_intersect fills the
+        # unused slots with the SAME depth (MAX_DEPTH) in both tensors, so their difference is already +0: the eq() and
+        # masked_fill passes over [rays, max_hits] would change nothing
+        dists = max_depth - min_depth
         inter["probs"] = dists / dists.sum(dim=-1, keepdim=True)
         inter["steps"] = dists.sum(-1) / self.encoder.step_size
         return ray_start, ray_dir, inter, hits, sampled
