@@ -312,8 +312,8 @@ NSVF_API int nsvf_composite_bwd(nsvf_stream_t stream, long long B, int K, const 
  *   nsvf_march_compact     : compacts the samples of window [start, end) of the live rays in row-major order (the
  *                            order boolean indexing produces): out_vox i32 [M], out_xyz f32 [M,3] = ray_start +
  *                            ray_dir * depth, out_dir f32 [M,3], out_dists f32 [M] (either optional), and
- *                            ray_off i32 [B+1] = exclusive offsets of the rays in that order.  launch_no = number of
- *                            earlier nsvf_march_compact launches on this plan (0, 1, 2, ...).  start = -1: the window
+ *                            ray_off i32 [B+1] = exclusive offsets of the rays in that order.  launch_no: ignored
+ *                            (kept for callers of the first-generation scan; pass 0).  start = -1: the window
  *                            is the one the preceding nsvf_march_epilogue (schedule_next) left in the plan, so the
  *                            launch can be queued BEFORE the host has read that window back; the outputs must then
  *                            hold max(chunk_size, B) rows (nothing is written if the schedule is finished).

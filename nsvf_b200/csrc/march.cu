@@ -18,8 +18,11 @@
 //     epilogue kernel integrates the differences and picks the next window (same rule as renderer.py:157-158), so
 //     one launch does scatter + early-stop + scheduling; the host reads 4 ints per window (or, without early
 //     termination, the whole window list once);
-//   * compaction is a single-pass kernel: per-ray counts are pure arithmetic on (len_r, window, alive), tile offsets
-//     come from a decoupled look-back scan (ticketed tiles, epoch-tagged 64-bit states: no reset between launches).
+//   * compaction: per-ray counts are pure arithmetic on (len_r, window, alive).  A first tiny kernel leaves the sample
+//     count of every 256-ray tile in the plan, the second one sums the counts of the tiles before its own (at most a
+//     few thousand L2-resident ints) and writes its samples — two short launches with no dependence between CTAs.  The
+//     first generation did it in one pass with a decoupled look-back over ticketed tiles: 30 us per window on 2048
+//     tiles, most of it the ticket counter and the prefix wave travelling down the chain.
 //
 // Precondition of this path: the valid samples of every ray form a prefix of its row (true for both samplers; the
 // sampler reports rows where it is not, nsvf_march_ray_lengths checks foreign inputs) — otherwise the caller uses
@@ -30,13 +33,14 @@
 namespace nsvf {
 
 // plan layout (int32 words, device memory, zero-initialised by the caller once per forward_chunk):
-//   [0..15]            header: 0 start, 1 end, 2 count, 3 done, 4 holes, 5 n_windows, 6 ticket, 7 ctas_done,
+//   [0..15]            header: 0 start, 1 end, 2 count, 3 done, 4 holes, 5 n_windows, 6 carry (sum of the pending differences before `start`), 7 ctas_done,
 //                              8 total_samples
 //   [16 .. 16+K)       counts[k]  = live rays with a valid sample in column k
 //   [16+K .. 16+2K+1)  diff[k]    = pending difference array for counts (prefix-summed from the window start)
-//   then (8-byte aligned) tile_state[n_tiles] u64 for the look-back scan
+//   then (8-byte aligned) tile_total[n_tiles] i32: samples of every 256-ray tile in the window being compacted
+//   (8 bytes reserved per tile)
 constexpr int kHdr = 16;
-constexpr int H_START = 0, H_END = 1, H_COUNT = 2, H_DONE = 3, H_HOLES = 4, H_NWIN = 5, H_TICKET = 6, H_CTAS = 7,
+constexpr int H_START = 0, H_END = 1, H_COUNT = 2, H_DONE = 3, H_HOLES = 4, H_NWIN = 5, H_CARRY = 6, H_CTAS = 7,
               H_TOTAL = 8;
 constexpr int kTile = 256;        // rays per compaction tile
 
@@ -115,9 +119,41 @@ __device__ void publish_schedule(int* plan, int K, int chunk_size, int from, boo
   int* diff = plan + kHdr + K;
   int end, count;
   if (!all_windows) {
-    select_window(counts, diff, K, from, chunk_size, integrate, end, count);
+    // One window at a time (early termination): the pending differences are NOT integrated over all K columns per
+    // window (22 dependent rounds of global loads and stores by a single warp at K = 700: half of the epilogue
+    // kernel's time).  Windows only move forward and every new difference lands at or behind the current window's
+    // end, so it is enough to carry the running sum of the differences in front of `from` in the header and to add
+    // the differences of the few columns the window selection actually looks at; counts[] / diff[] stay read-only.
+    int run = plan[H_CARRY], total = 0;
+    bool found = false;
+    end = K;
+    count = 0;
+    for (int k0 = from; k0 < K && !found; k0 += 32) {
+      const int k = k0 + lane;
+      const int d = k < K ? diff[k] : 0;
+      const int incl_d = warp_incl_sum_i(d, lane);
+      const int c = k < K ? counts[k] + run + incl_d : 0;       // live samples in column k
+      const int incl = warp_incl_sum_i(c, lane) + total;
+      const bool over = (k < K) && (k > from) && (incl > chunk_size);
+      const unsigned m = __ballot_sync(NSVF_FULL_MASK, over);
+      if (m) {
+        const int first = __ffs(m) - 1;
+        end = k0 + first;
+        const int prev = __shfl_sync(NSVF_FULL_MASK, incl, first > 0 ? first - 1 : 0);
+        const int prev_d = __shfl_sync(NSVF_FULL_MASK, incl_d, first > 0 ? first - 1 : 0);
+        count = first > 0 ? prev : total;
+        run += first > 0 ? prev_d : 0;                             // differences of the columns [from, end)
+        found = true;
+      } else {
+        total = __shfl_sync(NSVF_FULL_MASK, incl, 31);
+        run += __shfl_sync(NSVF_FULL_MASK, incl_d, 31);
+      }
+    }
+    if (!found) count = total;
+    (void)integrate;
     const int done = (from >= K || count == 0) ? 1 : 0;
     if (lane == 0) {
+      plan[H_CARRY] = run;
       plan[H_START] = from; plan[H_END] = end; plan[H_COUNT] = count; plan[H_DONE] = done;
       if (host_info != nullptr) {
         host_info[H_START] = from; host_info[H_END] = end; host_info[H_COUNT] = count; host_info[H_DONE] = done;
@@ -292,84 +328,81 @@ __device__ __forceinline__ int window_samples(int len, int start, int end) {
   return hi > start ? hi - start : 0;
 }
 
+// The window of a launch queued ahead of its read-back (start < 0) lives in the plan header: ONE thread per CTA reads it.
+__device__ __forceinline__ void resolve_window(const int* __restrict__ plan, int& start, int& end) {
+  __shared__ int sh_window[2];
+  if (start >= 0) return;          // uniform across the CTA (kernel argument)
+  if (threadIdx.x == 0) {
+    const int s0 = __ldcg(plan + H_START);
+    sh_window[0] = s0;
+    sh_window[1] = __ldcg(plan + H_DONE) ? s0 : __ldcg(plan + H_END);
+  }
+  __syncthreads();
+  start = sh_window[0];
+  end = sh_window[1];
+}
+
+__device__ __forceinline__ int block_sum(int x) {      // sum over the CTA (kTile threads), result in every thread
+  __shared__ int sh_part[kTile / 32], sh_sum;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int w = __reduce_add_sync(NSVF_FULL_MASK, x);
+  if (lane == 0) sh_part[warp] = w;
+  __syncthreads();
+  if (warp == 0) {
+    const int t = __reduce_add_sync(NSVF_FULL_MASK, lane < kTile / 32 ? sh_part[lane] : 0);
+    if (lane == 0) sh_sum = t;
+  }
+  __syncthreads();
+  return sh_sum;
+}
+
+// pass 1: samples of every 256-ray tile in the window
+__global__ void __launch_bounds__(kTile)
+march_count_kernel(long long B, int start, int end, const int* __restrict__ lens,
+                   const unsigned char* __restrict__ early_stop, const int* __restrict__ plan,
+                   int* __restrict__ tile_total) {
+  resolve_window(plan, start, end);
+  const long long ray = (long long)blockIdx.x * kTile + threadIdx.x;
+  int n = 0;
+  if (ray < B && (early_stop == nullptr || early_stop[ray] == 0)) n = window_samples(lens[ray], start, end);
+  const int total = block_sum(n);
+  if (threadIdx.x == 0) tile_total[blockIdx.x] = total;
+}
+
+// pass 2: offsets and samples
 __global__ void __launch_bounds__(kTile)
 march_compact_kernel(long long B, long long ldb, int K, int start, int end, const int* __restrict__ lens,
                      const unsigned char* __restrict__ early_stop, const int* __restrict__ idxT,
                      const float* __restrict__ depthT, const float* __restrict__ distsT,
                      const float* __restrict__ ray_start, const float* __restrict__ ray_dir,
                      int* __restrict__ out_vox, float* __restrict__ out_xyz, float* __restrict__ out_dir,
-                     float* __restrict__ out_dists, int* __restrict__ ray_off, int* __restrict__ plan,
-                     unsigned long long* __restrict__ tile_state, unsigned epoch, unsigned ticket_base) {
-  __shared__ unsigned sh_tile, sh_base;
-  __shared__ int sh_warp[kTile / 32], sh_total;
+                     float* __restrict__ out_dists, int* __restrict__ ray_off, const int* __restrict__ plan,
+                     const int* __restrict__ tile_total) {
+  __shared__ int sh_warp[kTile / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __shared__ int sh_start, sh_end;
-  if (tid == 0) {
-    sh_tile = atomicAdd(reinterpret_cast<unsigned*>(plan + H_TICKET), 1u) - ticket_base;
-    if (start < 0) {   // the window the previous epilogue scheduled: launched before the host has read it back.  ONE
-                       // thread per CTA reads it — the header shares its cache line with the ticket counter, and a
-                       // load per thread (320 k of them) doubled this kernel's time by queueing behind the atomics
-      const int s0 = __ldcg(plan + H_START);
-      sh_start = s0;
-      sh_end = __ldcg(plan + H_DONE) ? s0 : __ldcg(plan + H_END);
-    }
-  }
-  __syncthreads();
-  if (start < 0) { start = sh_start; end = sh_end; }
-  const unsigned tile = sh_tile;
-  const long long ray = (long long)tile * kTile + tid;
+  resolve_window(plan, start, end);
+  const long long ray = (long long)blockIdx.x * kTile + tid;
   int n = 0;
   if (ray < B && (early_stop == nullptr || early_stop[ray] == 0)) n = window_samples(lens[ray], start, end);
-  // the first column's loads do not depend on the offsets: issue them before the scan / look-back
+  // the first column's loads do not depend on the offsets: issue them before the sums
   int v0 = 0;
   float d0 = 0.f, s0 = 0.f;
   if (n > 0) {
     const long long a = (long long)start * ldb + ray;
     v0 = idxT[a]; d0 = depthT[a]; s0 = distsT[a];
   }
-  // block-wide exclusive scan of n
+  // samples of all tiles before this one
+  int part = 0;
+  for (int i = tid; i < (int)blockIdx.x; i += kTile) part += __ldcg(tile_total + i);
+  const int base = block_sum(part);
+  // exclusive scan of n inside the tile
   const int incl = warp_incl_sum_i(n, lane);
   if (lane == 31) sh_warp[warp] = incl;
   __syncthreads();
-  if (warp == 0) {
-    const int w = lane < kTile / 32 ? sh_warp[lane] : 0;
-    const int wi = warp_incl_sum_i(w, lane);
-    if (lane < kTile / 32) sh_warp[lane] = wi - w;          // exclusive warp bases
-    if (lane == kTile / 32 - 1) sh_total = wi;
-  }
-  __syncthreads();
-  const int tile_total = sh_total;
-  const int excl = incl - n + sh_warp[warp];
-  // decoupled look-back by warp 0: state = (epoch*4 + flag) << 32 | value, flag 1 = aggregate, 2 = inclusive prefix
-  if (warp == 0) {
-    const unsigned long long tag = (unsigned long long)epoch << 34;
-    unsigned base = 0;
-    if (tile == 0) {
-      if (lane == 0) atomicExch(tile_state + tile, tag | (2ull << 32) | (unsigned)tile_total);
-    } else {
-      if (lane == 0) atomicExch(tile_state + tile, tag | (1ull << 32) | (unsigned)tile_total);
-      long long p = (long long)tile - 1;      // lane l inspects tile p - l
-      while (true) {
-        const long long q = p - lane;
-        unsigned long long st = tag | (2ull << 32);         // tiles before 0: inclusive prefix 0
-        if (q >= 0) st = *reinterpret_cast<volatile unsigned long long*>(tile_state + q);
-        const bool ready = (st >> 34) == epoch;
-        if (!__all_sync(NSVF_FULL_MASK, ready)) continue;
-        const unsigned incl_mask = __ballot_sync(NSVF_FULL_MASK, ((st >> 32) & 3ull) == 2ull);
-        const int stop = incl_mask ? __ffs(incl_mask) - 1 : 31;    // nearest tile that already knows its prefix
-        unsigned v = lane <= stop ? (unsigned)(st & 0xffffffffull) : 0u;
+  int wbase = 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NSVF_FULL_MASK, v, o);
-        base += v;
-        if (incl_mask) break;
-        p -= 32;
-      }
-      if (lane == 0) atomicExch(tile_state + tile, tag | (2ull << 32) | (unsigned)(base + tile_total));
-    }
-    if (lane == 0) sh_base = base;
-  }
-  __syncthreads();
-  const int off = (int)sh_base + excl;
+  for (int w = 0; w < kTile / 32; ++w) wbase += w < warp ? sh_warp[w] : 0;
+  const int off = base + wbase + incl - n;
   if (ray < B) ray_off[ray] = off;
   if (ray == B - 1) ray_off[B] = off + n;
   if (n > 0) {
@@ -409,6 +442,11 @@ march_epilogue_kernel(long long B, long long ldb, int K, int start, int end, con
                       volatile int* host_info) {
   const int tid = threadIdx.x;
   int* diff = plan + kHdr + K;
+  // every ray that stops in this window takes one live sample off the columns [end, len): the -1's all land on
+  // diff[end] — thousands of atomics on ONE address per window when done per ray — so they are summed per CTA first
+  __shared__ int sh_stopped;
+  if (tid == 0) sh_stopped = 0;
+  __syncthreads();
   for (long long ray = (long long)blockIdx.x * kTile + tid; ray < B; ray += (long long)gridDim.x * kTile) {
     const int o0 = ray_off[ray], n = ray_off[ray + 1] - o0;
     if (n == 0) continue;
@@ -434,10 +472,12 @@ march_epilogue_kernel(long long B, long long ldb, int K, int start, int end, con
       if (acc > tolerance) {
         early_stop[ray] = 1;
         const int len = lens[ray];
-        if (len > end) { atomicSub(diff + end, 1); atomicAdd(diff + len, 1); }
+        if (len > end) { atomicAdd(&sh_stopped, 1); atomicAdd(diff + len, 1); }
       }
     }
   }
+  __syncthreads();
+  if (tid == 0 && sh_stopped != 0) atomicSub(diff + end, sh_stopped);
   if (schedule_next && last_cta(plan) && tid < 32)
     publish_schedule(plan, K, chunk_size, end, true, false, host_info, 0);
 }
@@ -655,15 +695,17 @@ extern "C" int nsvf_march_compact(nsvf_stream_t stream_, long long B, int K, int
   NSVF_REQUIRE(B >= 0 && K >= 0 && (start == -1 || (start >= 0 && start <= end && end <= K)) && launch_no >= 0,
                "march_compact: bad sizes");
   if (B == 0) return 0;
+  (void)launch_no;   // (the first-generation single-pass scan tagged its tile states with the launch number)
   const long long tiles = plan_tiles(B);
-  NSVF_REQUIRE(tiles * ((long long)launch_no + 1) < 0xffffffffll, "march_compact: ticket counter would overflow");
-  unsigned long long* tile_state =
-      reinterpret_cast<unsigned long long*>((int*)plan + plan_words_before_tiles(K));
-  NSVF_TIMED_LAUNCH("march_compact_kernel", stream,
-                    (march_compact_kernel<<<(unsigned)tiles, kTile, 0, stream>>>(
-                        B, plane_stride(B), K, start, end, lens, early_stop, idxT, depthT, distsT, ray_start, ray_dir, out_vox, out_xyz,
-                        out_dir, out_dists, ray_off, (int*)plan, tile_state, (unsigned)launch_no + 1u,
-                        (unsigned)(tiles * launch_no))));
+  int* tile_total = (int*)plan + plan_words_before_tiles(K);
+  profile_mark("march_compact_kernel", 0, stream);      // the two passes are timed as one unit
+  march_count_kernel<<<(unsigned)tiles, kTile, 0, stream>>>(B, start, end, lens, early_stop, (const int*)plan, tile_total);
+  NSVF_LAUNCH_OK("march_count_kernel");
+  march_compact_kernel<<<(unsigned)tiles, kTile, 0, stream>>>(
+      B, plane_stride(B), K, start, end, lens, early_stop, idxT, depthT, distsT, ray_start, ray_dir, out_vox, out_xyz, out_dir,
+      out_dists, ray_off, (const int*)plan, tile_total);
+  profile_mark("march_compact_kernel", 1, stream);
+  NSVF_LAUNCH_OK("march_compact_kernel");
   return 0;
 }
 
