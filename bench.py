@@ -47,11 +47,11 @@ import torch
 
 VIEWS, RES, PIX_PER_VIEW = 4, 800, 2048
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the frame's kernels, `ncu --set full` on the C3 hot-path frame
-# (profiles/r2_ncu_c3_frame.md; same scene, camera and chunking as frame_bench below)
+# (profiles/r2_ncu_c3_frame.md and r2_ncu_c3_frame_final.md; same scene, camera and chunking as frame_bench below)
 NCU_TRAFFIC = {"inverse_cdf_sampling_kernel": 7.305e9, "march_composite_fwd_kernel": 0.983e9,
-               "march_compact_kernel": 21.5e6, "trilinear_fwd_kernel": 19.7e6, "march_epilogue_kernel": 14.7e6,
-               "aabb_intersect_sorted_kernel": None, "march_transpose_kernel": None, "inverse_cdf_plan_kernel": None,
-               "inverse_cdf_stream_kernel": None}
+               "march_compact_kernel": 21.8e6, "trilinear_fwd_kernel": 18.7e6, "march_epilogue_kernel": 14.7e6,
+               "aabb_intersect_sorted_kernel": 2.139e9, "march_transpose_kernel": None, "inverse_cdf_plan_kernel": 0.840e9,
+               "inverse_cdf_stream_kernel": 0.165e9}   # stream: 2.31 GB over the frame's 14 launches (the first one 1.83 GB)
 LN_BWD_DRAM_TRAFFIC = 149.0e6  # bytes per launch: dram read 135 MB + write 14 MB, ncu --set full, [65536, 256] (profiles/r1b_ncu_ln_relu.md)
 METRIC = "rays/s (intersect+sample+composite), nsvf_base training step"
 
